@@ -1,0 +1,142 @@
+"""Synthetic grid-cloth scenes: the inputs the reference demos build in their main() functions.
+
+These mirror the *caller contract* of the hot path (mesh, hinge quads, sparsity pattern, vertex adjacency,
+constants), not the hot path itself:
+
+* ``square_cloth_xz``  -- SetClothShape_Square of self_contact_sparse/main.cpp:31-106 (cloth in the y=0 plane)
+* ``square_cloth_xy``  -- SetClothShape_Square of internal_cloth_sparse/main.cpp:31-103 (z=0 plane, row ix=0 pinned)
+* ``pattern_from_elems`` -- CJaggedArray::SetEdgeOfElem(+Sort) as used at self_contact_sparse/main.cpp:575-580
+* ``SELF_CONTACT`` / ``INTERNAL_CLOTH`` -- the compile-time constants of the two demos (main.cpp:138-156 / 137-154)
+
+A scene is a plain dict of contiguous numpy arrays (int32 / float64), consumed by the ctypes bindings.
+"""
+import numpy as np
+
+
+def _grid_topology(ndiv_x, ndiv_z):
+    """Triangles and hinge quads of an (ndiv_x+1) x (ndiv_z+1) vertex grid, vertex id = ix*(ndiv_z+1)+iz."""
+    nz1 = ndiv_z + 1
+    ix, iz = np.meshgrid(np.arange(ndiv_x), np.arange(ndiv_z), indexing="ij")
+    ix = ix.ravel()
+    iz = iz.ravel()
+    v00 = ix * nz1 + iz
+    v10 = (ix + 1) * nz1 + iz
+    v01 = ix * nz1 + iz + 1
+    v11 = (ix + 1) * nz1 + iz + 1
+    # two triangles per cell, in cell order
+    tri = np.stack([v00, v10, v01, v11, v01, v10], axis=1).reshape(-1, 3)
+    # hinge across the cell diagonal
+    q0 = np.stack([v00, v11, v10, v01], axis=1)
+    # hinge across the edge shared with the next cell in z
+    ix, iz = np.meshgrid(np.arange(ndiv_x), np.arange(ndiv_z - 1), indexing="ij")
+    ix = ix.ravel()
+    iz = iz.ravel()
+    q1 = np.stack([(ix + 1) * nz1 + iz, ix * nz1 + iz + 2, (ix + 1) * nz1 + iz + 1, ix * nz1 + iz + 1], axis=1)
+    # hinge across the edge shared with the next cell in x
+    ix, iz = np.meshgrid(np.arange(ndiv_x - 1), np.arange(ndiv_z), indexing="ij")
+    ix = ix.ravel()
+    iz = iz.ravel()
+    q2 = np.stack([ix * nz1 + iz + 1, (ix + 2) * nz1 + iz, (ix + 1) * nz1 + iz, (ix + 1) * nz1 + iz + 1], axis=1)
+    quad = np.concatenate([q0, q1, q2], axis=0)
+    return np.ascontiguousarray(tri, dtype=np.int32), np.ascontiguousarray(quad, dtype=np.int32)
+
+
+def pattern_from_elems(elem, nnode):
+    """Vertex->vertex adjacency (no self) from elements, ascending per row: (index[nnode+1], array[nnz])."""
+    elem = np.asarray(elem)
+    n = elem.shape[1]
+    rows = np.repeat(elem, n, axis=1).ravel()
+    cols = np.tile(elem, (1, n)).ravel()
+    keep = rows != cols
+    key = np.unique(rows[keep].astype(np.int64) * nnode + cols[keep].astype(np.int64))
+    r = (key // nnode).astype(np.int32)
+    c = (key % nnode).astype(np.int32)
+    index = np.zeros(nnode + 1, dtype=np.int32)
+    np.add.at(index, r + 1, 1)
+    index = np.cumsum(index, dtype=np.int64).astype(np.int32)
+    return index, np.ascontiguousarray(c)
+
+
+def _finish(xyz0, bc, tri, quad, total_area, areal_density):
+    np_ = xyz0.shape[0]
+    rowptr, colidx = pattern_from_elems(quad, np_)
+    eidx, earr = pattern_from_elems(tri, np_)
+    return {
+        "np": int(np_), "ntri": int(tri.shape[0]), "nquad": int(quad.shape[0]),
+        "xyz0": np.ascontiguousarray(xyz0, dtype=np.float64).ravel(),
+        "bc": np.ascontiguousarray(bc, dtype=np.int32),
+        "tri": tri.ravel(), "quad": quad.ravel(),
+        "rowptr": rowptr, "colidx": colidx,
+        "edge_index": eidx, "edge_array": earr,
+        "mass_point": total_area * areal_density / float(np_),
+        "bvh": None,
+    }
+
+
+def square_cloth_xz(ndiv_x, ndiv_z, h, areal_density=0.04):
+    """self_contact_sparse scene: vertices (ix*h, 0, iz*h), nothing pinned."""
+    tri, quad = _grid_topology(ndiv_x, ndiv_z)
+    ix, iz = np.meshgrid(np.arange(ndiv_x + 1), np.arange(ndiv_z + 1), indexing="ij")
+    xyz0 = np.stack([ix.ravel() * h, np.zeros(ix.size), iz.ravel() * h], axis=1)
+    bc = np.zeros(xyz0.shape[0], dtype=np.int32)
+    sc = _finish(xyz0, bc, tri, quad, (ndiv_x * h) * (ndiv_z * h), areal_density)
+    sc["ndiv"] = (ndiv_x, ndiv_z)
+    sc["h"] = h
+    return sc
+
+
+def square_cloth_xy(ndiv, cloth_size, areal_density=1.0):
+    """internal_cloth_sparse scene: vertices (ix*h, iy*h, 0) with h = cloth_size/ndiv, row ix=0 pinned."""
+    h = cloth_size / ndiv
+    tri, quad = _grid_topology(ndiv, ndiv)
+    ix, iy = np.meshgrid(np.arange(ndiv + 1), np.arange(ndiv + 1), indexing="ij")
+    xyz0 = np.stack([ix.ravel() * h, iy.ravel() * h, np.zeros(ix.size)], axis=1)
+    bc = np.zeros(xyz0.shape[0], dtype=np.int32)
+    bc[: ndiv + 1] = 1
+    sc = _finish(xyz0, bc, tri, quad, cloth_size * cloth_size, areal_density)
+    sc["ndiv"] = (ndiv, ndiv)
+    sc["h"] = h
+    return sc
+
+
+def jittered_rest(sc, amplitude_frac=0.2, seed=88172645463325252):
+    """Rest positions with a deterministic in-plane jitter (xorshift64), used only to feed a BVH *topology*
+    builder: the reference's own builder crashes on exactly-square grids."""
+    x = np.array(sc["xyz0"], dtype=np.float64).reshape(-1, 3).copy()
+    s = np.uint64(seed)
+    amp = amplitude_frac * sc["h"]
+    planar = [a for a in range(3) if np.ptp(x[:, a]) > 0]
+    m64 = (1 << 64) - 1
+    state = int(s)
+    out = np.empty((x.shape[0], len(planar)))
+    for i in range(x.shape[0]):
+        for k in range(len(planar)):
+            state ^= (state << 13) & m64
+            state ^= state >> 7
+            state ^= (state << 17) & m64
+            out[i, k] = (state >> 11) / float(1 << 53) * 2.0 - 1.0
+    for k, a in enumerate(planar):
+        x[:, a] += amp * out[:, k]
+    return x.ravel()
+
+
+# demo constants -------------------------------------------------------------------------------------------
+SELF_CONTACT = dict(dt=0.01, lam=0.0, myu=30.0, stiff_bend=1.0e-2, gravity=(0.0, 0.05, -10.0),
+                    stiff_contact=300.0, clearance=0.01, areal_density=0.04,
+                    col_kind=1, col_par=(-0.5, 0.0, 0.0, 0.0))
+INTERNAL_CLOTH = dict(dt=0.02, lam=1.0, myu=4.0, stiff_bend=1.0e-3, gravity=(0.0, 0.0, -10.0),
+                      stiff_contact=1.0e3, clearance=0.02, areal_density=1.0,
+                      col_kind=0, col_par=(0.0, 0.0, 0.0, 0.0))
+
+# collider kinds of the C-ABI (include/clothgpu.h)
+COLLIDER_NONE, COLLIDER_PLANE_Z, COLLIDER_SPHERE, COLLIDER_SPHERE_INSIDE = 0, 1, 2, 3
+
+
+def config1_default():
+    """self_contact_sparse default demo: 5 x 51 vertices (elem 0.1, 0.4 x 5.0)."""
+    return square_cloth_xz(4, 50, 0.1, SELF_CONTACT["areal_density"])
+
+
+def config3_256():
+    """256 x 256 vertices, h = 0.1, self_contact_sparse constants."""
+    return square_cloth_xz(255, 255, 0.1, SELF_CONTACT["areal_density"])
