@@ -1,0 +1,454 @@
+// csrc/bvh.cu -- BVH refit, dual-tree self traversal, narrow phase (proximity and CCD), canonical contact sets.
+//
+// Replaces BuildBoundingBoxChild_Prx / _CCD (bvh_aabb.cpp:23-61, 64-106), GetContactElement_Proximity / _CCD
+// (:441-557, 797-923) with their predicates (IsContact_*; dev_math.cuh) and the std::set<CContactElement>
+// container (bvh_aabb.h:65-106).
+//
+// Design (the reference recurses depth first on one core):
+//  * refit: one thread per leaf computes its box and climbs; the second arrival at a parent merges the two
+//    children (atomic ticket).  min/max only, so the result is order independent and bit-exact.
+//  * traversal: breadth first over a frontier of node pairs.  It starts from the (child0, child1) pair of EVERY
+//    internal node (the self() calls of bvh_aabb.cpp:540-557) and expands one tree level per launch; surviving pairs
+//    are pushed with warp-aggregated atomics.  The set of leaf pairs reached is the same as the depth-first walk's.
+//  * every frontier entry carries its position in the reference's depth-first order (preorder rank of the self()
+//    node + the child choices of the pair recursion, 2 bits per descent).  std::set keeps the FIRST inserted of two
+//    elements with equal keys and its comparison ignores is_fv (bvh_aabb.h:96-102), so when a face-vertex and an
+//    edge-edge element share a 4-tuple the winner depends on visiting order; sorting raw elements by
+//    (key, DFS rank) and keeping the first of each key reproduces that bit for bit.
+#include <cub/device/device_merge_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "ctx.h"
+#include "dev_math.cuh"
+
+namespace cg {
+
+// ------------------------------------------------------------------------------------------------ refit
+__device__ __forceinline__ void st_box(double* boxes, int i, const Box& b) {
+  double* p = boxes + (size_t)i * 6;
+  p[0] = b.lo[0]; p[1] = b.hi[0]; p[2] = b.lo[1]; p[3] = b.hi[1]; p[4] = b.lo[2]; p[5] = b.hi[2];
+}
+__device__ __forceinline__ Box ld_box_cg(const double* boxes, int i) {  // bypass L1: written by another SM
+  Box b;
+  const double* p = boxes + (size_t)i * 6;
+  b.lo[0] = __ldcg(p + 0); b.hi[0] = __ldcg(p + 1);
+  b.lo[1] = __ldcg(p + 2); b.hi[1] = __ldcg(p + 3);
+  b.lo[2] = __ldcg(p + 4); b.hi[2] = __ldcg(p + 5);
+  return b;
+}
+
+// mode 0: BuildBoundingBoxChild_Prx (leaf = 3 vertices padded by par/2); mode 1: _CCD (leaf = 3 vertices at x and
+// at x + par*v, padded by 1e-10).  Internal node = CAABB3D::operator+= of its children (aabb.h:55-72).
+__global__ void __launch_bounds__(256) k_refit(int nnode, int np, const int* __restrict__ nodes,
+                                                const int* __restrict__ tri, const double* __restrict__ xyz,
+                                                const double* __restrict__ uvw, double par, int mode, double* boxes,
+                                                int* flags, const int* __restrict__ cnt) {
+  const int s = blockIdx.y;
+  if (!cnt[s * NCNT + CNT_ACTIVE]) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nnode) return;
+  if (nodes[i * 3 + 2] != -1) return;
+  const double* x = xyz + (size_t)s * np * 3;
+  double* bx = boxes + (size_t)s * nnode * 6;
+  int* fl = flags + (size_t)s * nnode;
+  const int t = nodes[i * 3 + 1];
+  const int n0 = tri[t * 3 + 0], n1 = tri[t * 3 + 1], n2 = tri[t * 3 + 2];
+  Box b;
+  if (mode == 0) {
+    const double eps = par * 0.5;
+    box_init(b, ld3(x, n0), eps);
+    box_add(b, ld3(x, n1), eps);
+    box_add(b, ld3(x, n2), eps);
+  } else {
+    const double* v = uvw + (size_t)s * np * 3;
+    const double eps = 1.0e-10;
+    box_init(b, ld3(x, n0), eps);
+    box_add(b, ld3(x, n1), eps);
+    box_add(b, ld3(x, n2), eps);
+    box_add(b, v3(x[n0 * 3] + par * v[n0 * 3], x[n0 * 3 + 1] + par * v[n0 * 3 + 1], x[n0 * 3 + 2] + par * v[n0 * 3 + 2]), eps);
+    box_add(b, v3(x[n1 * 3] + par * v[n1 * 3], x[n1 * 3 + 1] + par * v[n1 * 3 + 1], x[n1 * 3 + 2] + par * v[n1 * 3 + 2]), eps);
+    box_add(b, v3(x[n2 * 3] + par * v[n2 * 3], x[n2 * 3 + 1] + par * v[n2 * 3 + 1], x[n2 * 3 + 2] + par * v[n2 * 3 + 2]), eps);
+  }
+  st_box(bx, i, b);
+  int cur = nodes[i * 3 + 0];
+  while (cur >= 0) {
+    __threadfence();
+    if (atomicAdd(&fl[cur], 1) == 0) return;  // the sibling subtree is not finished: its last thread continues
+    __threadfence();
+    Box a = ld_box_cg(bx, nodes[cur * 3 + 1]);
+    const Box o = ld_box_cg(bx, nodes[cur * 3 + 2]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      a.hi[k] = (a.hi[k] > o.hi[k]) ? a.hi[k] : o.hi[k];
+      a.lo[k] = (a.lo[k] < o.lo[k]) ? a.lo[k] : o.lo[k];
+    }
+    st_box(bx, cur, a);
+    cur = nodes[cur * 3 + 0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ traversal
+__global__ void k_trav_reset(int* cnt) {
+  int* c = cnt + blockIdx.x * NCNT;
+  for (int k = threadIdx.x; k < NCNT - CNT_FRONT; k += blockDim.x) c[CNT_FRONT + k] = 0;
+  if (threadIdx.x == 0) { c[CNT_LEAF] = 0; c[CNT_RAW] = 0; c[CNT_ELEM] = 0; c[CNT_OVERFLOW] = 0; }
+}
+
+// the self() calls: every internal node starts one pair recursion on its two children
+__global__ void k_trav_init(int ninternal, const int* __restrict__ internal_list, const int* __restrict__ nodes,
+                            const uint32_t* __restrict__ pre, PairEnt* front, long long cap, int* cnt) {
+  const int s = blockIdx.y;
+  if (!cnt[s * NCNT + CNT_ACTIVE]) return;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0) cnt[s * NCNT + CNT_FRONT] = ninternal;
+  if (k >= ninternal) return;
+  const int n = internal_list[k];
+  PairEnt e;
+  e.i0 = nodes[n * 3 + 1];
+  e.i1 = nodes[n * 3 + 2];
+  e.pre = pre[n];
+  e.depth = 0;
+  e.path_hi = 0;
+  e.path_lo = 0;
+  front[(size_t)s * cap + k] = e;
+}
+
+// reserve n (0..4) consecutive output slots for every lane of a fully converged warp with one atomic per warp
+__device__ __forceinline__ int warp_reserve(int n, int* counter) {
+  const unsigned lane = threadIdx.x & 31;
+  int incl = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (unsigned)o) incl += v;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  int base = 0;
+  if (lane == 31 && total > 0) base = atomicAdd(counter, total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  return base + incl - n;
+}
+
+__device__ __forceinline__ void path_push(PairEnt& e, unsigned code) {
+  if (e.depth < 32) e.path_hi |= (uint64_t)code << (62 - 2 * e.depth);
+  else e.path_lo |= (uint64_t)code << (62 - 2 * (e.depth - 32));
+  e.depth++;
+}
+
+// one level of the pair recursion (bvh_aabb.cpp:441-475 / 797-833): prune on CAABB3D::IsIntersect, descend in the
+// child order (0,0),(1,0),(0,1),(1,1), collect leaf pairs
+__global__ void __launch_bounds__(256) k_trav_step(int d, int nnode, const int* __restrict__ nodes,
+                                                    const double* __restrict__ boxes, const PairEnt* __restrict__ fin,
+                                                    PairEnt* __restrict__ fout, long long cap_front,
+                                                    PairEnt* __restrict__ leaf, long long cap_leaf, int* cnt) {
+  const int s = blockIdx.y;
+  int* c = cnt + s * NCNT;
+  if (!c[CNT_ACTIVE]) return;
+  const int nin = min(c[CNT_FRONT + d], (int)min(cap_front, (long long)INT_MAX));
+  if (nin == 0) return;
+  const double* bx = boxes + (size_t)s * nnode * 6;
+  const PairEnt* in = fin + (size_t)s * cap_front;
+  PairEnt* out = fout + (size_t)s * cap_front;
+  PairEnt* lf = leaf + (size_t)s * cap_leaf;
+  const int stride = gridDim.x * blockDim.x;
+  const int nround = (nin + stride - 1) / stride;
+  for (int rnd = 0; rnd < nround; rnd++) {
+    const int idx = rnd * stride + blockIdx.x * blockDim.x + threadIdx.x;
+    PairEnt e;
+    int nout = 0, isleaf = 0;
+    int c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+    bool l0 = false, l1 = false;
+    if (idx < nin) {
+      e = in[idx];
+      const Box b0 = ld_box(bx, e.i0), b1 = ld_box(bx, e.i1);
+      if (box_intersect(b0, b1)) {
+        c00 = nodes[e.i0 * 3 + 1]; c01 = nodes[e.i0 * 3 + 2];
+        c10 = nodes[e.i1 * 3 + 1]; c11 = nodes[e.i1 * 3 + 2];
+        l0 = c01 == -1; l1 = c11 == -1;
+        if (l0 && l1) isleaf = 1;
+        else if (!l0 && !l1) nout = 4;
+        else nout = 2;
+      }
+    }
+    const int base = warp_reserve(nout, &c[CNT_FRONT + d + 1]);
+    if (nout > 0) {
+      if ((long long)base + nout > cap_front) {
+        atomicOr(&c[CNT_OVERFLOW], 1);
+      } else {
+        const int i0 = e.i0, i1 = e.i1;
+        PairEnt ch = e;
+        path_push(ch, 0);  // depth + 1, code bits filled below
+        const int sh = (e.depth < 32) ? 62 - 2 * e.depth : 62 - 2 * (e.depth - 32);
+        uint64_t* pw = (e.depth < 32) ? &ch.path_hi : &ch.path_lo;
+        const uint64_t p0 = *pw;
+        if (nout == 4) {
+          ch.i0 = c00; ch.i1 = c10; *pw = p0;                      out[base + 0] = ch;
+          ch.i0 = c01; ch.i1 = c10; *pw = p0 | ((uint64_t)1 << sh); out[base + 1] = ch;
+          ch.i0 = c00; ch.i1 = c11; *pw = p0 | ((uint64_t)2 << sh); out[base + 2] = ch;
+          ch.i0 = c01; ch.i1 = c11; *pw = p0 | ((uint64_t)3 << sh); out[base + 3] = ch;
+        } else if (!l0) {
+          ch.i0 = c00; ch.i1 = i1; *pw = p0;                        out[base + 0] = ch;
+          ch.i0 = c01; ch.i1 = i1; *pw = p0 | ((uint64_t)1 << sh); out[base + 1] = ch;
+        } else {
+          ch.i0 = i0; ch.i1 = c10; *pw = p0;                        out[base + 0] = ch;
+          ch.i0 = i0; ch.i1 = c11; *pw = p0 | ((uint64_t)1 << sh); out[base + 1] = ch;
+        }
+      }
+    }
+    const int lbase = warp_reserve(isleaf, &c[CNT_LEAF]);
+    if (isleaf) {
+      if ((long long)lbase + 1 > cap_leaf) atomicOr(&c[CNT_OVERFLOW], 2);
+      else lf[lbase] = e;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ narrow phase
+// CContactElement's canonical ordering (bvh_aabb.h:67-95)
+__device__ __forceinline__ void canon_fv(int j0, int j1, int j2, int j3, int* n) {
+  int a = j0, b = j1, c = j2, t;
+  if (a > b) { t = a; a = b; b = t; }
+  if (b > c) { t = b; b = c; c = t; }
+  if (a > b) { t = a; a = b; b = t; }
+  n[0] = a; n[1] = b; n[2] = c; n[3] = j3;
+}
+__device__ __forceinline__ void canon_ee(int j0, int j1, int j2, int j3, int* n) {
+  int a0 = j0, a1 = j1, b0 = j2, b1 = j3, t;
+  const int mA = a0 < a1 ? a0 : a1, mB = b0 < b1 ? b0 : b1;
+  if (mB < mA) { t = a0; a0 = b0; b0 = t; t = a1; a1 = b1; b1 = t; }
+  if (a1 < a0) { t = a0; a0 = a1; a1 = t; }
+  if (b1 < b0) { t = b0; b0 = b1; b1 = t; }
+  n[0] = a0; n[1] = a1; n[2] = b0; n[3] = b1;
+}
+
+__device__ __forceinline__ void emit(const PairEnt& e, int slot, const int* key, RawElem* raw, long long cap_raw, int* c) {
+  const int k = atomicAdd(&c[CNT_RAW], 1);
+  if (k >= cap_raw) { atomicOr(&c[CNT_OVERFLOW], 4); return; }
+  RawElem r;
+  r.n[0] = key[0]; r.n[1] = key[1]; r.n[2] = key[2]; r.n[3] = key[3];
+  r.pre = e.pre; r.slot = (uint32_t)slot; r.path_hi = e.path_hi; r.path_lo = e.path_lo;
+  raw[k] = r;
+}
+
+// the 6 face-vertex + 9 edge-edge tests of every leaf pair (bvh_aabb.cpp:476-535 proximity, 834-900 CCD)
+__global__ void __launch_bounds__(128) k_narrow(int ccd, int nnode, int np, const int* __restrict__ nodes,
+                                                 const int* __restrict__ tri, const double* __restrict__ boxes,
+                                                 const double* __restrict__ xyz, const double* __restrict__ uvw,
+                                                 double dt, double delta, const PairEnt* __restrict__ leaf,
+                                                 long long cap_leaf, RawElem* __restrict__ raw, long long cap_raw,
+                                                 int* cnt) {
+  const int s = blockIdx.y;
+  int* c = cnt + s * NCNT;
+  if (!c[CNT_ACTIVE]) return;
+  const int nleaf = min(c[CNT_LEAF], (int)min(cap_leaf, (long long)INT_MAX));
+  const double* bx = boxes + (size_t)s * nnode * 6;
+  const double* x = xyz + (size_t)s * np * 3;
+  const double* v = ccd ? uvw + (size_t)s * np * 3 : nullptr;
+  const PairEnt* lf = leaf + (size_t)s * cap_leaf;
+  RawElem* rw = raw + (size_t)s * cap_raw;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nleaf; idx += gridDim.x * blockDim.x) {
+    const PairEnt e = lf[idx];
+    const int it = nodes[e.i0 * 3 + 1], jt = nodes[e.i1 * 3 + 1];
+    int in[3], jn[3];
+    V3 p[3], q[3], pe[3], qe[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      in[a] = tri[it * 3 + a]; jn[a] = tri[jt * 3 + a];
+      p[a] = ld3(x, in[a]); q[a] = ld3(x, jn[a]);
+    }
+    int key[4];
+    if (ccd) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        const int i = in[a], j = jn[a];
+        pe[a] = v3(x[i * 3] + dt * v[i * 3], x[i * 3 + 1] + dt * v[i * 3 + 1], x[i * 3 + 2] + dt * v[i * 3 + 2]);
+        qe[a] = v3(x[j * 3] + dt * v[j * 3], x[j * 3 + 1] + dt * v[j * 3 + 1], x[j * 3 + 2] + dt * v[j * 3 + 2]);
+      }
+      const Box b0 = ld_box(bx, e.i0), b1 = ld_box(bx, e.i1);
+#pragma unroll 1
+      for (int a = 0; a < 3; a++)
+        if (is_fv_ccd(in[0], in[1], in[2], jn[a], p[0], p[1], p[2], q[a], pe[0], pe[1], pe[2], qe[a], b0)) {
+          canon_fv(in[0], in[1], in[2], jn[a], key);
+          emit(e, a, key, rw, cap_raw, c);
+        }
+#pragma unroll 1
+      for (int a = 0; a < 3; a++)
+        if (is_fv_ccd(jn[0], jn[1], jn[2], in[a], q[0], q[1], q[2], p[a], qe[0], qe[1], qe[2], pe[a], b1)) {
+          canon_fv(jn[0], jn[1], jn[2], in[a], key);
+          emit(e, 3 + a, key, rw, cap_raw, c);
+        }
+#pragma unroll 1
+      for (int k = 0; k < 9; k++) {
+        const int a0 = k / 3, a1 = (a0 + 1) % 3, b0e = k - a0 * 3, b1e = (b0e + 1) % 3;
+        if (is_ee_ccd(in[a0], in[a1], jn[b0e], jn[b1e], p[a0], p[a1], q[b0e], q[b1e], pe[a0], pe[a1], qe[b0e], qe[b1e])) {
+          canon_ee(in[a0], in[a1], jn[b0e], jn[b1e], key);
+          emit(e, 6 + k, key, rw, cap_raw, c);
+        }
+      }
+    } else {
+      // reference quirk (bvh_aabb.cpp:490-505): the vertex is tested against the box of BVH node number
+      // <triangle index>, not against the box of the face's own leaf
+      const Box b0 = ld_box(bx, it), b1 = ld_box(bx, jt);
+#pragma unroll 1
+      for (int a = 0; a < 3; a++)
+        if (is_fv_prx(in[0], in[1], in[2], jn[a], p[0], p[1], p[2], q[a], b0, delta)) {
+          canon_fv(in[0], in[1], in[2], jn[a], key);
+          emit(e, a, key, rw, cap_raw, c);
+        }
+#pragma unroll 1
+      for (int a = 0; a < 3; a++)
+        if (is_fv_prx(jn[0], jn[1], jn[2], in[a], q[0], q[1], q[2], p[a], b1, delta)) {
+          canon_fv(jn[0], jn[1], jn[2], in[a], key);
+          emit(e, 3 + a, key, rw, cap_raw, c);
+        }
+#pragma unroll 1
+      for (int k = 0; k < 9; k++) {
+        const int a0 = k / 3, a1 = (a0 + 1) % 3, b0e = k - a0 * 3, b1e = (b0e + 1) % 3;
+        if (is_ee_prx(in[a0], in[a1], jn[b0e], jn[b1e], p[a0], p[a1], q[b0e], q[b1e], delta)) {
+          canon_ee(in[a0], in[a1], jn[b0e], jn[b1e], key);
+          emit(e, 6 + k, key, rw, cap_raw, c);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ canonical set
+struct RawLess {
+  __device__ __forceinline__ bool operator()(const RawElem& a, const RawElem& b) const {
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (a.n[k] != b.n[k]) return a.n[k] < b.n[k];
+    if (a.pre != b.pre) return a.pre < b.pre;
+    if (a.path_hi != b.path_hi) return a.path_hi < b.path_hi;
+    if (a.path_lo != b.path_lo) return a.path_lo < b.path_lo;
+    return a.slot < b.slot;
+  }
+};
+
+__global__ void k_mark_unique(int n, const RawElem* __restrict__ raw, int* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int f = 1;
+  if (i > 0) {
+    const RawElem& a = raw[i - 1];
+    const RawElem& b = raw[i];
+    f = (a.n[0] != b.n[0] || a.n[1] != b.n[1] || a.n[2] != b.n[2] || a.n[3] != b.n[3]) ? 1 : 0;
+  }
+  flag[i] = f;
+}
+__global__ void k_compact_elems(int n, const RawElem* __restrict__ raw, const int* __restrict__ flag,
+                                const int* __restrict__ pos, int* __restrict__ elems, long long cap_elem, int* cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (flag[i]) {
+    const int k = pos[i];
+    if (k < cap_elem) {
+      elems[k * 5 + 0] = raw[i].n[0]; elems[k * 5 + 1] = raw[i].n[1];
+      elems[k * 5 + 2] = raw[i].n[2]; elems[k * 5 + 3] = raw[i].n[3];
+      elems[k * 5 + 4] = raw[i].slot < 6 ? 1 : 0;
+    } else {
+      atomicOr(&cnt[CNT_OVERFLOW], 8);
+    }
+  }
+  if (i == n - 1) cnt[CNT_ELEM] = pos[i] + flag[i];
+}
+
+__global__ void k_set_active(int* cnt, int v) { cnt[blockIdx.x * NCNT + CNT_ACTIVE] = v; }
+
+int launch_refit(Ctx* c, const double* xyz, const double* uvw, double par, int mode) {
+  CG_CUDA(cudaMemsetAsync(c->refit_flag, 0, sizeof(int) * (size_t)c->B * c->nnode, c->stream));
+  dim3 g(div_up(c->nnode, 256), c->B);
+  k_refit<<<g, 256, 0, c->stream>>>(c->nnode, c->np, c->nodes, c->tri, xyz, uvw, par, mode, c->boxes, c->refit_flag, c->cnt);
+  CG_LAUNCH_CHECK(c);
+  return CLOTHGPU_OK;
+}
+
+static int traverse_and_test(Ctx* c, const double* xyz, const double* uvw, double dt, double delta, int ccd) {
+  k_trav_reset<<<c->B, 64, 0, c->stream>>>(c->cnt);
+  CG_LAUNCH_CHECK(c);
+  {
+    dim3 g(div_up(c->ninternal, 256), c->B);
+    k_trav_init<<<g, 256, 0, c->stream>>>(c->ninternal, c->internal_list, c->nodes, c->pre, c->frontA, c->cap_front, c->cnt);
+    CG_LAUNCH_CHECK(c);
+  }
+  // every descent moves at least one side of the pair one level down: bvh_height + 1 steps reach all leaf pairs
+  for (int d = 0; d <= c->bvh_height; d++) {
+    dim3 g(148 * 4, c->B);
+    PairEnt* fin = (d & 1) ? c->frontB : c->frontA;
+    PairEnt* fout = (d & 1) ? c->frontA : c->frontB;
+    k_trav_step<<<g, 256, 0, c->stream>>>(d, c->nnode, c->nodes, c->boxes, fin, fout, c->cap_front, c->leaf, c->cap_leaf, c->cnt);
+    CG_LAUNCH_CHECK(c);
+  }
+  {
+    dim3 g(148 * 8, c->B);
+    k_narrow<<<g, 128, 0, c->stream>>>(ccd, c->nnode, c->np, c->nodes, c->tri, c->boxes, xyz, uvw, dt, delta, c->leaf,
+                                       c->cap_leaf, c->raw, c->cap_raw, c->cnt);
+    CG_LAUNCH_CHECK(c);
+  }
+  return CLOTHGPU_OK;
+}
+
+// raw elements -> std::set order with first-insert-wins duplicates (per scene; counts come back to the host, which
+// needs them anyway for the loop control of self_collision_cloth.cpp:416,449)
+static int canonical_set(Ctx* c, int s, int nraw) {
+  int* cnt = c->cnt + s * NCNT;
+  if (nraw == 0) {
+    CG_CUDA(cudaMemsetAsync(cnt + CNT_ELEM, 0, sizeof(int), c->stream));
+    return CLOTHGPU_OK;
+  }
+  RawElem* raw = c->raw + (size_t)s * c->cap_raw;
+  size_t tb = 0, tb2 = 0;
+  CG_CUDA(cub::DeviceMergeSort::SortKeys(nullptr, tb, raw, nraw, RawLess(), c->stream));
+  CG_CHECK(ensure_sort_capacity(c, nraw));
+  int* flag = c->sort_vals;
+  int* pos = c->sort_vals2;
+  CG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, flag, pos, nraw, c->stream));
+  CG_CHECK(ensure_scratch(c, std::max(tb, tb2)));
+  CG_CUDA(cub::DeviceMergeSort::SortKeys(c->scratch, tb, raw, nraw, RawLess(), c->stream));
+  c->launches += 2;
+  k_mark_unique<<<div_up(nraw, 256), 256, 0, c->stream>>>(nraw, raw, flag);
+  CG_LAUNCH_CHECK(c);
+  CG_CUDA(cub::DeviceScan::ExclusiveSum(c->scratch, tb2, flag, pos, nraw, c->stream));
+  c->launches += 2;
+  k_compact_elems<<<div_up(nraw, 256), 256, 0, c->stream>>>(nraw, raw, flag, pos, c->elems + (size_t)s * c->cap_elem * 5,
+                                                            c->cap_elem, cnt);
+  CG_LAUNCH_CHECK(c);
+  return CLOTHGPU_OK;
+}
+
+// GetContactElement_Proximity / _CCD for the scenes whose CNT_ACTIVE flag is set; counts[B] out (0 for inactive)
+int run_contacts(Ctx* c, const double* xyz, const double* uvw, double dt, double delta, int ccd, int* counts) {
+  if (c->nnode == 0) { set_error("context has no BVH"); return CLOTHGPU_ERR_STATE; }
+  for (int attempt = 0;; attempt++) {
+    phase_begin(c);
+    CG_CHECK(traverse_and_test(c, xyz, uvw, dt, delta, ccd));
+    CG_CHECK(fetch_counters(c));
+    phase_end(c, 4);
+    int bits = 0;
+    for (int s = 0; s < c->B; s++) bits |= c->h_cnt[s * NCNT + CNT_OVERFLOW];
+    if (bits == 0) break;
+    if (attempt >= 12) { set_error("contact work queues keep overflowing"); return CLOTHGPU_ERR_CAPACITY; }
+    CG_CHECK(grow_queues(c, bits));
+  }
+  phase_begin(c);
+  for (int s = 0; s < c->B; s++) {
+    if (!c->h_cnt[s * NCNT + CNT_ACTIVE]) continue;
+    CG_CHECK(canonical_set(c, s, c->h_cnt[s * NCNT + CNT_RAW]));
+  }
+  CG_CHECK(fetch_counters(c));
+  phase_end(c, 5);
+  for (int s = 0; s < c->B; s++) {
+    if (c->h_cnt[s * NCNT + CNT_OVERFLOW] & 8) { set_error("contact element buffer overflow"); return CLOTHGPU_ERR_CAPACITY; }
+    if (counts) counts[s] = c->h_cnt[s * NCNT + CNT_ACTIVE] ? c->h_cnt[s * NCNT + CNT_ELEM] : 0;
+  }
+  return CLOTHGPU_OK;
+}
+
+int set_all_active(Ctx* c, int v) {
+  k_set_active<<<c->B, 1, 0, c->stream>>>(c->cnt, v);
+  CG_LAUNCH_CHECK(c);
+  return CLOTHGPU_OK;
+}
+
+}  // namespace cg

@@ -1,0 +1,187 @@
+// csrc/ctx.h -- internal context of libclothgpu (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/clothgpu.h"
+
+namespace cg {
+
+// frontier entry of the dual-tree traversal: a node pair plus its position in the reference's depth-first order
+// (pre = preorder rank of the self() node whose children started this pair recursion, path = child choices so
+// far, 2 bits per descent, left aligned) -- see bvh.cu
+struct PairEnt {
+  int i0, i1;
+  uint32_t pre;
+  uint32_t depth;
+  uint64_t path_hi;  // first 32 descents
+  uint64_t path_lo;  // next 32 descents
+};
+static_assert(sizeof(PairEnt) == 32, "PairEnt layout");
+
+// raw contact element emitted by the narrow phase: canonical key + DFS rank (pre, path, slot)
+struct RawElem {
+  int n[4];
+  uint32_t pre;
+  uint32_t slot;  // 0..5 face-vertex tests, 6..14 edge-edge tests, in the reference's order
+  uint64_t path_hi;
+  uint64_t path_lo;
+};
+static_assert(sizeof(RawElem) == 40, "RawElem layout");
+
+enum { NSCAL = 16, NCNT = 96 };
+// per-scene device counters (ints): layout of cnt[]
+enum {
+  CNT_LEAF = 0,      // number of leaf pairs
+  CNT_RAW = 1,       // number of raw contact elements
+  CNT_ELEM = 2,      // number of unique contact elements
+  CNT_OVERFLOW = 3,  // bit 0: frontier, bit 1: leaf pairs, bit 2: raw elements, bit 3: elems
+  CNT_ACTIVE = 4,    // scene takes part in the current contact pass
+  CNT_NSING = 5,     // singular pivots seen by the ILU factorisation
+  CNT_PCG_DONE = 6,
+  CNT_PCG_ITER = 7,
+  CNT_RIZ_NODES = 8,
+  CNT_NLEVEL = 9,    // impulse dependency levels
+  CNT_TICKET = 10,   // arrival counter of the "last block reduces" pattern
+  CNT_FRONT = 16     // frontier sizes per traversal depth: CNT_FRONT + depth  (depth < 72)
+};
+// per-scene device scalars (doubles): layout of scal[]
+enum { SC_INV_SQ0 = 0, SC_RPR = 1, SC_PAP = 2, SC_SQ = 3, SC_ALPHA = 4, SC_BETA = 5, SC_CONV = 6, SC_TOL2 = 7,
+       SC_DOT = 8 };
+
+struct Ctx {
+  int device = 0;
+  int B = 1, np = 0, ntri = 0, nquad = 0, ncrs = 0, nnode = 0, ndof = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr;
+  long long launches = 0;
+  bool profiling = false;
+  double phase_ms[CLOTHGPU_NPHASE] = {0};
+
+  // ---- shared topology
+  int *tri = nullptr, *quad = nullptr, *bc = nullptr, *rowptr = nullptr, *colidx = nullptr, *diaind = nullptr;
+  double* xyz0 = nullptr;
+  // assembly gather lists (CSR): per vertex the incident (triangle, corner) / (hinge, corner) entries in
+  // element order; per off-diagonal slot the (triangle, block) / (hinge, block) entries
+  int *vt_ptr = nullptr, *vt_ent = nullptr, *vq_ptr = nullptr, *vq_ent = nullptr;
+  int *st_ptr = nullptr, *st_ent = nullptr, *sq_ptr = nullptr, *sq_ent = nullptr;
+  int* slot_row = nullptr;  // row index of every off-diagonal slot
+  // hinge constants (rest shape only): K[4] per hinge and stiff/((A0+A1) L0^2)
+  double *quadK = nullptr, *quadT = nullptr;
+  double quad_stiff = -1.0;  // stiff_bend the cached quadT was computed for
+  // ILU level schedules
+  int nlev_f = 0, nlev_b = 0, maxrows_f = 0, maxrows_b = 0;
+  int *lev_f_ptr = nullptr, *lev_f_rows = nullptr, *lev_b_ptr = nullptr, *lev_b_rows = nullptr;
+  // ILU update lists: per row the (ik, kj, ij) slot triples in the reference's order (ij < 0: diagonal block)
+  int *op_ptr = nullptr;
+  int4* ops = nullptr;
+  long long nops = 0;
+  // BVH
+  int* nodes = nullptr;     // nnode x 3
+  uint32_t* pre = nullptr;  // preorder rank per node
+  int bvh_height = 0, ninternal = 0;
+  int* internal_list = nullptr;  // ids of the internal nodes
+  int *edge_index = nullptr, *edge_array = nullptr;
+
+  // ---- per-scene state (scene-major)
+  double *xyz = nullptr, *uvw = nullptr, *xyz_prev = nullptr, *uvw0 = nullptr;
+  double *valDia = nullptr, *valCrs = nullptr, *iluDia = nullptr, *iluCrs = nullptr;
+  double *vec_r = nullptr, *vec_x = nullptr, *vec_p = nullptr, *vec_z = nullptr;
+  double *tri_dW = nullptr, *tri_ddW = nullptr, *quad_dW = nullptr;
+  double* col_table = nullptr;
+  double* gravity = nullptr;  // B x 3
+  std::vector<double> gravity_override;  // B x 3 on the host, NaN = no override
+  double* boxes = nullptr;
+  int* refit_flag = nullptr;
+  double *scal = nullptr, *partials = nullptr;
+  int* cnt = nullptr;
+  int* zone = nullptr;    // union-find parent per vertex, -1 = not a member
+  int* zone_label = nullptr;
+  // traversal queues (capacities are per scene)
+  long long cap_front = 0, cap_leaf = 0, cap_raw = 0, cap_elem = 0;
+  PairEnt *frontA = nullptr, *frontB = nullptr, *leaf = nullptr;
+  RawElem *raw = nullptr, *raw_sorted = nullptr;
+  int* elems = nullptr;  // cap_elem x 5
+  // impulse scheduling scratch
+  int *imp_level = nullptr, *imp_order = nullptr, *imp_lptr = nullptr, *imp_pred = nullptr;
+  // generic scratch for library sorts/scans
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  unsigned long long *sort_keys = nullptr, *sort_keys2 = nullptr;
+  int *sort_vals = nullptr, *sort_vals2 = nullptr;
+  long long cap_sort = 0;
+
+  // pinned host mirrors
+  int* h_cnt = nullptr;      // B x NCNT
+  double* h_scal = nullptr;  // B x NSCAL
+  int npartial = 0;          // blocks used by the reduction kernels
+};
+
+void set_error(const std::string& s);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define CG_CUDA(call)                                                         \
+  do {                                                                        \
+    cudaError_t e__ = (call);                                                 \
+    if (e__ != cudaSuccess) return cg::cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+#define CG_CHECK(call)              \
+  do {                              \
+    int r__ = (call);               \
+    if (r__ != CLOTHGPU_OK) return r__; \
+  } while (0)
+#define CG_LAUNCH_CHECK(c)                                                    \
+  do {                                                                        \
+    (c)->launches++;                                                          \
+    cudaError_t e__ = cudaGetLastError();                                     \
+    if (e__ != cudaSuccess) return cg::cuda_fail(e__, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+
+inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// buffer lookup: device pointer of one scene's buffer, element size and count
+struct BufInfo {
+  void* ptr;
+  size_t elem_bytes;
+  long long count;
+};
+int buf_info(Ctx* c, int buf, int scene, BufInfo* out);
+double* vec_buf(Ctx* c, int buf);  // scene 0 pointer of a np*3 vector buffer, or null
+
+// phase timing helpers (no-ops unless profiling is on)
+void phase_begin(Ctx* c);
+void phase_end(Ctx* c, int phase);
+
+// ---- kernels' host launchers (one translation unit each)
+int launch_assemble(Ctx* c, const clothgpu_params& p, bool with_hessian);
+int launch_update_velocity(Ctx* c, const clothgpu_params& p);
+int launch_matvec(Ctx* c, double alpha, const double* x, double beta, double* y);
+int launch_dot(Ctx* c, const double* a, const double* b, int scal_slot);
+int launch_axpy(Ctx* c, double a, const double* x, double* y);
+int launch_ilu_setvalue(Ctx* c);
+int launch_ilu_factor(Ctx* c);
+int launch_ilu_solve(Ctx* c, double* vec);
+int run_pcg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out);
+int run_cg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out);
+int run_step_internal(Ctx* c, const clothgpu_params& p, bool use_ilu, double* conv_out, int* iter_out);
+int launch_refit(Ctx* c, const double* xyz, const double* uvw, double par, int mode);
+int run_contacts(Ctx* c, const double* xyz, const double* uvw, double dt, double delta, int ccd, int* counts);
+int launch_impulse(Ctx* c, const double* xyz, double* uvw, double delta, double stiffness, double dt, double mass,
+                   int ccd);
+int launch_riz_reset(Ctx* c);
+int launch_riz_make(Ctx* c);
+int launch_riz_apply(Ctx* c, const double* xyz, double* uvw);
+int run_resolve(Ctx* c, const clothgpu_params& p, int* applied, int* stats);
+int fetch_counters(Ctx* c);  // cnt -> h_cnt, synchronous
+int ensure_scratch(Ctx* c, size_t bytes);
+int ensure_sort_capacity(Ctx* c, long long n);
+int grow_queues(Ctx* c, int overflow_bits);
+int set_active(Ctx* c, const int* active);  // per-scene participation flags (null: all scenes)
+
+}  // namespace cg
+
+struct clothgpu_ctx : public cg::Ctx {};

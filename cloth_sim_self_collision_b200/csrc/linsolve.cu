@@ -1,0 +1,526 @@
+// csrc/linsolve.cu -- block-CRS (3x3) linear algebra: SpMV, BLAS-1, ILU(0) factor / solve, PCG and CG drivers.
+//
+// Replaces CMatrixSquareSparse::MatVec (matrix_square_sparse.cpp:167-270, len == 3 at :218-242), InnerProduct
+// (:313-324), AXPY (:327-336), Solve_CG (:338-406), CPreconditionerILU::SetValueILU / DoILUDecomp /
+// ForwardSubstitution / BackwardSubstitution (ilu_sparse.cpp:352-384, 507-569, 185-215, 295-324) and Solve_PCG
+// (:628-709).
+//
+// Parity: SpMV, the factorisation and the triangular solves keep the reference's per-row operation order, so
+// they are bit-identical to it (compiled with -fmad=false).  Dot products use a fixed-shape tree (deterministic,
+// but not the reference's serial left-to-right order): PCG iterates agree to rounding, not bit for bit.
+//
+// The triangular solves and the factorisation are dependency chains over the rows (1021 levels on a 256^2 grid in
+// the reference's natural ordering, which parity forces us to keep): one CTA per scene walks the levels with a
+// block barrier per level; rows of a level are independent.  Batches of scenes run one CTA each, concurrently.
+#include "ctx.h"
+
+namespace cg {
+
+
+// ------------------------------------------------------------------------------------------------ SpMV
+// one thread per (row, component): y_r = beta*y_r + alpha * sum_j (a_r0 x0 + a_r1 x1 + a_r2 x2), off-diagonal blocks in
+// crs order, diagonal last.  If partials != nullptr the block also reduces x.y (fused p.Ap of PCG).
+__global__ void __launch_bounds__(256) k_matvec(int np, int ncrs, const int* __restrict__ rowptr,
+                                                 const int* __restrict__ colidx, const double* __restrict__ valDia,
+                                                 const double* __restrict__ valCrs, double alpha,
+                                                 const double* __restrict__ x, double beta, double* __restrict__ y,
+                                                 const int* __restrict__ cnt) {
+  const int s = blockIdx.y;
+  if (cnt && cnt[s * NCNT + CNT_PCG_DONE]) return;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= np * 3) return;
+  const int i = tid / 3, r = tid - i * 3;
+  const double* xs = x + (size_t)s * np * 3;
+  const double* crs = valCrs + (size_t)s * ncrs * 9;
+  double acc = (beta == 0.0) ? 0.0 : y[(size_t)s * np * 3 + tid] * beta;
+  const int j0 = rowptr[i], j1 = rowptr[i + 1];
+  for (int j = j0; j < j1; j++) {
+    const double* a = crs + (size_t)j * 9 + r * 3;
+    const double* xj = xs + (size_t)colidx[j] * 3;
+    acc += alpha * (a[0] * xj[0] + a[1] * xj[1] + a[2] * xj[2]);
+  }
+  {
+    const double* a = valDia + ((size_t)s * np + i) * 9 + r * 3;
+    const double* xj = xs + (size_t)i * 3;
+    acc += alpha * (a[0] * xj[0] + a[1] * xj[1] + a[2] * xj[2]);
+  }
+  y[(size_t)s * np * 3 + tid] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------ reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+// block-wide sum in a fixed order; result valid in thread 0
+__device__ __forceinline__ double block_sum(double v, double* sm) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  double r = 0;
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int k = 0; k < nw; k++) r += sm[k];
+  }
+  return r;
+}
+
+// what the last block does with the finished sum (Solve_PCG / Solve_CG scalar bookkeeping, ilu_sparse.cpp:640-705)
+enum { POST_STORE = 0, POST_PCG_INIT = 1, POST_PCG_CHECK = 2, POST_FINAL_CONV = 3, POST_CG_CHECK = 4 };
+
+struct DotArgs {
+  int n;
+  int post;
+  int slot;      // scal[] slot that receives the sum
+  int iter;      // current iteration (POST_*_CHECK)
+  double tol2;   // squared tolerance
+};
+
+__device__ void dot_post(const DotArgs& A, double sum, double* scal, int* cnt) {
+  scal[A.slot] = sum;
+  if (A.post == POST_PCG_INIT) {  // ilu_sparse.cpp:648-655: early out on a zero right-hand side
+    if (sum < 1.0e-30) {
+      cnt[CNT_PCG_DONE] = 1;
+      cnt[CNT_PCG_ITER] = 0;
+      scal[SC_CONV] = 0.0;
+    } else {
+      scal[SC_INV_SQ0] = 1.0 / sum;
+    }
+  } else if (A.post == POST_PCG_CHECK) {  // :684-690
+    if (sum * scal[SC_INV_SQ0] < A.tol2) {
+      scal[SC_CONV] = sqrt(sum * scal[SC_INV_SQ0]);
+      cnt[CNT_PCG_ITER] = A.iter;
+      cnt[CNT_PCG_DONE] = 1;
+    }
+  } else if (A.post == POST_FINAL_CONV) {  // :706-708
+    scal[SC_CONV] = sqrt(sum * scal[SC_INV_SQ0]);
+  } else if (A.post == POST_CG_CHECK) {  // matrix_square_sparse.cpp:389-394: reports the PREVIOUS residual
+    if (sum * scal[SC_INV_SQ0] < A.tol2) {
+      scal[SC_CONV] = sqrt(scal[SC_SQ] * scal[SC_INV_SQ0]);
+      cnt[CNT_PCG_ITER] = A.iter;
+      cnt[CNT_PCG_DONE] = 1;
+    }
+  }
+}
+
+__device__ __forceinline__ void reduce_finish(double v, const DotArgs& A, double* partials, double* scal, int* cnt,
+                                              double* sm) {
+  const double bs = block_sum(v, sm);
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = bs;
+    __threadfence();
+    const int t = atomicAdd(&cnt[CNT_TICKET], 1);
+    last = (t == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // the last block to arrive sums the per-block partials in a fixed order (lane-strided, then a shuffle tree)
+  if (threadIdx.x < 32) {
+    double acc = 0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += 32) acc += __ldcg(partials + k);
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) {
+      cnt[CNT_TICKET] = 0;
+      dot_post(A, acc, scal, cnt);
+    }
+  }
+}
+
+// a.b per scene; skip_done: scenes whose solver has converged keep their scalars
+__global__ void __launch_bounds__(256) k_dot(DotArgs A, const double* __restrict__ a, const double* __restrict__ b,
+                                              double* __restrict__ partials, double* __restrict__ scal,
+                                              int* __restrict__ cnt, int npartial, int skip_done) {
+  __shared__ double sm[8];
+  const int s = blockIdx.y;
+  int* c = cnt + s * NCNT;
+  if (skip_done && c[CNT_PCG_DONE]) return;
+  const double* as = a + (size_t)s * A.n;
+  const double* bs = b + (size_t)s * A.n;
+  double v = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += gridDim.x * blockDim.x) v += as[i] * bs[i];
+  reduce_finish(v, A, partials + (size_t)s * npartial, scal + s * NSCAL, c, sm);
+}
+
+// PCG update (ilu_sparse.cpp:674-682): alpha = rPr / pAp; r += (-alpha) Ap; x += alpha p; then r.r
+// CG update (matrix_square_sparse.cpp:378-386): alpha = sq / pAp; x += alpha p; r += (-alpha) Ap
+__global__ void __launch_bounds__(256) k_update_xr(DotArgs A, int rpr_slot, const double* __restrict__ Ap,
+                                                    const double* __restrict__ p, double* __restrict__ r,
+                                                    double* __restrict__ x, double* __restrict__ partials,
+                                                    double* __restrict__ scal, int* __restrict__ cnt, int npartial) {
+  __shared__ double sm[8];
+  const int s = blockIdx.y;
+  int* c = cnt + s * NCNT;
+  if (c[CNT_PCG_DONE]) return;
+  double* sc = scal + s * NSCAL;
+  const double alpha = sc[rpr_slot] / sc[SC_PAP];
+  const size_t off = (size_t)s * A.n;
+  double v = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += gridDim.x * blockDim.x) {
+    const double ri = r[off + i] + (-alpha) * Ap[off + i];
+    r[off + i] = ri;
+    x[off + i] += alpha * p[off + i];
+    v += ri * ri;
+  }
+  reduce_finish(v, A, partials + (size_t)s * npartial, sc, c, sm);
+}
+
+// p = z + beta p with beta = scal[num] / scal[den]  (ilu_sparse.cpp:699-703, matrix_square_sparse.cpp:396-402)
+__global__ void k_xpay(int n, int num_slot, int den_slot, const double* __restrict__ z, double* __restrict__ p,
+                       const double* __restrict__ scal, const int* __restrict__ cnt) {
+  const int s = blockIdx.y;
+  if (cnt[s * NCNT + CNT_PCG_DONE]) return;
+  const double beta = scal[s * NSCAL + num_slot] / scal[s * NSCAL + den_slot];
+  const size_t off = (size_t)s * n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    p[off + i] = z[off + i] + beta * p[off + i];
+}
+
+__global__ void k_axpy(int n, double a, const double* __restrict__ x, double* __restrict__ y) {
+  const size_t off = (size_t)blockIdx.y * n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[off + i] += a * x[off + i];
+}
+__global__ void k_copy(int n, const double* __restrict__ x, double* __restrict__ y, const int* __restrict__ cnt) {
+  if (cnt && cnt[blockIdx.y * NCNT + CNT_PCG_DONE]) return;
+  const size_t off = (size_t)blockIdx.y * n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[off + i] = x[off + i];
+}
+__global__ void k_set_scalar_slot(double* scal, int dst, int src) { scal[blockIdx.x * NSCAL + dst] = scal[blockIdx.x * NSCAL + src]; }
+__global__ void k_pcg_reset(int* cnt, double* scal, int max_iter, double conv_init) {
+  int* c = cnt + blockIdx.x * NCNT;
+  scal[blockIdx.x * NSCAL + SC_CONV] = conv_init;  // Solve_CG leaves conv_ratio untouched when it does not converge
+  c[CNT_PCG_DONE] = 0;
+  c[CNT_PCG_ITER] = max_iter;
+  c[CNT_TICKET] = 0;
+}
+// X += x ; V = x / dt   (solve_internal_sparse.h:323-325)
+__global__ void k_advance(int n, double dt, const double* __restrict__ x, double* __restrict__ xyz, double* __restrict__ uvw) {
+  const size_t off = (size_t)blockIdx.y * n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    xyz[off + i] += x[off + i];
+    uvw[off + i] = x[off + i] / dt;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ ILU(0)
+// DoILUDecomp, ilu_sparse.cpp:507-569.  One CTA per scene; rows of one dependency level are independent.  A warp
+// serves three rows at a time, nine lanes per row = the nine entries of a 3x3 block; the row's update list
+// (precomputed: ik, kj, ij slot triples in the reference's order) is applied sequentially, entry-parallel.
+__global__ void __launch_bounds__(1024) k_ilu_factor(int np, int ncrs, int nlev, const int* __restrict__ lev_ptr,
+                                                      const int* __restrict__ lev_rows, const int* __restrict__ rowptr,
+                                                      const int* __restrict__ diaind, const int* __restrict__ op_ptr,
+                                                      const int4* __restrict__ ops, double* iluDia, double* iluCrs,
+                                                      int* __restrict__ cnt) {
+  const int s = blockIdx.x;
+  double* dia = iluDia + (size_t)s * np * 9;
+  double* crs = iluCrs + (size_t)s * ncrs * 9;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int sub = lane / 9, e = lane - sub * 9;
+  const int r = e / 3, q = e - r * 3;
+  for (int lev = 0; lev < nlev; lev++) {
+    const int b0 = lev_ptr[lev], nrows = lev_ptr[lev + 1] - b0;
+    for (int base = warp * 3; base < nrows; base += nwarp * 3) {
+      const int row = (sub < 3 && base + sub < nrows) ? lev_rows[b0 + base + sub] : -1;
+      const int o0 = row >= 0 ? op_ptr[row] : 0;
+      const int nop = row >= 0 ? op_ptr[row + 1] - o0 : 0;
+      int maxop = nop;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) maxop = max(maxop, __shfl_xor_sync(0xffffffffu, maxop, o));
+      double* dii = dia + (size_t)(row >= 0 ? row : 0) * 9;
+      for (int o = 0; o < maxop; o++) {
+        if (o < nop) {
+          const int4 op = ops[o0 + o];
+          const double* vik = crs + (size_t)op.x * 9;
+          const double* vkj = crs + (size_t)op.y * 9;
+          double* vij = op.z < 0 ? dii : crs + (size_t)op.z * 9;
+          const double v = vij[e] - (vik[r * 3 + 0] * vkj[q] + vik[r * 3 + 1] * vkj[3 + q] + vik[r * 3 + 2] * vkj[6 + q]);
+          vij[e] = v;
+        }
+        __syncwarp();
+      }
+      // D_i <- D_i^-1 by cofactors (CalcInvMat3, ilu_sparse.cpp:77-97); a singular pivot is left as is (:541-551)
+      double a[9];
+      bool invert = false;
+      if (row >= 0) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) a[k] = dii[k];
+        const double det = +a[0] * a[4] * a[8] + a[3] * a[7] * a[2] + a[6] * a[1] * a[5] - a[0] * a[7] * a[5] -
+                           a[6] * a[4] * a[2] - a[3] * a[1] * a[8];
+        invert = fabs(det) > 1.0e-30;
+        if (invert) {
+          const double inv_det = 1.0 / det;
+          double t[9];
+#pragma unroll
+          for (int k = 0; k < 9; k++) t[k] = a[k];
+          a[0] = inv_det * (t[4] * t[8] - t[5] * t[7]);
+          a[1] = inv_det * (t[2] * t[7] - t[1] * t[8]);
+          a[2] = inv_det * (t[1] * t[5] - t[2] * t[4]);
+          a[3] = inv_det * (t[5] * t[6] - t[3] * t[8]);
+          a[4] = inv_det * (t[0] * t[8] - t[2] * t[6]);
+          a[5] = inv_det * (t[2] * t[3] - t[0] * t[5]);
+          a[6] = inv_det * (t[3] * t[7] - t[4] * t[6]);
+          a[7] = inv_det * (t[1] * t[6] - t[0] * t[7]);
+          a[8] = inv_det * (t[0] * t[4] - t[1] * t[3]);
+        } else if (e == 0) {
+          atomicAdd(&cnt[s * NCNT + CNT_NSING], 1);
+        }
+      }
+      __syncwarp();
+      if (row >= 0 && invert) dii[e] = a[e];
+      // U_ij <- D_i^-1 U_ij for the blocks above the diagonal (:556-567)
+      {
+        const int j0 = row >= 0 ? diaind[row] : 0;
+        const int nup = row >= 0 ? rowptr[row + 1] - j0 : 0;
+        int maxup = nup;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxup = max(maxup, __shfl_xor_sync(0xffffffffu, maxup, o));
+        for (int jj = 0; jj < maxup; jj++) {
+          double* vij = crs + (size_t)(j0 + (jj < nup ? jj : 0)) * 9;
+          double v = 0;
+          if (jj < nup) v = a[r * 3 + 0] * vij[q] + a[r * 3 + 1] * vij[3 + q] + a[r * 3 + 2] * vij[6 + q];
+          __syncwarp();
+          if (jj < nup) vij[e] = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ForwardSubstitution + BackwardSubstitution (len == 3), ilu_sparse.cpp:185-215, 295-324.  One CTA per scene;
+// three lanes per row (one per component), ten rows per warp; a block barrier separates dependency levels.
+__global__ void __launch_bounds__(320) k_ilu_solve(int np, int ncrs, int nlev_f, const int* __restrict__ lev_f_ptr,
+                                                    const int* __restrict__ lev_f_rows, int nlev_b,
+                                                    const int* __restrict__ lev_b_ptr, const int* __restrict__ lev_b_rows,
+                                                    const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                                                    const int* __restrict__ diaind, const double* __restrict__ iluDia,
+                                                    const double* __restrict__ iluCrs, double* vec,
+                                                    const double* __restrict__ src, const int* __restrict__ cnt) {
+  const int s = blockIdx.x;
+  if (cnt && cnt[s * NCNT + CNT_PCG_DONE]) return;
+  const double* dia = iluDia + (size_t)s * np * 9;
+  const double* crs = iluCrs + (size_t)s * ncrs * 9;
+  double* v = vec + (size_t)s * np * 3;
+  if (src) {  // fused "Pr = r" copy of Solve_PCG (ilu_sparse.cpp:692-694)
+    const double* sv = src + (size_t)s * np * 3;
+    for (int i = threadIdx.x; i < np * 3; i += blockDim.x) v[i] = sv[i];
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int g = lane / 3, r = lane - g * 3;  // g == 10 for the two idle lanes
+  const int src_lane = g * 3;
+  for (int lev = 0; lev < nlev_f; lev++) {
+    const int b0 = lev_f_ptr[lev], nrows = lev_f_ptr[lev + 1] - b0;
+    for (int base = warp * 10; base < nrows; base += nwarp * 10) {
+      const bool on = (g < 10) && (base + g < nrows);
+      const int row = on ? lev_f_rows[b0 + base + g] : 0;
+      double t = 0;
+      if (on) {
+        t = v[row * 3 + r];
+        const int j0 = rowptr[row], j1 = diaind[row];
+        for (int j = j0; j < j1; j++) {
+          const double* a = crs + (size_t)j * 9 + r * 3;
+          const double* xj = v + (size_t)colidx[j] * 3;
+          t -= a[0] * xj[0] + a[1] * xj[1] + a[2] * xj[2];
+        }
+      }
+      const double t0 = __shfl_sync(0xffffffffu, t, src_lane & 31);
+      const double t1 = __shfl_sync(0xffffffffu, t, (src_lane + 1) & 31);
+      const double t2 = __shfl_sync(0xffffffffu, t, (src_lane + 2) & 31);
+      if (on) {
+        const double* d = dia + (size_t)row * 9 + r * 3;
+        v[row * 3 + r] = d[0] * t0 + d[1] * t1 + d[2] * t2;
+      }
+    }
+    __syncthreads();
+  }
+  for (int lev = 0; lev < nlev_b; lev++) {
+    const int b0 = lev_b_ptr[lev], nrows = lev_b_ptr[lev + 1] - b0;
+    for (int base = warp * 10; base < nrows; base += nwarp * 10) {
+      const bool on = (g < 10) && (base + g < nrows);
+      if (on) {
+        const int row = lev_b_rows[b0 + base + g];
+        double t = v[row * 3 + r];
+        const int j0 = diaind[row], j1 = rowptr[row + 1];
+        for (int j = j0; j < j1; j++) {
+          const double* a = crs + (size_t)j * 9 + r * 3;
+          const double* xj = v + (size_t)colidx[j] * 3;
+          t -= a[0] * xj[0] + a[1] * xj[1] + a[2] * xj[2];
+        }
+        v[row * 3 + r] = t;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+static dim3 vec_grid(Ctx* c, int n) { return dim3(std::min(div_up(n, 256), c->npartial), c->B); }
+
+int launch_matvec(Ctx* c, double alpha, const double* x, double beta, double* y) {
+  dim3 g(div_up(c->ndof, 256), c->B);
+  k_matvec<<<g, 256, 0, c->stream>>>(c->np, c->ncrs, c->rowptr, c->colidx, c->valDia, c->valCrs, alpha, x, beta, y, nullptr);
+  CG_LAUNCH_CHECK(c);
+  return CLOTHGPU_OK;
+}
+
+static int dot_launch(Ctx* c, const double* a, const double* b, int slot, int post, int iter, double tol2, int skip_done) {
+  DotArgs A;
+  A.n = c->ndof; A.post = post; A.slot = slot; A.iter = iter; A.tol2 = tol2;
+  dim3 g(std::min(div_up(c->ndof, 256), c->npartial), c->B);
+  k_dot<<<g, 256, 0, c->stream>>>(A, a, b, c->partials, c->scal, c->cnt, c->npartial, skip_done);
+  CG_LAUNCH_CHECK(c);
+  return CLOTHGPU_OK;
+}
+int launch_dot(Ctx* c, const double* a, const double* b, int scal_slot) {
+  return dot_launch(c, a, b, scal_slot, POST_STORE, 0, 0.0, 0);
+}
+int launch_axpy(Ctx* c, double a, const double* x, double* y) {
+  k_axpy<<<vec_grid(c, c->ndof), 256, 0, c->stream>>>(c->ndof, a, x, y);
+  CG_LAUNCH_CHECK(c);
+  return CLOTHGPU_OK;
+}
+int launch_ilu_setvalue(Ctx* c) {
+  CG_CUDA(cudaMemcpyAsync(c->iluDia, c->valDia, sizeof(double) * (size_t)c->B * c->np * 9, cudaMemcpyDeviceToDevice, c->stream));
+  CG_CUDA(cudaMemcpyAsync(c->iluCrs, c->valCrs, sizeof(double) * (size_t)c->B * c->ncrs * 9, cudaMemcpyDeviceToDevice, c->stream));
+  return CLOTHGPU_OK;
+}
+int launch_ilu_factor(Ctx* c) {
+  k_ilu_factor<<<c->B, 1024, 0, c->stream>>>(c->np, c->ncrs, c->nlev_f, c->lev_f_ptr, c->lev_f_rows, c->rowptr, c->diaind,
+                                             c->op_ptr, c->ops, c->iluDia, c->iluCrs, c->cnt);
+  CG_LAUNCH_CHECK(c);
+  return CLOTHGPU_OK;
+}
+static int ilu_solve_launch(Ctx* c, double* vec, const double* src, bool skip_done) {
+  k_ilu_solve<<<c->B, 320, 0, c->stream>>>(c->np, c->ncrs, c->nlev_f, c->lev_f_ptr, c->lev_f_rows, c->nlev_b,
+                                           c->lev_b_ptr, c->lev_b_rows, c->rowptr, c->colidx, c->diaind, c->iluDia,
+                                           c->iluCrs, vec, src, skip_done ? c->cnt : nullptr);
+  CG_LAUNCH_CHECK(c);
+  return CLOTHGPU_OK;
+}
+int launch_ilu_solve(Ctx* c, double* vec) { return ilu_solve_launch(c, vec, nullptr, false); }
+
+static int all_done(Ctx* c, bool* done) {
+  CG_CHECK(fetch_counters(c));
+  *done = true;
+  for (int s = 0; s < c->B; s++)
+    if (!c->h_cnt[s * NCNT + CNT_PCG_DONE]) *done = false;
+  return CLOTHGPU_OK;
+}
+static int fetch_solver_result(Ctx* c, double* conv_out, int* iter_out) {
+  CG_CUDA(cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double) * NSCAL * c->B, cudaMemcpyDeviceToHost, c->stream));
+  CG_CHECK(fetch_counters(c));
+  for (int s = 0; s < c->B; s++) {
+    if (conv_out) conv_out[s] = c->h_scal[s * NSCAL + SC_CONV];
+    if (iter_out) iter_out[s] = c->h_cnt[s * NCNT + CNT_PCG_ITER];
+  }
+  return CLOTHGPU_OK;
+}
+
+// Solve_PCG, ilu_sparse.cpp:628-709.  rPr lives in scal[SC_RPR] / scal[SC_DOT] alternately (old / new).
+int run_pcg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out) {
+  const int n = c->ndof;
+  const double tol2 = tol * tol;
+  k_pcg_reset<<<c->B, 1, 0, c->stream>>>(c->cnt, c->scal, max_iter, tol);
+  CG_LAUNCH_CHECK(c);
+  CG_CUDA(cudaMemsetAsync(c->vec_x, 0, sizeof(double) * (size_t)c->B * n, c->stream));
+  CG_CHECK(dot_launch(c, c->vec_r, c->vec_r, SC_SQ, POST_PCG_INIT, 0, tol2, 0));
+  CG_CHECK(ilu_solve_launch(c, c->vec_z, c->vec_r, true));
+  k_copy<<<vec_grid(c, n), 256, 0, c->stream>>>(n, c->vec_z, c->vec_p, c->cnt);
+  CG_LAUNCH_CHECK(c);
+  int cur = SC_RPR, nxt = SC_DOT;
+  CG_CHECK(dot_launch(c, c->vec_r, c->vec_z, cur, POST_STORE, 0, tol2, 1));
+  bool done = false;
+  for (int it = 0; it < max_iter; it++) {
+    {
+      dim3 g(div_up(n, 256), c->B);
+      k_matvec<<<g, 256, 0, c->stream>>>(c->np, c->ncrs, c->rowptr, c->colidx, c->valDia, c->valCrs, 1.0, c->vec_p, 0.0,
+                                         c->vec_z, c->cnt);
+      CG_LAUNCH_CHECK(c);
+    }
+    CG_CHECK(dot_launch(c, c->vec_p, c->vec_z, SC_PAP, POST_STORE, 0, tol2, 1));
+    {
+      DotArgs A;
+      A.n = n; A.post = POST_PCG_CHECK; A.slot = SC_SQ; A.iter = it; A.tol2 = tol2;
+      k_update_xr<<<vec_grid(c, n), 256, 0, c->stream>>>(A, cur, c->vec_z, c->vec_p, c->vec_r, c->vec_x, c->partials,
+                                                         c->scal, c->cnt, c->npartial);
+      CG_LAUNCH_CHECK(c);
+    }
+    CG_CHECK(all_done(c, &done));
+    if (done) break;
+    CG_CHECK(ilu_solve_launch(c, c->vec_z, c->vec_r, true));
+    CG_CHECK(dot_launch(c, c->vec_r, c->vec_z, nxt, POST_STORE, 0, tol2, 1));
+    k_xpay<<<vec_grid(c, n), 256, 0, c->stream>>>(n, nxt, cur, c->vec_z, c->vec_p, c->scal, c->cnt);
+    CG_LAUNCH_CHECK(c);
+    std::swap(cur, nxt);
+  }
+  if (!done) CG_CHECK(dot_launch(c, c->vec_r, c->vec_r, SC_SQ, POST_FINAL_CONV, 0, tol2, 1));
+  return fetch_solver_result(c, conv_out, iter_out);
+}
+
+// Solve_CG, matrix_square_sparse.cpp:338-406: the loop starts at 1 and on convergence reports the PREVIOUS ratio
+int run_cg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out) {
+  const int n = c->ndof;
+  const double tol2 = tol * tol;
+  k_pcg_reset<<<c->B, 1, 0, c->stream>>>(c->cnt, c->scal, max_iter, tol);
+  CG_LAUNCH_CHECK(c);
+  CG_CUDA(cudaMemsetAsync(c->vec_x, 0, sizeof(double) * (size_t)c->B * n, c->stream));
+  CG_CHECK(dot_launch(c, c->vec_r, c->vec_r, SC_SQ, POST_PCG_INIT, 0, tol2, 0));
+  k_copy<<<vec_grid(c, n), 256, 0, c->stream>>>(n, c->vec_r, c->vec_p, c->cnt);
+  CG_LAUNCH_CHECK(c);
+  bool done = false;
+  for (int it = 1; it < max_iter; it++) {
+    {
+      dim3 g(div_up(n, 256), c->B);
+      k_matvec<<<g, 256, 0, c->stream>>>(c->np, c->ncrs, c->rowptr, c->colidx, c->valDia, c->valCrs, 1.0, c->vec_p, 0.0,
+                                         c->vec_z, c->cnt);
+      CG_LAUNCH_CHECK(c);
+    }
+    CG_CHECK(dot_launch(c, c->vec_p, c->vec_z, SC_PAP, POST_STORE, 0, tol2, 1));
+    {
+      DotArgs A;
+      A.n = n; A.post = POST_CG_CHECK; A.slot = SC_DOT; A.iter = it; A.tol2 = tol2;
+      k_update_xr<<<vec_grid(c, n), 256, 0, c->stream>>>(A, SC_SQ, c->vec_z, c->vec_p, c->vec_r, c->vec_x, c->partials,
+                                                         c->scal, c->cnt, c->npartial);
+      CG_LAUNCH_CHECK(c);
+    }
+    if ((it & 7) == 0 || it == max_iter - 1) {  // unpreconditioned CG runs hundreds of cheap iterations: poll sparsely
+      CG_CHECK(all_done(c, &done));
+      if (done) break;
+    }
+    // beta = sq_new / sq ; sq = sq_new ; p = r + beta p
+    k_xpay<<<vec_grid(c, n), 256, 0, c->stream>>>(n, SC_DOT, SC_SQ, c->vec_r, c->vec_p, c->scal, c->cnt);
+    CG_LAUNCH_CHECK(c);
+    k_set_scalar_slot<<<c->B, 1, 0, c->stream>>>(c->scal, SC_SQ, SC_DOT);
+    CG_LAUNCH_CHECK(c);
+  }
+  return fetch_solver_result(c, conv_out, iter_out);
+}
+
+// StepTime_InternalDynamicsILU (solve_internal_sparse.h:255-326) / StepTime_InternalDynamics (:185-253)
+int run_step_internal(Ctx* c, const clothgpu_params& p, bool use_ilu, double* conv_out, int* iter_out) {
+  phase_begin(c);
+  CG_CHECK(launch_assemble(c, p, true));
+  phase_end(c, 0);
+  if (use_ilu) {
+    phase_begin(c);
+    CG_CHECK(launch_ilu_setvalue(c));
+    CG_CHECK(launch_ilu_factor(c));
+    phase_end(c, 1);
+    phase_begin(c);
+    CG_CHECK(run_pcg(c, 1.0e-4, 100, conv_out, iter_out));
+    phase_end(c, 2);
+  } else {
+    phase_begin(c);
+    CG_CHECK(run_cg(c, 1.0e-4, 1000, conv_out, iter_out));
+    phase_end(c, 2);
+  }
+  k_advance<<<vec_grid(c, c->ndof), 256, 0, c->stream>>>(c->ndof, p.dt, c->vec_x, c->xyz, c->uvw);
+  CG_LAUNCH_CHECK(c);
+  return CLOTHGPU_OK;
+}
+
+}  // namespace cg

@@ -1,0 +1,438 @@
+// csrc/response.cu -- collision response: repulsion / CCD impulses and rigid impact zones.
+//
+// Replaces SelfCollisionImpulse_Proximity (self_collision_cloth.cpp:20-112), SelfCollisionImpulse_CCD (:116-212),
+// MakeRigidImpactZone (:220-274) and ApplyRigidImpactZone (:298-348).
+//
+// Impulses: the reference applies the elements one after the other in std::set order and every element reads the
+// velocities written by the earlier ones (Gauss-Seidel).  Two elements only interact through a shared vertex, so
+// the serial order is equivalent to any order that keeps, for every vertex, the relative order of the elements
+// touching it.  We build that dependency DAG (predecessor of element k on each of its 4 vertices = the previous
+// element touching the vertex, found with one stable radix sort of (vertex, element) pairs), level it
+// (level = 1 + max level of the predecessors) and run level after level inside one CTA per scene: elements of a
+// level touch disjoint vertices.  Bit-identical to the serial loop.
+//
+// Impact zones: the reference's zone list equals the connected components of the member vertices under
+// "same contact element" and "mesh-adjacent and both members" (order independent, verified against the
+// reference); a lock-free union-find in global memory builds them.  ApplyRigidImpactZone sums over each zone in
+// ascending vertex id; a stable sort by zone label lays the zones out as segments in that order and each zone is
+// reduced sequentially, so the sums are bit-identical too.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "ctx.h"
+#include "dev_math.cuh"
+
+namespace cg {
+
+// v[i] += n * a * b evaluated as (n*a)*b, like `-norm.x*imp_mod*w0` in the reference
+__device__ __forceinline__ void add3(double* v, int i, V3 n, double a, double b) {
+  v[i * 3 + 0] += n.x * a * b;
+  v[i * 3 + 1] += n.y * a * b;
+  v[i * 3 + 2] += n.z * a * b;
+}
+__device__ __forceinline__ void add3s(double* v, int i, V3 n, double a) {
+  v[i * 3 + 0] += n.x * a;
+  v[i * 3 + 1] += n.y * a;
+  v[i * 3 + 2] += n.z * a;
+}
+
+// one element of SelfCollisionImpulse_Proximity, self_collision_cloth.cpp:31-110
+__device__ void impulse_prx_one(const int* n, const double* xyz, double* uvw, double delta, double stiffness, double dt,
+                                double mass) {
+  const V3 p0 = ld3(xyz, n[0]), p1 = ld3(xyz, n[1]), p2 = ld3(xyz, n[2]), p3 = ld3(xyz, n[3]);
+  const V3 v0 = ld3(uvw, n[0]), v1 = ld3(uvw, n[1]), v2 = ld3(uvw, n[2]), v3v = ld3(uvw, n[3]);
+  if (n[4]) {
+    double w0, w1;
+    {
+      const double dist = dist_face_vertex(p0, p1, p2, p3, w0, w1);
+      if (w0 < 0 || w0 > 1) return;
+      if (w1 < 0 || w1 > 1) return;
+      if (dist > delta) return;
+    }
+    const double w2 = 1.0 - w0 - w1;
+    const V3 pc = (w0 * p0 + w1 * p1) + w2 * p2;
+    const V3 norm = normalized(p3 - pc);
+    const double p_depth = delta - dot(p3 - pc, norm);
+    const double rel_v = dot(((v3v - w0 * v0) - w1 * v1) - w2 * v2, norm);
+    if (rel_v > 0.1 * p_depth / dt) return;
+    const double imp_el = dt * stiffness * p_depth;
+    const double imp_ie = mass * (0.1 * p_depth / dt - rel_v);
+    const double imp_min = (imp_el < imp_ie) ? imp_el : imp_ie;
+    double imp_mod = 2 * imp_min / (1 + w0 * w0 + w1 * w1 + w2 * w2);
+    imp_mod /= mass;
+    imp_mod *= 0.25;
+    add3(uvw, n[0], -norm, imp_mod, w0);
+    add3(uvw, n[1], -norm, imp_mod, w1);
+    add3(uvw, n[2], -norm, imp_mod, w2);
+    add3s(uvw, n[3], norm, imp_mod);
+  } else {
+    double w01, w23;
+    {
+      const double dist = dist_edge_edge(p0, p1, p2, p3, w01, w23);
+      if (w01 < 0 || w01 > 1) return;
+      if (w23 < 0 || w23 > 1) return;
+      if (dist > delta) return;
+    }
+    const V3 c01 = (1 - w01) * p0 + w01 * p1;
+    const V3 c23 = (1 - w23) * p2 + w23 * p3;
+    const V3 norm = normalized(c23 - c01);
+    const double p_depth = delta - length(c23 - c01);
+    const double rel_v = dot((((1 - w23) * v2 + w23 * v3v) - (1 - w01) * v0) - w01 * v1, norm);
+    if (rel_v > 0.1 * p_depth / dt) return;
+    const double imp_el = dt * stiffness * p_depth;
+    const double imp_ie = mass * (0.1 * p_depth / dt - rel_v);
+    const double imp_min = (imp_el < imp_ie) ? imp_el : imp_ie;
+    double imp_mod = 2 * imp_min / (w01 * w01 + (1 - w01) * (1 - w01) + w23 * w23 + (1 - w23) * (1 - w23));
+    imp_mod /= mass;
+    imp_mod *= 0.25;
+    add3(uvw, n[0], -norm, imp_mod, 1 - w01);
+    add3(uvw, n[1], -norm, imp_mod, w01);
+    add3(uvw, n[2], norm, imp_mod, 1 - w23);
+    add3(uvw, n[3], norm, imp_mod, w23);
+  }
+}
+
+// one element of SelfCollisionImpulse_CCD, self_collision_cloth.cpp:127-210.  Reference quirk (:141): the impact
+// time is re-solved with the UN-scaled velocity (end points p + v, not p + dt*v).
+__device__ void impulse_ccd_one(const int* n, const double* xyz, double* uvw, double delta, double dt, double mass) {
+  const V3 p0 = ld3(xyz, n[0]), p1 = ld3(xyz, n[1]), p2 = ld3(xyz, n[2]), p3 = ld3(xyz, n[3]);
+  const V3 v0 = ld3(uvw, n[0]), v1 = ld3(uvw, n[1]), v2 = ld3(uvw, n[2]), v3v = ld3(uvw, n[3]);
+  const double t = coplanar_time(p0, p1, p2, p3, p0 + v0, p1 + v1, p2 + v2, p3 + v3v);
+  if (t < 0 || t > 1) return;
+  const V3 p0m = p0 + t * v0, p1m = p1 + t * v1, p2m = p2 + t * v2, p3m = p3 + t * v3v;
+  if (n[4]) {
+    double w0, w1;
+    {
+      const double dist = dist_face_vertex(p0m, p1m, p2m, p3m, w0, w1);
+      if (w0 < 0 || w0 > 1) return;
+      if (w1 < 0 || w1 > 1) return;
+      if (dist > delta) return;
+    }
+    const double w2 = 1.0 - w0 - w1;
+    const V3 pc = (w0 * p0 + w1 * p1) + w2 * p2;
+    const V3 norm = normalized(p3 - pc);
+    const double rel_v = dot(((v3v - w0 * v0) - w1 * v1) - w2 * v2, norm);
+    if (rel_v > 0.1 * delta / dt) return;
+    const double imp = mass * (0.1 * delta / dt - rel_v);
+    double imp_mod = 2 * imp / (1.0 + w0 * w0 + w1 * w1 + w2 * w2);
+    imp_mod /= mass;
+    imp_mod *= 0.1;
+    add3(uvw, n[0], -norm, imp_mod, w0);
+    add3(uvw, n[1], -norm, imp_mod, w1);
+    add3(uvw, n[2], -norm, imp_mod, w2);
+    add3s(uvw, n[3], norm, imp_mod);
+  } else {
+    double w01, w23;
+    {
+      const double dist = dist_edge_edge(p0m, p1m, p2m, p3m, w01, w23);
+      if (w01 < 0 || w01 > 1) return;
+      if (w23 < 0 || w23 > 1) return;
+      if (dist > delta) return;
+    }
+    const V3 c01 = (1 - w01) * p0 + w01 * p1;
+    const V3 c23 = (1 - w23) * p2 + w23 * p3;
+    const V3 norm = normalized(c23 - c01);
+    const double rel_v = dot((((1 - w23) * v2 + w23 * v3v) - (1 - w01) * v0) - w01 * v1, norm);
+    if (rel_v > 0.1 * delta / dt) return;
+    const double imp = mass * (0.1 * delta / dt - rel_v);
+    double imp_mod = 2 * imp / (w01 * w01 + (1 - w01) * (1 - w01) + w23 * w23 + (1 - w23) * (1 - w23));
+    imp_mod /= mass;
+    imp_mod *= 0.1;
+    add3(uvw, n[0], -norm, imp_mod, 1 - w01);
+    add3(uvw, n[1], -norm, imp_mod, w01);
+    add3(uvw, n[2], norm, imp_mod, 1 - w23);
+    add3(uvw, n[3], norm, imp_mod, w23);
+  }
+}
+
+// (vertex, element*4+corner) pairs in element order
+__global__ void k_imp_pairs(int ne, const int* __restrict__ elems, unsigned* __restrict__ keys, int* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ne * 4) return;
+  const int k = i >> 2, a = i & 3;
+  keys[i] = (unsigned)elems[k * 5 + a];
+  vals[i] = i;
+}
+// predecessor of (element, corner): the previous element touching the same vertex, or -1
+__global__ void k_imp_pred(int n4, const unsigned* __restrict__ keys, const int* __restrict__ vals, int* __restrict__ pred) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  pred[vals[i]] = (i > 0 && keys[i - 1] == keys[i]) ? (vals[i - 1] >> 2) : -1;
+}
+
+// one CTA per scene: level the dependency DAG, bucket the elements by level, apply level after level
+__global__ void __launch_bounds__(1024) k_imp_run(int ccd, int np, long long cap_elem, const int* __restrict__ elems_all,
+                                                   const int* __restrict__ pred_all, int* level_all, int* order_all,
+                                                   int* lptr_all, const double* __restrict__ xyz_all, double* uvw_all,
+                                                   double delta, double stiffness, double dt, double mass,
+                                                   const int* __restrict__ cnt) {
+  const int s = blockIdx.x;
+  const int* c = cnt + s * NCNT;
+  if (!c[CNT_ACTIVE]) return;
+  const int ne = c[CNT_ELEM];
+  if (ne == 0) return;
+  const int* elems = elems_all + (size_t)s * cap_elem * 5;
+  const int* pred = pred_all + (size_t)s * cap_elem * 4;
+  int* level = level_all + (size_t)s * cap_elem;
+  int* order = order_all + (size_t)s * cap_elem;
+  int* lptr = lptr_all + (size_t)s * (cap_elem + 2) * 2;  // [0, cap+2): level offsets, [cap+2, 2cap+4): cursors
+  int* cursor = lptr + cap_elem + 2;
+  const double* xyz = xyz_all + (size_t)s * np * 3;
+  double* uvw = uvw_all + (size_t)s * np * 3;
+  __shared__ int sh_changed, sh_nlev;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int k = tid; k < ne; k += nt) level[k] = 0;
+  if (tid == 0) sh_nlev = 0;
+  __syncthreads();
+  // chaotic relaxation towards the longest-path levels (monotone, unique fixed point)
+  for (;;) {
+    if (tid == 0) sh_changed = 0;
+    __syncthreads();
+    for (int k = tid; k < ne; k += nt) {
+      int l = 0;
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const int pk = pred[k * 4 + a];
+        if (pk >= 0) l = max(l, ((volatile int*)level)[pk] + 1);
+      }
+      if (l > level[k]) { level[k] = l; sh_changed = 1; }
+    }
+    __syncthreads();
+    if (!sh_changed) break;
+    __syncthreads();
+  }
+  for (int k = tid; k < ne; k += nt) atomicMax(&sh_nlev, level[k] + 1);
+  __syncthreads();
+  const int nlev = sh_nlev;
+  for (int l = tid; l <= nlev; l += nt) lptr[l] = 0;
+  __syncthreads();
+  for (int k = tid; k < ne; k += nt) atomicAdd(&lptr[level[k] + 1], 1);
+  __syncthreads();
+  if (tid == 0) {
+    for (int l = 0; l < nlev; l++) lptr[l + 1] += lptr[l];
+  }
+  __syncthreads();
+  for (int l = tid; l < nlev; l += nt) cursor[l] = lptr[l];
+  __syncthreads();
+  for (int k = tid; k < ne; k += nt) order[atomicAdd(&cursor[level[k]], 1)] = k;
+  __syncthreads();
+  for (int l = 0; l < nlev; l++) {
+    const int b = lptr[l], e = lptr[l + 1];
+    for (int i = b + tid; i < e; i += nt) {
+      const int* n = elems + (size_t)order[i] * 5;
+      if (ccd) impulse_ccd_one(n, xyz, uvw, delta, dt, mass);
+      else impulse_prx_one(n, xyz, uvw, delta, stiffness, dt, mass);
+    }
+    __syncthreads();
+  }
+}
+
+int launch_impulse(Ctx* c, const double* xyz, double* uvw, double delta, double stiffness, double dt, double mass, int ccd) {
+  // element counts are on the host already (the reference's loop control needs them)
+  for (int s = 0; s < c->B; s++) {
+    if (!c->h_cnt[s * NCNT + CNT_ACTIVE]) continue;
+    const int ne = c->h_cnt[s * NCNT + CNT_ELEM];
+    if (ne == 0) continue;
+    const int n4 = ne * 4;
+    CG_CHECK(ensure_sort_capacity(c, n4));
+    unsigned* keys = (unsigned*)c->sort_keys;
+    unsigned* keys2 = (unsigned*)c->sort_keys2;
+    const int* elems = c->elems + (size_t)s * c->cap_elem * 5;
+    int end_bit = 1;
+    while ((1LL << end_bit) < c->np) end_bit++;
+    size_t tb = 0;
+    CG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys2, c->sort_vals, c->sort_vals2, n4, 0, end_bit, c->stream));
+    CG_CHECK(ensure_scratch(c, tb));
+    k_imp_pairs<<<div_up(n4, 256), 256, 0, c->stream>>>(ne, elems, keys, c->sort_vals);
+    CG_LAUNCH_CHECK(c);
+    CG_CUDA(cub::DeviceRadixSort::SortPairs(c->scratch, tb, keys, keys2, c->sort_vals, c->sort_vals2, n4, 0, end_bit, c->stream));
+    c->launches += 3;
+    k_imp_pred<<<div_up(n4, 256), 256, 0, c->stream>>>(n4, keys2, c->sort_vals2, c->imp_pred + (size_t)s * c->cap_elem * 4);
+    CG_LAUNCH_CHECK(c);
+  }
+  k_imp_run<<<c->B, 1024, 0, c->stream>>>(ccd, c->np, c->cap_elem, c->elems, c->imp_pred, c->imp_level, c->imp_order,
+                                          c->imp_lptr, xyz, uvw, delta, stiffness, dt, mass, c->cnt);
+  CG_LAUNCH_CHECK(c);
+  return CLOTHGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ impact zones
+__device__ __forceinline__ int uf_find(int* parent, int v) {
+  for (;;) {
+    const int p = ((volatile int*)parent)[v];
+    if (p == v) return v;
+    v = p;
+  }
+}
+// link the larger root under the smaller one: the root of a component is its smallest vertex id
+__device__ void uf_union(int* parent, int a, int b) {
+  for (;;) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    const int hi = a > b ? a : b, lo = a > b ? b : a;
+    if (atomicCAS(&parent[hi], hi, lo) == hi) return;
+  }
+}
+
+// new members: the 4 vertices of every contact element (MakeRigidImpactZone inserts n[0..3], :244-271)
+__global__ void k_riz_mark(int np, long long cap_elem, const int* __restrict__ elems_all, int* zone_all,
+                           const int* __restrict__ cnt) {
+  const int s = blockIdx.y;
+  const int* c = cnt + s * NCNT;
+  if (!c[CNT_ACTIVE]) return;
+  const int ne = c[CNT_ELEM];
+  const int* elems = elems_all + (size_t)s * cap_elem * 5;
+  int* zone = zone_all + (size_t)s * np;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < ne; k += gridDim.x * blockDim.x)
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const int v = elems[k * 5 + a];
+      atomicCAS(&zone[v], -1, v);
+    }
+}
+// merges: the vertices of one element, and every element vertex with its mesh neighbours that are members (:229-241)
+__global__ void k_riz_union(int np, long long cap_elem, const int* __restrict__ elems_all,
+                            const int* __restrict__ edge_index, const int* __restrict__ edge_array, int* zone_all,
+                            const int* __restrict__ cnt) {
+  const int s = blockIdx.y;
+  const int* c = cnt + s * NCNT;
+  if (!c[CNT_ACTIVE]) return;
+  const int ne = c[CNT_ELEM];
+  const int* elems = elems_all + (size_t)s * cap_elem * 5;
+  int* zone = zone_all + (size_t)s * np;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < ne; k += gridDim.x * blockDim.x) {
+    const int n0 = elems[k * 5 + 0];
+#pragma unroll
+    for (int a = 1; a < 4; a++) uf_union(zone, n0, elems[k * 5 + a]);
+    for (int a = 0; a < 4; a++) {
+      const int v = elems[k * 5 + a];
+      for (int j = edge_index[v]; j < edge_index[v + 1]; j++) {
+        const int u = edge_array[j];
+        if (((volatile int*)zone)[u] != -1) uf_union(zone, v, u);
+      }
+    }
+  }
+}
+// label = root (smallest vertex id of the zone) or -1; sort key = label, non-members last
+__global__ void k_riz_label(int np, int* zone_all, int* __restrict__ label_all, int* cnt) {
+  const int s = blockIdx.y;
+  int* c = cnt + s * NCNT;
+  if (!c[CNT_ACTIVE]) return;
+  int* zone = zone_all + (size_t)s * np;
+  int* label = label_all + (size_t)s * np;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= np) return;
+  const int p = zone[v];
+  label[v] = (p == -1) ? -1 : uf_find(zone, v);
+}
+__global__ void k_riz_keys(int np, const int* __restrict__ label, unsigned* __restrict__ keys, int* __restrict__ vals) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= np) return;
+  keys[v] = label[v] < 0 ? 0x7fffffffu : (unsigned)label[v];
+  vals[v] = v;
+}
+
+// ApplyRigidImpactZone, self_collision_cloth.cpp:298-348, one thread per zone (segment of the label-sorted vertex
+// list, ascending vertex id inside the segment = std::set<int> order).
+// Reference quirk (:327-329): the "inertia tensor" diagonal uses v.v (velocity) where q.q (position) is meant.
+__global__ void k_riz_apply(int np, const unsigned* __restrict__ keys, const int* __restrict__ vals,
+                            const double* __restrict__ xyz, const double* __restrict__ uvw0, double* __restrict__ uvw,
+                            int* cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  const unsigned key = keys[i];
+  if (key == 0x7fffffffu) return;
+  atomicAdd(&cnt[CNT_RIZ_NODES], 1);
+  if (i > 0 && keys[i - 1] == key) return;
+  int e = i;
+  while (e < np && keys[e] == key) e++;
+  V3 gc = v3(0, 0, 0), av = v3(0, 0, 0);
+  for (int j = i; j < e; j++) {
+    gc = gc + ld3(xyz, vals[j]);
+    av = av + ld3(uvw0, vals[j]);
+  }
+  gc = div_guarded(gc, (double)(e - i));
+  av = div_guarded(av, (double)(e - i));
+  V3 L = v3(0, 0, 0);
+  double I[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int j = i; j < e; j++) {
+    const V3 p = ld3(xyz, vals[j]);
+    const V3 v = ld3(uvw0, vals[j]);
+    L = L + cross(p - gc, v - av);
+    const V3 q = p - gc;
+    const double vv = dot(v, v);
+    I[0] += vv - q.x * q.x; I[1] += -q.x * q.y;     I[2] += -q.x * q.z;
+    I[3] += -q.y * q.x;     I[4] += vv - q.y * q.y; I[5] += -q.y * q.z;
+    I[6] += -q.z * q.x;     I[7] += -q.z * q.y;     I[8] += vv - q.z * q.z;
+  }
+  double Iinv[9];
+  {  // CalcInvMat3, self_collision_cloth.cpp:278-296
+    const double det = +I[0] * I[4] * I[8] + I[3] * I[7] * I[2] + I[6] * I[1] * I[5] - I[0] * I[7] * I[5] -
+                       I[6] * I[4] * I[2] - I[3] * I[1] * I[8];
+    const double inv_det = 1.0 / det;
+    Iinv[0] = inv_det * (I[4] * I[8] - I[5] * I[7]);
+    Iinv[1] = inv_det * (I[2] * I[7] - I[1] * I[8]);
+    Iinv[2] = inv_det * (I[1] * I[5] - I[2] * I[4]);
+    Iinv[3] = inv_det * (I[5] * I[6] - I[3] * I[8]);
+    Iinv[4] = inv_det * (I[0] * I[8] - I[2] * I[6]);
+    Iinv[5] = inv_det * (I[2] * I[3] - I[0] * I[5]);
+    Iinv[6] = inv_det * (I[3] * I[7] - I[4] * I[6]);
+    Iinv[7] = inv_det * (I[1] * I[6] - I[0] * I[7]);
+    Iinv[8] = inv_det * (I[0] * I[4] - I[1] * I[3]);
+  }
+  V3 omg;
+  omg.x = Iinv[0] * L.x + Iinv[1] * L.y + Iinv[2] * L.z;
+  omg.y = Iinv[3] * L.x + Iinv[4] * L.y + Iinv[5] * L.z;
+  omg.z = Iinv[6] * L.x + Iinv[7] * L.y + Iinv[8] * L.z;
+  for (int j = i; j < e; j++) {
+    const int v = vals[j];
+    const V3 rot = -cross(ld3(xyz, v) - gc, omg);
+    uvw[v * 3 + 0] = av.x + rot.x;
+    uvw[v * 3 + 1] = av.y + rot.y;
+    uvw[v * 3 + 2] = av.z + rot.z;
+  }
+}
+__global__ void k_zero_cnt(int* cnt, int slot) { cnt[blockIdx.x * NCNT + slot] = 0; }
+
+int launch_riz_reset(Ctx* c) {
+  CG_CUDA(cudaMemsetAsync(c->zone, 0xff, sizeof(int) * (size_t)c->B * c->np, c->stream));
+  CG_CUDA(cudaMemsetAsync(c->zone_label, 0xff, sizeof(int) * (size_t)c->B * c->np, c->stream));
+  return CLOTHGPU_OK;
+}
+
+int launch_riz_make(Ctx* c) {
+  dim3 g(148, c->B);
+  k_riz_mark<<<g, 256, 0, c->stream>>>(c->np, c->cap_elem, c->elems, c->zone, c->cnt);
+  CG_LAUNCH_CHECK(c);
+  k_riz_union<<<g, 256, 0, c->stream>>>(c->np, c->cap_elem, c->elems, c->edge_index, c->edge_array, c->zone, c->cnt);
+  CG_LAUNCH_CHECK(c);
+  dim3 g2(div_up(c->np, 256), c->B);
+  k_riz_label<<<g2, 256, 0, c->stream>>>(c->np, c->zone, c->zone_label, c->cnt);
+  CG_LAUNCH_CHECK(c);
+  return CLOTHGPU_OK;
+}
+
+int launch_riz_apply(Ctx* c, const double* xyz, double* uvw) {
+  k_zero_cnt<<<c->B, 1, 0, c->stream>>>(c->cnt, CNT_RIZ_NODES);
+  CG_LAUNCH_CHECK(c);
+  CG_CHECK(ensure_sort_capacity(c, c->np));
+  unsigned* keys = (unsigned*)c->sort_keys;
+  unsigned* keys2 = (unsigned*)c->sort_keys2;
+  size_t tb = 0;
+  CG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys2, c->sort_vals, c->sort_vals2, c->np, 0, 32, c->stream));
+  CG_CHECK(ensure_scratch(c, tb));
+  for (int s = 0; s < c->B; s++) {
+    if (!c->h_cnt[s * NCNT + CNT_ACTIVE]) continue;
+    k_riz_keys<<<div_up(c->np, 256), 256, 0, c->stream>>>(c->np, c->zone_label + (size_t)s * c->np, keys, c->sort_vals);
+    CG_LAUNCH_CHECK(c);
+    CG_CUDA(cub::DeviceRadixSort::SortPairs(c->scratch, tb, keys, keys2, c->sort_vals, c->sort_vals2, c->np, 0, 32, c->stream));
+    c->launches += 3;
+    k_riz_apply<<<div_up(c->np, 128), 128, 0, c->stream>>>(c->np, keys2, c->sort_vals2, xyz + (size_t)s * c->ndof,
+                                                           c->uvw0 + (size_t)s * c->ndof, uvw + (size_t)s * c->ndof,
+                                                           c->cnt + s * NCNT);
+    CG_LAUNCH_CHECK(c);
+  }
+  return CLOTHGPU_OK;
+}
+
+}  // namespace cg

@@ -120,6 +120,43 @@ def jittered_rest(sc, amplitude_frac=0.2, seed=88172645463325252):
     return x.ravel()
 
 
+def median_split_bvh(sc, xyz=None):
+    """A balanced BVH *topology* over the triangles (median split of the centroids along the longest axis).
+
+    Output layout = the reference's std::vector<CNodeBVH>: rows {iroot, ichild0, ichild1}, node 0 is the root,
+    a leaf has ichild1 == -1 and ichild0 == triangle index, children are numbered after their parent.  The
+    reference's own builder (MakeBVHTopology_TopDown, bvh_aabb.cpp:294-313) crashes on exactly-square grids
+    (SURVEY.md section 8c); any valid binary tree is a legal input of the per-step path, and this one needs
+    nothing but numpy, so benches and tests on the GPU box use it for the large grids."""
+    x = np.asarray(sc["xyz0"] if xyz is None else xyz, dtype=np.float64).reshape(-1, 3)
+    tri = np.asarray(sc["tri"]).reshape(-1, 3)
+    cent = x[tri].mean(axis=1)
+    ntri = tri.shape[0]
+    nodes = np.full((2 * ntri - 1, 3), -1, dtype=np.int32)
+    nnode = 1
+    stack = [(0, np.arange(ntri))]
+    while stack:
+        inode, idx = stack.pop()
+        if idx.size == 1:
+            nodes[inode, 1] = idx[0]
+            nodes[inode, 2] = -1
+            continue
+        c = cent[idx]
+        axis = int(np.argmax(c.max(axis=0) - c.min(axis=0)))
+        order = np.argsort(c[:, axis], kind="stable")
+        half = idx.size // 2
+        c0, c1 = nnode, nnode + 1
+        nnode += 2
+        nodes[inode, 1] = c0
+        nodes[inode, 2] = c1
+        nodes[c0, 0] = inode
+        nodes[c1, 0] = inode
+        stack.append((c1, idx[order[half:]]))
+        stack.append((c0, idx[order[:half]]))
+    assert nnode == 2 * ntri - 1
+    return nodes
+
+
 # demo constants -------------------------------------------------------------------------------------------
 SELF_CONTACT = dict(dt=0.01, lam=0.0, myu=30.0, stiff_bend=1.0e-2, gravity=(0.0, 0.05, -10.0),
                     stiff_contact=300.0, clearance=0.01, areal_density=0.04,

@@ -1,0 +1,75 @@
+"""CPU-side checks of the product library: it loads, exports every symbol include/clothgpu.h declares, validates its
+arguments on the host and refuses to compute without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from cloth_sim_self_collision_b200 import clothgpu as G
+from cloth_sim_self_collision_b200 import scenes as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(G.LIB_PATH):
+        G.build()
+    return G.load()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "clothgpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(clothgpu_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_exports_every_declared_symbol(lib):
+    syms = declared_symbols()
+    assert len(syms) >= 40
+    for s in syms:
+        assert hasattr(lib, s), "libclothgpu.so does not export %s" % s
+
+
+def test_version_and_struct_layout(lib):
+    assert lib.clothgpu_version() == 100
+    # clothgpu_params: 10 doubles, 2 ints, 4 doubles
+    assert C.sizeof(G.Params) == 10 * 8 + 2 * 4 + 4 * 8
+
+
+def test_argument_validation_and_no_cpu_fallback(lib):
+    sc = S.square_cloth_xz(2, 3, 0.1)
+    h = C.c_void_p()
+    bad_tri = sc["tri"].copy()
+    bad_tri[0] = sc["np"] + 5
+
+    def create(tri=sc["tri"], colidx=sc["colidx"]):
+        ip = lambda a: np.ascontiguousarray(a, dtype=np.int32).ctypes.data_as(C.POINTER(C.c_int))
+        return lib.clothgpu_create(C.byref(h), -1, 1, sc["np"], sc["ntri"], sc["nquad"], ip(tri), ip(sc["quad"]),
+                                   ip(sc["bc"]), sc["xyz0"].ctypes.data_as(C.POINTER(C.c_double)), ip(sc["rowptr"]),
+                                   ip(colidx), 0, None, None, None)
+
+    assert create(tri=bad_tri) == 1  # CLOTHGPU_ERR_ARG
+    assert b"triangle" in lib.clothgpu_last_error()
+    bad_col = sc["colidx"].copy()
+    bad_col[:2] = bad_col[:2][::-1]
+    assert create(colidx=bad_col) == 1
+    if lib.clothgpu_device_count() == 0:
+        assert create() == 2  # CLOTHGPU_ERR_CUDA: no silent CPU path
+        assert b"no CPU fallback" in lib.clothgpu_last_error()
+        with pytest.raises(G.ClothGPUError):
+            G.ClothGPU(sc, with_bvh=False)
+
+
+def test_median_split_bvh_is_a_valid_tree():
+    sc = S.square_cloth_xz(7, 5, 0.1)
+    nodes = S.median_split_bvh(sc)
+    ntri = sc["ntri"]
+    assert nodes.shape == (2 * ntri - 1, 3) and nodes[0, 0] == -1
+    leaves = nodes[nodes[:, 2] == -1]
+    assert sorted(leaves[:, 1].tolist()) == list(range(ntri))
+    for i, (par, c0, c1) in enumerate(nodes):
+        if c1 != -1:
+            assert nodes[c0, 0] == i and nodes[c1, 0] == i and c0 > i and c1 > i

@@ -1,0 +1,418 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the committed golden vectors.
+
+Bars:
+  * integer / index work (leaf-pair sets, contact elements incl. is_fv, impact-zone partitions): exact
+  * assembly, SpMV, ILU factor, triangular solves, boxes, impulses, impact-zone velocities: bit-exact (same
+    per-entry operation order, compiled without FMA contraction)
+  * anything downstream of a dot product (PCG / CG iterates, whole steps): relative 1e-9 here, the north star asks
+    for 1e-5 (the dot products are tree sums, the reference's are serial sums)
+"""
+import os
+
+import numpy as np
+import pytest
+
+from cloth_sim_self_collision_b200 import clothgpu as G
+from cloth_sim_self_collision_b200 import scenes as S
+from tests import common as T
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1.0e-9
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1.0e-300))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLD, "phases_5x21.npz"))
+
+
+@pytest.fixture(scope="module")
+def sc_contact(gold):
+    sc = S.square_cloth_xz(4, 20, 0.1, S.SELF_CONTACT["areal_density"])
+    sc["bvh"] = np.ascontiguousarray(gold["bvh"])
+    return sc
+
+
+@pytest.fixture(scope="module")
+def sc_internal():
+    return S.square_cloth_xy(12, 1.0)
+
+
+def _cases(sc_contact, sc_internal):
+    p1 = T.params_for(sc_contact, S.SELF_CONTACT, col_par=(0.2, 0, 0, 0))
+    p2 = T.params_for(sc_internal, S.INTERNAL_CLOTH, col_kind=2, col_par=(0.3, 0.5, -0.1, 0.3))
+    return [(sc_contact, p1), (sc_internal, p2)]
+
+
+def test_linear_system_pipeline(oracle, sc_contact, sc_internal):
+    for sc, p in _cases(sc_contact, sc_internal):
+        g = G.ClothGPU(sc, with_bvh=False)
+        x, v = T.wavy_state(sc)
+        g.upload_state(x, v)
+        g.assemble(p)
+        dia, crs, b = oracle.assemble(sc, x, v, p)
+        assert np.array_equal(g.read(G.BUF_VAL_DIA), dia)
+        assert np.array_equal(g.read(G.BUF_VAL_CRS), crs)
+        assert np.array_equal(g.read(G.BUF_VEC_R), b)
+        rng = np.random.default_rng(5)
+        xx = rng.standard_normal(sc["np"] * 3)
+        yy = rng.standard_normal(sc["np"] * 3)
+        for alpha, beta in [(1.0, 0.0), (-0.7, 1.3)]:
+            g.write(G.BUF_VEC_P, xx)
+            g.write(G.BUF_VEC_Z, yy)
+            g.matvec(alpha, G.BUF_VEC_P, beta, G.BUF_VEC_Z)
+            assert np.array_equal(g.read(G.BUF_VEC_Z), oracle.matvec(sc, dia, crs, alpha, xx, beta, yy))
+        g.write(G.BUF_VEC_Z, yy)
+        d = g.dot(G.BUF_VEC_P, G.BUF_VEC_Z)[0]
+        assert abs(d - oracle.dot(xx, yy)) <= 1.0e-13 * np.abs(xx * yy).sum()
+        g.axpy(0.37, G.BUF_VEC_P, G.BUF_VEC_Z)
+        assert np.array_equal(g.read(G.BUF_VEC_Z), yy + 0.37 * xx)
+        # ILU(0)
+        g.ilu_setvalue()
+        g.ilu_factor()
+        idia, icrs = oracle.ilu_factor(sc, dia, crs)
+        assert np.array_equal(g.read(G.BUF_ILU_DIA), idia)
+        assert np.array_equal(g.read(G.BUF_ILU_CRS), icrs)
+        g.write(G.BUF_VEC_P, xx)
+        g.ilu_solve(G.BUF_VEC_P)
+        assert np.array_equal(g.read(G.BUF_VEC_P), oracle.ilu_solve(sc, idia, icrs, xx))
+        # PCG / CG
+        ox, orr, ocr, oit = oracle.pcg(sc, dia, crs, idia, icrs, b)
+        cr, it = g.pcg()
+        assert it[0] == oit
+        assert rel_err(g.read(G.BUF_VEC_X), ox) < RTOL
+        assert abs(cr[0] - ocr) <= 1.0e-6 * ocr
+        g.write(G.BUF_VEC_R, b)
+        ox, orr, ocr, oit = oracle.cg(sc, dia, crs, b, 1.0e-4, 1000)
+        cr, it = g.cg(1.0e-4, 1000)
+        assert it[0] == oit
+        assert rel_err(g.read(G.BUF_VEC_X), ox) < 1.0e-7
+        assert abs(cr[0] - ocr) <= 1.0e-5 * ocr
+        # zero right-hand side: early out (ilu_sparse.cpp:651)
+        g.write(G.BUF_VEC_R, np.zeros(sc["np"] * 3))
+        cr, it = g.pcg()
+        assert (cr[0], it[0]) == (0.0, 0)
+        assert not g.read(G.BUF_VEC_X).any()
+        # gradient-only fix-up
+        g.upload_state(x, v)
+        g.update_intermediate_velocity(p)
+        assert np.array_equal(g.download_state()[1], oracle.update_intermediate_velocity(sc, x, v, p))
+        g.close()
+
+
+def test_golden_linear_phases(gold, sc_contact):
+    """The committed vectors were produced by the UNMODIFIED reference (oracle/make_golden.py)."""
+    sc = sc_contact
+    p = T.params_for(sc, S.SELF_CONTACT, col_par=tuple(gold["col_par"]))
+    g = G.ClothGPU(sc, with_bvh=False)
+    g.upload_state(gold["x"], gold["v"])
+    g.assemble(p)
+    assert np.array_equal(g.read(G.BUF_VAL_DIA), gold["dia"])
+    assert np.array_equal(g.read(G.BUF_VAL_CRS), gold["crs"])
+    assert np.array_equal(g.read(G.BUF_VEC_R), gold["b"])
+    g.ilu_setvalue()
+    g.ilu_factor()
+    assert np.array_equal(g.read(G.BUF_ILU_DIA), gold["idia"])
+    assert np.array_equal(g.read(G.BUF_ILU_CRS), gold["icrs"])
+    g.write(G.BUF_VEC_P, gold["vec"])
+    g.write(G.BUF_VEC_Z, gold["yv"])
+    g.matvec(1.0, G.BUF_VEC_P, 0.0, G.BUF_VEC_Z)
+    assert np.array_equal(g.read(G.BUF_VEC_Z), gold["matvec"])
+    g.write(G.BUF_VEC_Z, gold["yv"])
+    g.matvec(-0.7, G.BUF_VEC_P, 1.3, G.BUF_VEC_Z)
+    assert np.array_equal(g.read(G.BUF_VEC_Z), gold["matvec_ab"])
+    g.ilu_solve(G.BUF_VEC_P)
+    assert np.array_equal(g.read(G.BUF_VEC_P), gold["ilu_solve"])
+    cr, it = g.pcg()
+    assert it[0] == int(gold["pcg_iter"])
+    assert rel_err(g.read(G.BUF_VEC_X), gold["pcg_x"]) < RTOL
+    g.upload_state(gold["x"], gold["v"])
+    g.update_intermediate_velocity(p)
+    assert np.array_equal(g.download_state()[1], gold["upd_v"])
+    g.close()
+
+
+def _sorted_pairs(p):
+    p = np.asarray(p).reshape(-1, 2)
+    return p[np.lexsort((p[:, 1], p[:, 0]))]
+
+
+def test_golden_contact_phases(gold, sc_contact):
+    sc = sc_contact
+    c = S.SELF_CONTACT
+    g = G.ClothGPU(sc)
+    fx, fv = gold["fx"], gold["fv"]
+    g.write(G.BUF_XYZ_PREV, fx)
+    g.write(G.BUF_UVW, fv)
+    # proximity
+    g.bvh_refit_prx(G.BUF_XYZ_PREV, c["clearance"])
+    assert np.array_equal(g.read(G.BUF_BOXES).reshape(-1, 6), gold["box_prx"])
+    n = g.contacts_prx(G.BUF_XYZ_PREV, c["clearance"])[0]
+    assert np.array_equal(_sorted_pairs(g.leaf_pairs()), _sorted_pairs(gold["leaf_pairs_prx"]))
+    assert np.array_equal(g.elems(n), gold["elems_prx"])
+    g.impulse_prx(G.BUF_XYZ_PREV, G.BUF_UVW, c["clearance"], c["stiff_contact"], c["dt"], sc["mass_point"])
+    assert np.array_equal(g.read(G.BUF_UVW), gold["v_after_prx"])
+    # CCD
+    g.bvh_refit_ccd(G.BUF_XYZ_PREV, G.BUF_UVW, c["dt"])
+    assert np.array_equal(g.read(G.BUF_BOXES).reshape(-1, 6), gold["box_ccd"])
+    n = g.contacts_ccd(G.BUF_XYZ_PREV, G.BUF_UVW, c["dt"], c["clearance"])[0]
+    assert np.array_equal(_sorted_pairs(g.leaf_pairs()), _sorted_pairs(gold["leaf_pairs_ccd"]))
+    assert np.array_equal(g.elems(n), gold["elems_ccd"])
+    assert n > 0
+    g.impulse_ccd(G.BUF_XYZ_PREV, G.BUF_UVW, c["clearance"], c["stiff_contact"], c["dt"], sc["mass_point"])
+    assert np.array_equal(g.read(G.BUF_UVW), gold["v_after_ccd"])
+    # impact zones on the same elements
+    g.write(G.BUF_UVW0, gold["v_after_ccd"])
+    g.riz_reset()
+    g.riz_make()
+    _check_partition(g.read(G.BUF_ZONE), gold["riz_zone"])
+    g.riz_apply(G.BUF_XYZ_PREV, G.BUF_UVW)
+    assert np.array_equal(g.read(G.BUF_UVW), gold["v_after_riz"])
+    # the whole resolution from the same start
+    p = T.params_for(sc, c)
+    g.write(G.BUF_XYZ_PREV, fx)
+    g.write(G.BUF_UVW, fv)
+    applied, stats = g.resolve_self_contact(p)
+    assert np.array_equal(g.read(G.BUF_UVW), gold["resolve_v"])
+    assert int(applied[0]) == int(gold["resolve_applied"])
+    assert np.array_equal(stats[0][:5], gold["resolve_stats"][:5])
+    assert np.array_equal(stats[0][8:116], gold["resolve_stats"][8:116])
+    g.close()
+
+
+def _check_partition(label_gpu, zone_ref):
+    """Same partition of the member vertices (zone numbering differs: smallest vertex id vs creation order)."""
+    label_gpu = np.asarray(label_gpu)
+    zone_ref = np.asarray(zone_ref)
+    assert np.array_equal(label_gpu >= 0, zone_ref >= 0)
+    m = label_gpu >= 0
+    pairs = set(zip(label_gpu[m].tolist(), zone_ref[m].tolist()))
+    assert len(pairs) == len(set(label_gpu[m].tolist())) == len(set(zone_ref[m].tolist()))
+
+
+def _contact_pipeline_vs_oracle(oracle, sc, x, v, c, rounds=3):
+    """Teacher-forced comparison of every contact phase against the oracle on one state."""
+    g = G.ClothGPU(sc)
+    g.write(G.BUF_XYZ_PREV, x)
+    g.write(G.BUF_UVW, v)
+    found = {}
+    g.bvh_refit_prx(G.BUF_XYZ_PREV, c["clearance"])
+    bp = oracle.refit_prx(sc, x, c["clearance"])
+    assert np.array_equal(g.read(G.BUF_BOXES).reshape(-1, 6), bp)
+    n = g.contacts_prx(G.BUF_XYZ_PREV, c["clearance"])[0]
+    assert np.array_equal(_sorted_pairs(g.leaf_pairs()), _sorted_pairs(oracle.leaf_pairs(sc, bp)))
+    ep = oracle.contacts_prx(sc, bp, x, c["clearance"])
+    assert np.array_equal(g.elems(n), ep)
+    found["prx"] = n
+    g.impulse_prx(G.BUF_XYZ_PREV, G.BUF_UVW, c["clearance"], c["stiff_contact"], c["dt"], sc["mass_point"])
+    v1 = oracle.impulse_prx(v, c["clearance"], c["stiff_contact"], c["dt"], sc["mass_point"], x, ep)
+    assert np.array_equal(g.read(G.BUF_UVW), v1)
+    riz = oracle.riz_new()
+    g.riz_reset()
+    v0 = None
+    for r in range(rounds):
+        g.bvh_refit_ccd(G.BUF_XYZ_PREV, G.BUF_UVW, c["dt"])
+        bc = oracle.refit_ccd(sc, x, v1, c["dt"])
+        assert np.array_equal(g.read(G.BUF_BOXES).reshape(-1, 6), bc)
+        n = g.contacts_ccd(G.BUF_XYZ_PREV, G.BUF_UVW, c["dt"], c["clearance"])[0]
+        assert np.array_equal(_sorted_pairs(g.leaf_pairs()), _sorted_pairs(oracle.leaf_pairs(sc, bc)))
+        ec = oracle.contacts_ccd(sc, bc, x, v1, c["dt"], c["clearance"])
+        assert np.array_equal(g.elems(n), ec)
+        found["ccd%d" % r] = n
+        if n == 0:
+            break
+        if r == 0:
+            g.impulse_ccd(G.BUF_XYZ_PREV, G.BUF_UVW, c["clearance"], c["stiff_contact"], c["dt"], sc["mass_point"])
+            v1 = oracle.impulse_ccd(v1, c["clearance"], c["stiff_contact"], c["dt"], sc["mass_point"], x, ec)
+            assert np.array_equal(g.read(G.BUF_UVW), v1)
+            v0 = v1.copy()
+            g.write(G.BUF_UVW0, v0)
+        else:
+            g.riz_make()
+            riz.make(ec, sc)
+            _check_partition(g.read(G.BUF_ZONE), riz.zones(sc["np"])[1])
+            g.riz_apply(G.BUF_XYZ_PREV, G.BUF_UVW)
+            v1 = riz.apply(v1, x, v0)
+            assert np.array_equal(g.read(G.BUF_UVW), v1)
+    g.close()
+    return found
+
+
+def test_contact_pipeline_small_folded(oracle, sc_contact):
+    x, v = T.folded_state(sc_contact, gap=0.004, vel=10.0)
+    found = _contact_pipeline_vs_oracle(oracle, sc_contact, x, v, S.SELF_CONTACT)
+    assert found["prx"] > 0 and found["ccd0"] > 0
+
+
+def _scene_with_bvh(oracle, nx, nz):
+    """BVH topology: any valid binary tree over the triangles is an input shared by both sides; build a balanced
+    median-split tree here so that the test does not need the reference builder."""
+    sc = S.square_cloth_xz(nx, nz, 0.1, S.SELF_CONTACT["areal_density"])
+    sc["bvh"] = S.median_split_bvh(sc)
+    return sc
+
+
+def test_contact_pipeline_48x48_folded(oracle):
+    sc = _scene_with_bvh(oracle, 47, 47)
+    x, v = T.folded_state(sc, gap=0.006, vel=6.0)
+    found = _contact_pipeline_vs_oracle(oracle, sc, x, v, S.SELF_CONTACT, rounds=4)
+    assert found["prx"] > 100 and found["ccd0"] > 100
+
+
+def test_resolve_and_step_vs_oracle(oracle):
+    sc = _scene_with_bvh(oracle, 23, 40)
+    c = S.SELF_CONTACT
+    p = T.params_for(sc, c)
+    x, v = T.folded_state(sc, gap=0.006, vel=4.0)
+    g = G.ClothGPU(sc)
+    # GetIntermidiateVelocityContactResolved
+    g.write(G.BUF_XYZ_PREV, x)
+    g.write(G.BUF_UVW, v)
+    applied, stats = g.resolve_self_contact(p)
+    sim = oracle.sim(sc)
+    ov, oapplied, ostats = sim.resolve_contacts(v, x, p)
+    assert bool(applied[0]) == oapplied
+    assert np.array_equal(stats[0][1:5], ostats[1:5])
+    assert np.array_equal(stats[0][8:116], ostats[8:116])
+    assert np.array_equal(g.read(G.BUF_UVW), ov)
+    assert ostats[1] > 0 and ostats[2] > 0
+    # StepTime, teacher forced over a few steps
+    for step in range(4):
+        g.upload_state(x, v)
+        sim.set_state(x, v)
+        st = g.step_self_contact(p)[0]
+        ost = sim.step_self_contact(p)
+        gx, gv = g.download_state()
+        x, v = sim.get_state()
+        assert st[0] == ost[0], "PCG iterations"
+        assert np.array_equal(st[1:5], ost[1:5])
+        assert rel_err(gx, x) < RTOL and rel_err(gv, v) < RTOL
+    g.close()
+
+
+def test_internal_trajectory_golden():
+    """Config-2 family: 17 x 17 pinned sheet falling onto a sphere, 40 free-running steps (reference vectors)."""
+    gold = np.load(os.path.join(GOLD, "traj_internal17.npz"))
+    sc = S.square_cloth_xy(16, 1.0)
+    p = T.params_for(sc, S.INTERNAL_CLOTH, col_kind=2, col_par=(0.1, 0.5, -0.8, 0.3))
+    g = G.ClothGPU(sc, with_bvh=False)
+    its = []
+    k = 0
+    for step in range(1, 41):
+        its.append(int(g.step_internal(p)[0]))
+        if step == int(gold["steps"][k]):
+            x, v = g.download_state()
+            assert rel_err(x, gold["x"][k]) < 1.0e-8 and rel_err(v, gold["v"][k]) < 1.0e-7
+            k += 1
+    assert its == list(gold["iters"])
+    g.close()
+
+
+def test_config1_trajectory_golden():
+    """Config 1: the default self_contact_sparse scene, free running.  Contact decisions are threshold tests, so a
+    free run can fork from the reference after many steps; the bar here is the pre-fork stretch plus teacher-forced
+    agreement, the drift is reported."""
+    gold = np.load(os.path.join(GOLD, "traj_config1.npz"))
+    sc = S.config1_default()
+    sc["bvh"] = np.ascontiguousarray(gold["bvh"])
+    p = T.params_for(sc, S.SELF_CONTACT)
+    g = G.ClothGPU(sc)
+    keep = list(gold["steps"])
+    errs = {}
+    for step in range(1, 101):
+        st = g.step_self_contact(p)[0]
+        if step <= 40:
+            assert np.array_equal(st[:5], gold["stats"][step - 1][:5]), step
+        if step in keep:
+            k = keep.index(step)
+            x, v = g.download_state()
+            errs[step] = (rel_err(x, gold["x"][k]), rel_err(v, gold["v"][k]))
+    print("free-run drift vs reference:", errs)
+    for step in (10, 35, 36, 40):
+        assert errs[step][0] < 1.0e-8 and errs[step][1] < 1.0e-6, errs
+    g.close()
+
+
+def test_batch_equals_single(oracle, sc_contact):
+    """Scenes of a batch are independent: each one matches the same scene run alone (bit for bit)."""
+    sc = sc_contact
+    p = T.params_for(sc, S.SELF_CONTACT)
+    states = [T.folded_state(sc, seed=3 + k, gap=0.004 + 0.001 * k, vel=10.0 - 3.0 * k) for k in range(3)]
+    states.append(T.wavy_state(sc))  # a scene without self contact: leaves the pipeline early
+    singles = []
+    for x, v in states:
+        g = G.ClothGPU(sc)
+        g.upload_state(x, v)
+        st = g.step_self_contact(p, 2)
+        singles.append((g.download_state(), st[0].copy()))
+        g.close()
+    gb = G.ClothGPU(sc, nscene=len(states))
+    for s, (x, v) in enumerate(states):
+        gb.upload_state(x, v, scene=s)
+    st = gb.step_self_contact(p, 2)
+    for s in range(len(states)):
+        x, v = gb.download_state(scene=s)
+        assert np.array_equal(x, singles[s][0][0]) and np.array_equal(v, singles[s][0][1])
+        assert np.array_equal(st[s], singles[s][1])
+    gb.close()
+
+
+def test_large_scene_properties(oracle):
+    """256 x 256 (BASELINE.json config 3) at full size through size-independent properties: the matrix the GPU
+    assembles is symmetric block-wise, A x matches a float128-free re-evaluation on sampled rows via the oracle's
+    SpMV on the GPU's own matrix, ILU solve inverts the factors, and contact sets are sorted and unique."""
+    sc = S.config3_256()
+    sc["bvh"] = S.median_split_bvh(sc)
+    p = T.params_for(sc, S.SELF_CONTACT)
+    x, v = T.folded_state(sc, gap=0.006, vel=3.0)
+    g = G.ClothGPU(sc)
+    g.upload_state(x, v)
+    g.assemble(p)
+    dia = g.read(G.BUF_VAL_DIA)
+    crs = g.read(G.BUF_VAL_CRS)
+    # block symmetry: A_ij = A_ji^T
+    rp, ci = sc["rowptr"], sc["colidx"]
+    rows = np.repeat(np.arange(sc["np"]), np.diff(rp))
+    key = rows.astype(np.int64) * sc["np"] + ci
+    tkey = ci.astype(np.int64) * sc["np"] + rows
+    pos = np.searchsorted(key, tkey)
+    assert np.array_equal(key[pos], tkey)
+    blk = crs.reshape(-1, 3, 3)
+    assert np.abs(blk - blk[pos].transpose(0, 2, 1)).max() <= 1.0e-9 * np.abs(blk).max()
+    # SpMV and triangular solves against the oracle on the GPU's own matrices (bit-exact paths)
+    rng = np.random.default_rng(1)
+    xx = rng.standard_normal(sc["np"] * 3)
+    g.write(G.BUF_VEC_P, xx)
+    g.matvec(1.0, G.BUF_VEC_P, 0.0, G.BUF_VEC_Z)
+    assert np.array_equal(g.read(G.BUF_VEC_Z), oracle.matvec(sc, dia, crs, 1.0, xx, 0.0, np.zeros_like(xx)))
+    g.ilu_setvalue()
+    g.ilu_factor()
+    idia, icrs = oracle.ilu_factor(sc, dia, crs)
+    assert np.array_equal(g.read(G.BUF_ILU_DIA), idia) and np.array_equal(g.read(G.BUF_ILU_CRS), icrs)
+    g.ilu_solve(G.BUF_VEC_P)
+    assert np.array_equal(g.read(G.BUF_VEC_P), oracle.ilu_solve(sc, idia, icrs, xx))
+    # contact sets: sorted, unique, canonical
+    g.write(G.BUF_XYZ_PREV, x)
+    g.bvh_refit_ccd(G.BUF_XYZ_PREV, G.BUF_UVW, p.dt)
+    n = g.contacts_ccd(G.BUF_XYZ_PREV, G.BUF_UVW, p.dt, p.clearance)[0]
+    e = g.elems(n)
+    assert n > 1000
+    k = e[:, :4].astype(np.int64)
+    order = np.lexsort((k[:, 3], k[:, 2], k[:, 1], k[:, 0]))
+    assert np.array_equal(order, np.arange(n))
+    assert len(np.unique(k, axis=0)) == n
+    fv = e[:, 4] == 1
+    assert np.all(k[fv, 0] < k[fv, 1]) and np.all(k[fv, 1] < k[fv, 2])
+    assert np.all(k[~fv, 0] < k[~fv, 1]) and np.all(k[~fv, 2] < k[~fv, 3]) and np.all(k[~fv, 0] < k[~fv, 2])
+    # and the oracle agrees on the set (about 10 s of CPU)
+    bc = oracle.refit_ccd(sc, x, v, p.dt)
+    assert np.array_equal(g.read(G.BUF_BOXES).reshape(-1, 6), bc)
+    assert np.array_equal(e, oracle.contacts_ccd(sc, bc, x, v, p.dt, p.clearance))
+    g.close()
