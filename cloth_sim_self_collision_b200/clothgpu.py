@@ -207,6 +207,19 @@ class ClothGPU:
         self._check(self.lib.clothgpu_phase_ms(self.h, _dp(out)))
         return dict(zip(PHASE_NAMES, out[:len(PHASE_NAMES)]))
 
+    def set_kernel_timing(self, on):
+        self._check(self.lib.clothgpu_set_kernel_timing(self.h, 1 if on else 0))
+
+    def kernel_times(self):
+        """{kernel name: (launches, total ms)} accumulated since set_kernel_timing(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self.lib.clothgpu_kernel_times(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.split()
+            out[name] = (int(n), float(ms))
+        return out
+
     # ------------------------------------------------------------------ implicit step
     def assemble(self, p):
         p = params_from(p)

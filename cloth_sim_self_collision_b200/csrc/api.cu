@@ -345,7 +345,7 @@ int clothgpu_step_self_contact(clothgpu_ctx* c, const clothgpu_params* p, int ns
       CG_CHECK(set_active(c, applied.data()));
       phase_begin(c);
       dim3 g(std::min(div_up(c->ndof, 256), 296), c->B);
-      k_reintegrate<<<g, 256, 0, c->stream>>>(c->ndof, p->dt, c->xyz_prev, c->uvw, c->xyz, c->cnt);
+      k_reintegrate<<<g, 256, 0, KS(c, "k_reintegrate")>>>(c->ndof, p->dt, c->xyz_prev, c->uvw, c->xyz, c->cnt);
       CG_LAUNCH_CHECK(c);
       CG_CHECK(launch_update_velocity(c, *p));
       phase_end(c, 8);

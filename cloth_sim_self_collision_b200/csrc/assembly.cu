@@ -415,19 +415,19 @@ static int upload_gravity(Ctx* c, const clothgpu_params& p) {
 
 static int element_pass(Ctx* c, const clothgpu_params& p, bool with_hessian) {
   if (p.stiff_bend != c->quad_stiff) {
-    k_quad_rest<<<div_up(c->nquad, 128), 128, 0, c->stream>>>(c->nquad, c->quad, c->xyz0, p.stiff_bend, c->quadK, c->quadT);
+    k_quad_rest<<<div_up(c->nquad, 128), 128, 0, KS(c, "k_quad_rest")>>>(c->nquad, c->quad, c->xyz0, p.stiff_bend, c->quadK, c->quadT);
     CG_LAUNCH_CHECK(c);
     c->quad_stiff = p.stiff_bend;
   }
   if (c->ntri > 0) {
     dim3 g(div_up(c->ntri, 128), c->B);
-    k_tri_elements<<<g, 128, 0, c->stream>>>(c->ntri, c->np, c->tri, c->xyz0, c->xyz, p.lambda, p.myu, c->tri_dW,
+    k_tri_elements<<<g, 128, 0, KS(c, "k_tri_elements")>>>(c->ntri, c->np, c->tri, c->xyz0, c->xyz, p.lambda, p.myu, c->tri_dW,
                                              with_hessian ? c->tri_ddW : nullptr);
     CG_LAUNCH_CHECK(c);
   }
   if (c->nquad > 0) {
     dim3 g(div_up(c->nquad, 128), c->B);
-    k_quad_elements<<<g, 128, 0, c->stream>>>(c->nquad, c->np, c->quad, c->xyz, c->quadK, c->quadT, c->quad_dW);
+    k_quad_elements<<<g, 128, 0, KS(c, "k_quad_elements")>>>(c->nquad, c->np, c->quad, c->xyz, c->quadK, c->quadT, c->quad_dW);
     CG_LAUNCH_CHECK(c);
   }
   return CLOTHGPU_OK;
@@ -443,14 +443,14 @@ int launch_assemble(Ctx* c, const clothgpu_params& p, bool with_hessian) {
   for (int k = 0; k < 4; k++) P.col_par[k] = p.collider_par[k];
   {
     dim3 g(div_up(c->np, 128), c->B);
-    k_gather_vertex<<<g, 128, 0, c->stream>>>(c->np, c->ntri, c->nquad, P, c->bc, c->vt_ptr, c->vt_ent, c->vq_ptr,
+    k_gather_vertex<<<g, 128, 0, KS(c, "k_gather_vertex")>>>(c->np, c->ntri, c->nquad, P, c->bc, c->vt_ptr, c->vt_ent, c->vq_ptr,
                                               c->vq_ent, c->xyz, c->uvw, c->gravity, c->col_table, c->tri_dW,
                                               c->tri_ddW, c->quad_dW, c->quadK, c->quadT, c->valDia, c->vec_r);
     CG_LAUNCH_CHECK(c);
   }
   if (c->ncrs > 0) {
     dim3 g(div_up(c->ncrs, 128), c->B);
-    k_gather_slot<<<g, 128, 0, c->stream>>>(c->np, c->ncrs, c->ntri, c->bc, c->slot_row, c->colidx, c->st_ptr,
+    k_gather_slot<<<g, 128, 0, KS(c, "k_gather_slot")>>>(c->np, c->ncrs, c->ntri, c->bc, c->slot_row, c->colidx, c->st_ptr,
                                             c->st_ent, c->sq_ptr, c->sq_ent, c->tri_ddW, c->quadK, c->quadT, c->valCrs);
     CG_LAUNCH_CHECK(c);
   }
@@ -461,7 +461,7 @@ int launch_update_velocity(Ctx* c, const clothgpu_params& p) {
   CG_CHECK(upload_gravity(c, p));
   CG_CHECK(element_pass(c, p, false));
   dim3 g(div_up(c->np, 128), c->B);
-  k_gather_velocity<<<g, 128, 0, c->stream>>>(c->np, c->ntri, c->nquad, p.dt, p.mass_point, c->bc, c->vt_ptr,
+  k_gather_velocity<<<g, 128, 0, KS(c, "k_gather_velocity")>>>(c->np, c->ntri, c->nquad, p.dt, p.mass_point, c->bc, c->vt_ptr,
                                               c->vt_ent, c->vq_ptr, c->vq_ent, c->gravity, c->tri_dW, c->quad_dW, c->uvw, c->cnt);
   CG_LAUNCH_CHECK(c);
   return CLOTHGPU_OK;

@@ -359,17 +359,17 @@ __global__ void k_set_active(int* cnt, int v) { cnt[blockIdx.x * NCNT + CNT_ACTI
 int launch_refit(Ctx* c, const double* xyz, const double* uvw, double par, int mode) {
   CG_CUDA(cudaMemsetAsync(c->refit_flag, 0, sizeof(int) * (size_t)c->B * c->nnode, c->stream));
   dim3 g(div_up(c->nnode, 256), c->B);
-  k_refit<<<g, 256, 0, c->stream>>>(c->nnode, c->np, c->nodes, c->tri, xyz, uvw, par, mode, c->boxes, c->refit_flag, c->cnt);
+  k_refit<<<g, 256, 0, KS(c, "k_refit")>>>(c->nnode, c->np, c->nodes, c->tri, xyz, uvw, par, mode, c->boxes, c->refit_flag, c->cnt);
   CG_LAUNCH_CHECK(c);
   return CLOTHGPU_OK;
 }
 
 static int traverse_and_test(Ctx* c, const double* xyz, const double* uvw, double dt, double delta, int ccd) {
-  k_trav_reset<<<c->B, 64, 0, c->stream>>>(c->cnt);
+  k_trav_reset<<<c->B, 64, 0, KS(c, "k_trav_reset")>>>(c->cnt);
   CG_LAUNCH_CHECK(c);
   {
     dim3 g(div_up(c->ninternal, 256), c->B);
-    k_trav_init<<<g, 256, 0, c->stream>>>(c->ninternal, c->internal_list, c->nodes, c->pre, c->frontA, c->cap_front, c->cnt);
+    k_trav_init<<<g, 256, 0, KS(c, "k_trav_init")>>>(c->ninternal, c->internal_list, c->nodes, c->pre, c->frontA, c->cap_front, c->cnt);
     CG_LAUNCH_CHECK(c);
   }
   // every descent moves at least one side of the pair one level down: bvh_height + 1 steps reach all leaf pairs
@@ -377,12 +377,12 @@ static int traverse_and_test(Ctx* c, const double* xyz, const double* uvw, doubl
     dim3 g(148 * 4, c->B);
     PairEnt* fin = (d & 1) ? c->frontB : c->frontA;
     PairEnt* fout = (d & 1) ? c->frontA : c->frontB;
-    k_trav_step<<<g, 256, 0, c->stream>>>(d, c->nnode, c->nodes, c->boxes, fin, fout, c->cap_front, c->leaf, c->cap_leaf, c->cnt);
+    k_trav_step<<<g, 256, 0, KS(c, "k_trav_step")>>>(d, c->nnode, c->nodes, c->boxes, fin, fout, c->cap_front, c->leaf, c->cap_leaf, c->cnt);
     CG_LAUNCH_CHECK(c);
   }
   {
     dim3 g(148 * 8, c->B);
-    k_narrow<<<g, 128, 0, c->stream>>>(ccd, c->nnode, c->np, c->nodes, c->tri, c->boxes, xyz, uvw, dt, delta, c->leaf,
+    k_narrow<<<g, 128, 0, KS(c, "k_narrow")>>>(ccd, c->nnode, c->np, c->nodes, c->tri, c->boxes, xyz, uvw, dt, delta, c->leaf,
                                        c->cap_leaf, c->raw, c->cap_raw, c->cnt);
     CG_LAUNCH_CHECK(c);
   }
@@ -407,11 +407,11 @@ static int canonical_set(Ctx* c, int s, int nraw) {
   CG_CHECK(ensure_scratch(c, std::max(tb, tb2)));
   CG_CUDA(cub::DeviceMergeSort::SortKeys(c->scratch, tb, raw, nraw, RawLess(), c->stream));
   c->launches += 2;
-  k_mark_unique<<<div_up(nraw, 256), 256, 0, c->stream>>>(nraw, raw, flag);
+  k_mark_unique<<<div_up(nraw, 256), 256, 0, KS(c, "k_mark_unique")>>>(nraw, raw, flag);
   CG_LAUNCH_CHECK(c);
   CG_CUDA(cub::DeviceScan::ExclusiveSum(c->scratch, tb2, flag, pos, nraw, c->stream));
   c->launches += 2;
-  k_compact_elems<<<div_up(nraw, 256), 256, 0, c->stream>>>(nraw, raw, flag, pos, c->elems + (size_t)s * c->cap_elem * 5,
+  k_compact_elems<<<div_up(nraw, 256), 256, 0, KS(c, "k_compact_elems")>>>(nraw, raw, flag, pos, c->elems + (size_t)s * c->cap_elem * 5,
                                                             c->cap_elem, cnt);
   CG_LAUNCH_CHECK(c);
   return CLOTHGPU_OK;
@@ -446,7 +446,7 @@ int run_contacts(Ctx* c, const double* xyz, const double* uvw, double dt, double
 }
 
 int set_all_active(Ctx* c, int v) {
-  k_set_active<<<c->B, 1, 0, c->stream>>>(c->cnt, v);
+  k_set_active<<<c->B, 1, 0, KS(c, "k_set_active")>>>(c->cnt, v);
   CG_LAUNCH_CHECK(c);
   return CLOTHGPU_OK;
 }

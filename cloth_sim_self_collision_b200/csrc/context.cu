@@ -116,6 +116,23 @@ int fetch_counters(Ctx* c) {
   return CLOTHGPU_OK;
 }
 
+void ktime_begin(Ctx* c, const char* name) {
+  if (!c->ktiming) return;
+  c->kt_name = name;
+  cudaEventRecord(c->kt0, c->stream);
+}
+void ktime_end(Ctx* c) {
+  if (!c->ktiming || !c->kt_name) return;
+  cudaEventRecord(c->kt1, c->stream);
+  cudaEventSynchronize(c->kt1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->kt0, c->kt1);
+  auto& e = c->ktimes[c->kt_name];
+  e.first += ms;
+  e.second += 1;
+  c->kt_name = nullptr;
+}
+
 void phase_begin(Ctx* c) {
   if (c->profiling) cudaEventRecord(c->evp0, c->stream);
 }
@@ -358,6 +375,7 @@ static int create_impl(Ctx* c, int nscene, int np, int ntri, int nquad, const in
   CG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CG_CUDA(cudaEventCreate(&c->ev0)); CG_CUDA(cudaEventCreate(&c->ev1));
   CG_CUDA(cudaEventCreate(&c->evp0)); CG_CUDA(cudaEventCreate(&c->evp1));
+  CG_CUDA(cudaEventCreate(&c->kt0)); CG_CUDA(cudaEventCreate(&c->kt1));
   CG_CHECK(dev_upload(&c->tri, tri, (long long)ntri * 3));
   CG_CHECK(dev_upload(&c->quad, quad, (long long)nquad * 4));
   CG_CHECK(dev_upload(&c->bc, bcflag, np));
@@ -488,6 +506,8 @@ void clothgpu_destroy(clothgpu_ctx* c) {
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->evp0) cudaEventDestroy(c->evp0);
   if (c->evp1) cudaEventDestroy(c->evp1);
+  if (c->kt0) cudaEventDestroy(c->kt0);
+  if (c->kt1) cudaEventDestroy(c->kt1);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -590,6 +610,25 @@ int clothgpu_set_profiling(clothgpu_ctx* c, int on) {
   if (!c) { set_error("null context"); return CLOTHGPU_ERR_ARG; }
   c->profiling = on != 0;
   for (double& v : c->phase_ms) v = 0;
+  return CLOTHGPU_OK;
+}
+int clothgpu_set_kernel_timing(clothgpu_ctx* c, int on) {
+  if (!c) { set_error("null context"); return CLOTHGPU_ERR_ARG; }
+  CG_CUDA(cudaStreamSynchronize(c->stream));
+  c->ktiming = on != 0;
+  c->ktimes.clear();
+  return CLOTHGPU_OK;
+}
+int clothgpu_kernel_times(clothgpu_ctx* c, char* out, int cap) {
+  if (!c || !out || cap < 1) { set_error("bad argument"); return CLOTHGPU_ERR_ARG; }
+  std::string s;
+  char line[256];
+  for (const auto& kv : c->ktimes) {
+    snprintf(line, sizeof(line), "%s %lld %.6f\n", kv.first.c_str(), kv.second.second, kv.second.first);
+    s += line;
+  }
+  if ((int)s.size() + 1 > cap) { set_error("kernel_times: buffer too small"); return CLOTHGPU_ERR_ARG; }
+  memcpy(out, s.c_str(), s.size() + 1);
   return CLOTHGPU_OK;
 }
 int clothgpu_phase_ms(clothgpu_ctx* c, double* ms) {

@@ -4,7 +4,9 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/clothgpu.h"
@@ -61,6 +63,11 @@ struct Ctx {
   long long launches = 0;
   bool profiling = false;
   double phase_ms[CLOTHGPU_NPHASE] = {0};
+  // per-kernel timing (clothgpu_set_kernel_timing): every launch is bracketed by events and synchronised
+  bool ktiming = false;
+  const char* kt_name = nullptr;
+  cudaEvent_t kt0 = nullptr, kt1 = nullptr;
+  std::map<std::string, std::pair<double, long long>> ktimes;  // name -> (total ms, launches)
 
   // ---- shared topology
   int *tri = nullptr, *quad = nullptr, *bc = nullptr, *rowptr = nullptr, *colidx = nullptr, *diaind = nullptr;
@@ -134,13 +141,19 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     int r__ = (call);               \
     if (r__ != CLOTHGPU_OK) return r__; \
   } while (0)
+// stream argument of a kernel launch; in kernel-timing mode it also records the start event
+#define KS(c, name) (cg::ktime_begin((c), (name)), (c)->stream)
 #define CG_LAUNCH_CHECK(c)                                                    \
   do {                                                                        \
     (c)->launches++;                                                          \
+    if ((c)->ktiming) cg::ktime_end(c);                                       \
     cudaError_t e__ = cudaGetLastError();                                     \
     if (e__ != cudaSuccess) return cg::cuda_fail(e__, "kernel launch", __FILE__, __LINE__); \
   } while (0)
 
+struct Ctx;
+void ktime_begin(Ctx* c, const char* name);
+void ktime_end(Ctx* c);
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // buffer lookup: device pointer of one scene's buffer, element size and count

@@ -362,7 +362,7 @@ static dim3 vec_grid(Ctx* c, int n) { return dim3(std::min(div_up(n, 256), c->np
 
 int launch_matvec(Ctx* c, double alpha, const double* x, double beta, double* y) {
   dim3 g(div_up(c->ndof, 256), c->B);
-  k_matvec<<<g, 256, 0, c->stream>>>(c->np, c->ncrs, c->rowptr, c->colidx, c->valDia, c->valCrs, alpha, x, beta, y, nullptr);
+  k_matvec<<<g, 256, 0, KS(c, "k_matvec")>>>(c->np, c->ncrs, c->rowptr, c->colidx, c->valDia, c->valCrs, alpha, x, beta, y, nullptr);
   CG_LAUNCH_CHECK(c);
   return CLOTHGPU_OK;
 }
@@ -371,7 +371,7 @@ static int dot_launch(Ctx* c, const double* a, const double* b, int slot, int po
   DotArgs A;
   A.n = c->ndof; A.post = post; A.slot = slot; A.iter = iter; A.tol2 = tol2;
   dim3 g(std::min(div_up(c->ndof, 256), c->npartial), c->B);
-  k_dot<<<g, 256, 0, c->stream>>>(A, a, b, c->partials, c->scal, c->cnt, c->npartial, skip_done);
+  k_dot<<<g, 256, 0, KS(c, "k_dot")>>>(A, a, b, c->partials, c->scal, c->cnt, c->npartial, skip_done);
   CG_LAUNCH_CHECK(c);
   return CLOTHGPU_OK;
 }
@@ -379,7 +379,7 @@ int launch_dot(Ctx* c, const double* a, const double* b, int scal_slot) {
   return dot_launch(c, a, b, scal_slot, POST_STORE, 0, 0.0, 0);
 }
 int launch_axpy(Ctx* c, double a, const double* x, double* y) {
-  k_axpy<<<vec_grid(c, c->ndof), 256, 0, c->stream>>>(c->ndof, a, x, y);
+  k_axpy<<<vec_grid(c, c->ndof), 256, 0, KS(c, "k_axpy")>>>(c->ndof, a, x, y);
   CG_LAUNCH_CHECK(c);
   return CLOTHGPU_OK;
 }
@@ -389,13 +389,13 @@ int launch_ilu_setvalue(Ctx* c) {
   return CLOTHGPU_OK;
 }
 int launch_ilu_factor(Ctx* c) {
-  k_ilu_factor<<<c->B, 1024, 0, c->stream>>>(c->np, c->ncrs, c->nlev_f, c->lev_f_ptr, c->lev_f_rows, c->rowptr, c->diaind,
+  k_ilu_factor<<<c->B, 1024, 0, KS(c, "k_ilu_factor")>>>(c->np, c->ncrs, c->nlev_f, c->lev_f_ptr, c->lev_f_rows, c->rowptr, c->diaind,
                                              c->op_ptr, c->ops, c->iluDia, c->iluCrs, c->cnt);
   CG_LAUNCH_CHECK(c);
   return CLOTHGPU_OK;
 }
 static int ilu_solve_launch(Ctx* c, double* vec, const double* src, bool skip_done) {
-  k_ilu_solve<<<c->B, 320, 0, c->stream>>>(c->np, c->ncrs, c->nlev_f, c->lev_f_ptr, c->lev_f_rows, c->nlev_b,
+  k_ilu_solve<<<c->B, 320, 0, KS(c, "k_ilu_solve")>>>(c->np, c->ncrs, c->nlev_f, c->lev_f_ptr, c->lev_f_rows, c->nlev_b,
                                            c->lev_b_ptr, c->lev_b_rows, c->rowptr, c->colidx, c->diaind, c->iluDia,
                                            c->iluCrs, vec, src, skip_done ? c->cnt : nullptr);
   CG_LAUNCH_CHECK(c);
@@ -424,12 +424,12 @@ static int fetch_solver_result(Ctx* c, double* conv_out, int* iter_out) {
 int run_pcg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out) {
   const int n = c->ndof;
   const double tol2 = tol * tol;
-  k_pcg_reset<<<c->B, 1, 0, c->stream>>>(c->cnt, c->scal, max_iter, tol);
+  k_pcg_reset<<<c->B, 1, 0, KS(c, "k_pcg_reset")>>>(c->cnt, c->scal, max_iter, tol);
   CG_LAUNCH_CHECK(c);
   CG_CUDA(cudaMemsetAsync(c->vec_x, 0, sizeof(double) * (size_t)c->B * n, c->stream));
   CG_CHECK(dot_launch(c, c->vec_r, c->vec_r, SC_SQ, POST_PCG_INIT, 0, tol2, 0));
   CG_CHECK(ilu_solve_launch(c, c->vec_z, c->vec_r, true));
-  k_copy<<<vec_grid(c, n), 256, 0, c->stream>>>(n, c->vec_z, c->vec_p, c->cnt);
+  k_copy<<<vec_grid(c, n), 256, 0, KS(c, "k_copy")>>>(n, c->vec_z, c->vec_p, c->cnt);
   CG_LAUNCH_CHECK(c);
   int cur = SC_RPR, nxt = SC_DOT;
   CG_CHECK(dot_launch(c, c->vec_r, c->vec_z, cur, POST_STORE, 0, tol2, 1));
@@ -437,7 +437,7 @@ int run_pcg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out) {
   for (int it = 0; it < max_iter; it++) {
     {
       dim3 g(div_up(n, 256), c->B);
-      k_matvec<<<g, 256, 0, c->stream>>>(c->np, c->ncrs, c->rowptr, c->colidx, c->valDia, c->valCrs, 1.0, c->vec_p, 0.0,
+      k_matvec<<<g, 256, 0, KS(c, "k_matvec")>>>(c->np, c->ncrs, c->rowptr, c->colidx, c->valDia, c->valCrs, 1.0, c->vec_p, 0.0,
                                          c->vec_z, c->cnt);
       CG_LAUNCH_CHECK(c);
     }
@@ -445,7 +445,7 @@ int run_pcg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out) {
     {
       DotArgs A;
       A.n = n; A.post = POST_PCG_CHECK; A.slot = SC_SQ; A.iter = it; A.tol2 = tol2;
-      k_update_xr<<<vec_grid(c, n), 256, 0, c->stream>>>(A, cur, c->vec_z, c->vec_p, c->vec_r, c->vec_x, c->partials,
+      k_update_xr<<<vec_grid(c, n), 256, 0, KS(c, "k_update_xr")>>>(A, cur, c->vec_z, c->vec_p, c->vec_r, c->vec_x, c->partials,
                                                          c->scal, c->cnt, c->npartial);
       CG_LAUNCH_CHECK(c);
     }
@@ -453,7 +453,7 @@ int run_pcg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out) {
     if (done) break;
     CG_CHECK(ilu_solve_launch(c, c->vec_z, c->vec_r, true));
     CG_CHECK(dot_launch(c, c->vec_r, c->vec_z, nxt, POST_STORE, 0, tol2, 1));
-    k_xpay<<<vec_grid(c, n), 256, 0, c->stream>>>(n, nxt, cur, c->vec_z, c->vec_p, c->scal, c->cnt);
+    k_xpay<<<vec_grid(c, n), 256, 0, KS(c, "k_xpay")>>>(n, nxt, cur, c->vec_z, c->vec_p, c->scal, c->cnt);
     CG_LAUNCH_CHECK(c);
     std::swap(cur, nxt);
   }
@@ -465,17 +465,17 @@ int run_pcg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out) {
 int run_cg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out) {
   const int n = c->ndof;
   const double tol2 = tol * tol;
-  k_pcg_reset<<<c->B, 1, 0, c->stream>>>(c->cnt, c->scal, max_iter, tol);
+  k_pcg_reset<<<c->B, 1, 0, KS(c, "k_pcg_reset")>>>(c->cnt, c->scal, max_iter, tol);
   CG_LAUNCH_CHECK(c);
   CG_CUDA(cudaMemsetAsync(c->vec_x, 0, sizeof(double) * (size_t)c->B * n, c->stream));
   CG_CHECK(dot_launch(c, c->vec_r, c->vec_r, SC_SQ, POST_PCG_INIT, 0, tol2, 0));
-  k_copy<<<vec_grid(c, n), 256, 0, c->stream>>>(n, c->vec_r, c->vec_p, c->cnt);
+  k_copy<<<vec_grid(c, n), 256, 0, KS(c, "k_copy")>>>(n, c->vec_r, c->vec_p, c->cnt);
   CG_LAUNCH_CHECK(c);
   bool done = false;
   for (int it = 1; it < max_iter; it++) {
     {
       dim3 g(div_up(n, 256), c->B);
-      k_matvec<<<g, 256, 0, c->stream>>>(c->np, c->ncrs, c->rowptr, c->colidx, c->valDia, c->valCrs, 1.0, c->vec_p, 0.0,
+      k_matvec<<<g, 256, 0, KS(c, "k_matvec")>>>(c->np, c->ncrs, c->rowptr, c->colidx, c->valDia, c->valCrs, 1.0, c->vec_p, 0.0,
                                          c->vec_z, c->cnt);
       CG_LAUNCH_CHECK(c);
     }
@@ -483,7 +483,7 @@ int run_cg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out) {
     {
       DotArgs A;
       A.n = n; A.post = POST_CG_CHECK; A.slot = SC_DOT; A.iter = it; A.tol2 = tol2;
-      k_update_xr<<<vec_grid(c, n), 256, 0, c->stream>>>(A, SC_SQ, c->vec_z, c->vec_p, c->vec_r, c->vec_x, c->partials,
+      k_update_xr<<<vec_grid(c, n), 256, 0, KS(c, "k_update_xr")>>>(A, SC_SQ, c->vec_z, c->vec_p, c->vec_r, c->vec_x, c->partials,
                                                          c->scal, c->cnt, c->npartial);
       CG_LAUNCH_CHECK(c);
     }
@@ -492,9 +492,9 @@ int run_cg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out) {
       if (done) break;
     }
     // beta = sq_new / sq ; sq = sq_new ; p = r + beta p
-    k_xpay<<<vec_grid(c, n), 256, 0, c->stream>>>(n, SC_DOT, SC_SQ, c->vec_r, c->vec_p, c->scal, c->cnt);
+    k_xpay<<<vec_grid(c, n), 256, 0, KS(c, "k_xpay")>>>(n, SC_DOT, SC_SQ, c->vec_r, c->vec_p, c->scal, c->cnt);
     CG_LAUNCH_CHECK(c);
-    k_set_scalar_slot<<<c->B, 1, 0, c->stream>>>(c->scal, SC_SQ, SC_DOT);
+    k_set_scalar_slot<<<c->B, 1, 0, KS(c, "k_set_scalar_slot")>>>(c->scal, SC_SQ, SC_DOT);
     CG_LAUNCH_CHECK(c);
   }
   return fetch_solver_result(c, conv_out, iter_out);
@@ -518,7 +518,7 @@ int run_step_internal(Ctx* c, const clothgpu_params& p, bool use_ilu, double* co
     CG_CHECK(run_cg(c, 1.0e-4, 1000, conv_out, iter_out));
     phase_end(c, 2);
   }
-  k_advance<<<vec_grid(c, c->ndof), 256, 0, c->stream>>>(c->ndof, p.dt, c->vec_x, c->xyz, c->uvw);
+  k_advance<<<vec_grid(c, c->ndof), 256, 0, KS(c, "k_advance")>>>(c->ndof, p.dt, c->vec_x, c->xyz, c->uvw);
   CG_LAUNCH_CHECK(c);
   return CLOTHGPU_OK;
 }

@@ -242,14 +242,14 @@ int launch_impulse(Ctx* c, const double* xyz, double* uvw, double delta, double 
     size_t tb = 0;
     CG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys2, c->sort_vals, c->sort_vals2, n4, 0, end_bit, c->stream));
     CG_CHECK(ensure_scratch(c, tb));
-    k_imp_pairs<<<div_up(n4, 256), 256, 0, c->stream>>>(ne, elems, keys, c->sort_vals);
+    k_imp_pairs<<<div_up(n4, 256), 256, 0, KS(c, "k_imp_pairs")>>>(ne, elems, keys, c->sort_vals);
     CG_LAUNCH_CHECK(c);
     CG_CUDA(cub::DeviceRadixSort::SortPairs(c->scratch, tb, keys, keys2, c->sort_vals, c->sort_vals2, n4, 0, end_bit, c->stream));
     c->launches += 3;
-    k_imp_pred<<<div_up(n4, 256), 256, 0, c->stream>>>(n4, keys2, c->sort_vals2, c->imp_pred + (size_t)s * c->cap_elem * 4);
+    k_imp_pred<<<div_up(n4, 256), 256, 0, KS(c, "k_imp_pred")>>>(n4, keys2, c->sort_vals2, c->imp_pred + (size_t)s * c->cap_elem * 4);
     CG_LAUNCH_CHECK(c);
   }
-  k_imp_run<<<c->B, 1024, 0, c->stream>>>(ccd, c->np, c->cap_elem, c->elems, c->imp_pred, c->imp_level, c->imp_order,
+  k_imp_run<<<c->B, 1024, 0, KS(c, "k_imp_run")>>>(ccd, c->np, c->cap_elem, c->elems, c->imp_pred, c->imp_level, c->imp_order,
                                           c->imp_lptr, xyz, uvw, delta, stiffness, dt, mass, c->cnt);
   CG_LAUNCH_CHECK(c);
   return CLOTHGPU_OK;
@@ -402,18 +402,18 @@ int launch_riz_reset(Ctx* c) {
 
 int launch_riz_make(Ctx* c) {
   dim3 g(148, c->B);
-  k_riz_mark<<<g, 256, 0, c->stream>>>(c->np, c->cap_elem, c->elems, c->zone, c->cnt);
+  k_riz_mark<<<g, 256, 0, KS(c, "k_riz_mark")>>>(c->np, c->cap_elem, c->elems, c->zone, c->cnt);
   CG_LAUNCH_CHECK(c);
-  k_riz_union<<<g, 256, 0, c->stream>>>(c->np, c->cap_elem, c->elems, c->edge_index, c->edge_array, c->zone, c->cnt);
+  k_riz_union<<<g, 256, 0, KS(c, "k_riz_union")>>>(c->np, c->cap_elem, c->elems, c->edge_index, c->edge_array, c->zone, c->cnt);
   CG_LAUNCH_CHECK(c);
   dim3 g2(div_up(c->np, 256), c->B);
-  k_riz_label<<<g2, 256, 0, c->stream>>>(c->np, c->zone, c->zone_label, c->cnt);
+  k_riz_label<<<g2, 256, 0, KS(c, "k_riz_label")>>>(c->np, c->zone, c->zone_label, c->cnt);
   CG_LAUNCH_CHECK(c);
   return CLOTHGPU_OK;
 }
 
 int launch_riz_apply(Ctx* c, const double* xyz, double* uvw) {
-  k_zero_cnt<<<c->B, 1, 0, c->stream>>>(c->cnt, CNT_RIZ_NODES);
+  k_zero_cnt<<<c->B, 1, 0, KS(c, "k_zero_cnt")>>>(c->cnt, CNT_RIZ_NODES);
   CG_LAUNCH_CHECK(c);
   CG_CHECK(ensure_sort_capacity(c, c->np));
   unsigned* keys = (unsigned*)c->sort_keys;
@@ -423,11 +423,11 @@ int launch_riz_apply(Ctx* c, const double* xyz, double* uvw) {
   CG_CHECK(ensure_scratch(c, tb));
   for (int s = 0; s < c->B; s++) {
     if (!c->h_cnt[s * NCNT + CNT_ACTIVE]) continue;
-    k_riz_keys<<<div_up(c->np, 256), 256, 0, c->stream>>>(c->np, c->zone_label + (size_t)s * c->np, keys, c->sort_vals);
+    k_riz_keys<<<div_up(c->np, 256), 256, 0, KS(c, "k_riz_keys")>>>(c->np, c->zone_label + (size_t)s * c->np, keys, c->sort_vals);
     CG_LAUNCH_CHECK(c);
     CG_CUDA(cub::DeviceRadixSort::SortPairs(c->scratch, tb, keys, keys2, c->sort_vals, c->sort_vals2, c->np, 0, 32, c->stream));
     c->launches += 3;
-    k_riz_apply<<<div_up(c->np, 128), 128, 0, c->stream>>>(c->np, keys2, c->sort_vals2, xyz + (size_t)s * c->ndof,
+    k_riz_apply<<<div_up(c->np, 128), 128, 0, KS(c, "k_riz_apply")>>>(c->np, keys2, c->sort_vals2, xyz + (size_t)s * c->ndof,
                                                            c->uvw0 + (size_t)s * c->ndof, uvw + (size_t)s * c->ndof,
                                                            c->cnt + s * NCNT);
     CG_LAUNCH_CHECK(c);

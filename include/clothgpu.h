@@ -143,6 +143,11 @@ long long clothgpu_launch_count(const clothgpu_ctx* ctx);
 enum { CLOTHGPU_NPHASE = 16 };
 int clothgpu_set_profiling(clothgpu_ctx* ctx, int on);
 int clothgpu_phase_ms(clothgpu_ctx* ctx, double* ms);
+/* per-kernel device time: while on, every kernel launch is bracketed by CUDA events on the context's stream and
+ * synchronised (measurement mode, slower).  clothgpu_kernel_times writes one "name launches total_ms" line per kernel
+ * into out (NUL terminated). */
+int clothgpu_set_kernel_timing(clothgpu_ctx* ctx, int on);
+int clothgpu_kernel_times(clothgpu_ctx* ctx, char* out, int cap);
 
 /* ------------------------------------------------------------------------------------------------ implicit step */
 /* mat_A.SetZero + AddWdWddW_Cloth + AddWdWddW_Contact + AddWdW_Gravity + rhs + mass + SetBoundaryCondition:
