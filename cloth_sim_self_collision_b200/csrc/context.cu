@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -239,6 +240,17 @@ static int build_topology(Ctx* c, const int* tri, const int* quad, const int* ro
   };
   CG_CHECK(levelize(true, c->nlev_f, c->maxrows_f, &c->lev_f_ptr, &c->lev_f_rows));
   CG_CHECK(levelize(false, c->nlev_b, c->maxrows_b, &c->lev_b_ptr, &c->lev_b_rows));
+  {
+    const char* mode = getenv("CLOTHGPU_TRISOLVE");
+    c->use_strips = !(mode && strcmp(mode, "levels") == 0);
+    const char* fs = getenv("CLOTHGPU_STRIPS");
+    const int force_ns = fs ? atoi(fs) : 0;
+    for (int dir = 0; dir < 2 && c->use_strips; dir++) {
+      TriPlanHost H;
+      CG_CHECK(build_triplan_host(np, rowptr, colidx, dia.data(), dir == 0, force_ns, H));
+      CG_CHECK(upload_triplan(c, H, dir == 0 ? c->plan_f : c->plan_b));
+    }
+  }
 
   // update list of DoILUDecomp (ilu_sparse.cpp:507-540): for row i, lower blocks k ascending, upper blocks j of
   // row k ascending, target (i,j) if present in the pattern (or the diagonal when j == i)
@@ -499,6 +511,9 @@ void clothgpu_destroy(clothgpu_ctx* c) {
                   c->gravity, c->boxes, c->refit_flag, c->scal, c->partials, c->cnt, c->zone, c->zone_label,
                   c->scratch, c->sort_keys, c->sort_keys2, c->sort_vals, c->sort_vals2};
   for (void* p : ptrs) cudaFree(p);
+  cudaFree(c->tri_dbg_buf);
+  free_triplan(c->plan_f);
+  free_triplan(c->plan_b);
   free_queues(c);
   if (c->h_cnt) cudaFreeHost(c->h_cnt);
   if (c->h_scal) cudaFreeHost(c->h_scal);
@@ -529,6 +544,7 @@ int clothgpu_write(clothgpu_ctx* c, int buf, int scene, const void* host, long l
   if (!bi.ptr) { set_error("buffer not allocated (context created without a BVH?)"); return CLOTHGPU_ERR_STATE; }
   CG_CUDA(cudaMemcpyAsync(bi.ptr, host, (size_t)count * bi.elem_bytes, cudaMemcpyHostToDevice, c->stream));
   CG_CUDA(cudaStreamSynchronize(c->stream));
+  if (buf == CLOTHGPU_BUF_ILU_DIA || buf == CLOTHGPU_BUF_ILU_CRS) c->ilu_packed_valid = false;
   if (buf == CLOTHGPU_BUF_ELEMS) {  // the caller supplies the contact elements of the next response op
     if (count % 5) { set_error("ELEMS count must be a multiple of 5"); return CLOTHGPU_ERR_ARG; }
     c->h_cnt[scene * NCNT + CNT_ELEM] = (int)(count / 5);

@@ -36,6 +36,31 @@ struct RawElem {
 static_assert(sizeof(RawElem) == 40, "RawElem layout");
 
 enum { NSCAL = 16, NCNT = 96 };
+// strip-pipelined triangular solves / factorisation (trisolve.cu, ilufactor.cu)
+enum { TS_ROWS = 10, TS_NST = 8, TS_META_HDR = 48, TS_MAXD = 8, TS_SMEM_HDR = 256 };
+
+// host-side plan of one sweep direction (pure host data: built and verified without a GPU)
+struct TriPlanHost {
+  bool fwd = true;
+  int np = 0, ns = 0, R = 0, nms = 0, max_meta_bytes = 0, max_val_bytes = 0, max_ghost = 0, max_steps = 0;
+  int nfast = 0;  // micro-steps that take the software-pipelined path
+  long long nval = 0;
+  double sim_makespan = 0;
+  std::vector<int> strip_ms, strip_gh, ms_rows, meta_off, val_off, pk_src, gh_row, gh_src, gh_need, meta;
+};
+// its device image plus the per-context pipeline state
+struct TriPlan {
+  bool fwd = true;
+  int ns = 0, R = 0, nms = 0, max_meta_bytes = 0, max_val_bytes = 0, max_ghost = 0, max_steps = 0, smem_bytes = 0;
+  long long nval = 0;
+  double sim_makespan = 0;
+  int *strip_ms = nullptr, *strip_gh = nullptr, *ms_rows = nullptr, *meta_off = nullptr, *val_off = nullptr;
+  int *meta = nullptr, *pk_src = nullptr, *gh_row = nullptr, *gh_src = nullptr, *gh_need = nullptr;
+  double* packed = nullptr;                // B x nval: factor blocks in lane order
+  unsigned long long* progress = nullptr;  // B x ns: micro-steps published per strip (monotone across launches)
+  unsigned long long* ticket = nullptr;    // strip hand-out counter (monotone across launches)
+  unsigned long long pbase = 0, tbase = 0;
+};
 // per-scene device counters (ints): layout of cnt[]
 enum {
   CNT_LEAF = 0,      // number of leaf pairs
@@ -83,6 +108,13 @@ struct Ctx {
   // ILU level schedules
   int nlev_f = 0, nlev_b = 0, maxrows_f = 0, maxrows_b = 0;
   int *lev_f_ptr = nullptr, *lev_f_rows = nullptr, *lev_b_ptr = nullptr, *lev_b_rows = nullptr;
+  // strip-pipelined triangular solves
+  TriPlan plan_f, plan_b;
+  bool ilu_packed_valid = false;  // plan_*.packed mirrors iluDia / iluCrs
+  bool tri_debug = false;         // clothgpu_debug_trisolve: per-CTA wait / compute cycle counters
+  unsigned long long* tri_dbg_buf = nullptr;
+  int tri_dbg_grid[2] = {0, 0};
+  bool use_strips = true;         // CLOTHGPU_TRISOLVE=levels selects the level-scheduled single-CTA kernels
   // ILU update lists: per row the (ik, kj, ij) slot triples in the reference's order (ij < 0: diagonal block)
   int *op_ptr = nullptr;
   int4* ops = nullptr;
@@ -178,6 +210,12 @@ int launch_axpy(Ctx* c, double a, const double* x, double* y);
 int launch_ilu_setvalue(Ctx* c);
 int launch_ilu_factor(Ctx* c);
 int launch_ilu_solve(Ctx* c, double* vec);
+int launch_ilu_solve_strips(Ctx* c, double* vec, const double* src, bool skip_done);
+int build_triplan_host(int np, const int* rowptr, const int* colidx, const int* dia, bool fwd, int force_ns,
+                       TriPlanHost& P);
+int verify_triplan_host(int np, const int* rowptr, const int* colidx, const int* dia, const TriPlanHost& P);
+int upload_triplan(Ctx* c, const TriPlanHost& H, TriPlan& D);
+void free_triplan(TriPlan& D);
 int run_pcg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out);
 int run_cg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out);
 int run_step_internal(Ctx* c, const clothgpu_params& p, bool use_ilu, double* conv_out, int* iter_out);

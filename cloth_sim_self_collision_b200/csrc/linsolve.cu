@@ -384,17 +384,20 @@ int launch_axpy(Ctx* c, double a, const double* x, double* y) {
   return CLOTHGPU_OK;
 }
 int launch_ilu_setvalue(Ctx* c) {
+  c->ilu_packed_valid = false;
   CG_CUDA(cudaMemcpyAsync(c->iluDia, c->valDia, sizeof(double) * (size_t)c->B * c->np * 9, cudaMemcpyDeviceToDevice, c->stream));
   CG_CUDA(cudaMemcpyAsync(c->iluCrs, c->valCrs, sizeof(double) * (size_t)c->B * c->ncrs * 9, cudaMemcpyDeviceToDevice, c->stream));
   return CLOTHGPU_OK;
 }
 int launch_ilu_factor(Ctx* c) {
+  c->ilu_packed_valid = false;
   k_ilu_factor<<<c->B, 1024, 0, KS(c, "k_ilu_factor")>>>(c->np, c->ncrs, c->nlev_f, c->lev_f_ptr, c->lev_f_rows, c->rowptr, c->diaind,
                                              c->op_ptr, c->ops, c->iluDia, c->iluCrs, c->cnt);
   CG_LAUNCH_CHECK(c);
   return CLOTHGPU_OK;
 }
 static int ilu_solve_launch(Ctx* c, double* vec, const double* src, bool skip_done) {
+  if (c->use_strips) return launch_ilu_solve_strips(c, vec, src, skip_done);
   k_ilu_solve<<<c->B, 320, 0, KS(c, "k_ilu_solve")>>>(c->np, c->ncrs, c->nlev_f, c->lev_f_ptr, c->lev_f_rows, c->nlev_b,
                                            c->lev_b_ptr, c->lev_b_rows, c->rowptr, c->colidx, c->diaind, c->iluDia,
                                            c->iluCrs, vec, src, skip_done ? c->cnt : nullptr);

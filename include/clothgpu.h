@@ -166,6 +166,16 @@ int clothgpu_ilu_setvalue(clothgpu_ctx* ctx);
 int clothgpu_ilu_factor(clothgpu_ctx* ctx);
 /* CPreconditionerILU::Solve, ilu_sparse.h:23-26: forward + backward substitution in place on a vector buffer */
 int clothgpu_ilu_solve(clothgpu_ctx* ctx, int buf_vec);
+/* Host-only self check of the strip-pipelined triangular-solve plan (csrc/trisolve.cu) that clothgpu_create derives
+ * from the block-CRS pattern: builds the forward and backward plans and verifies their invariants.  Needs no GPU.
+ * force_ns > 0 fixes the strip count.  stats: NULL or 16 ints, per direction {strips, rows per strip, micro-steps,
+ * longest strip, max ghosts, simulated makespan, micro-steps on the pipelined fast path, value bytes per stage} */
+int clothgpu_selftest_triplan(int np, const int* crs_rowptr, const int* crs_colidx, int force_ns, int* stats);
+/* Instrumentation of the triangular-solve kernels: while on, the compute warp of every CTA accumulates cycle counters.
+ * out: NULL, or 2 x cap_ctas x 8 values of the last forward / backward launch {start ns, end ns, cycles waiting for
+ * matrix chunks, cycles waiting for imported values, compute cycles, signalling cycles, micro-steps, strip};
+ * nctas[2] receives the CTA counts.  The call first returns the counters, then sets the new on/off state. */
+int clothgpu_debug_trisolve(clothgpu_ctx* ctx, int on, unsigned long long* out, int cap_ctas, int* nctas);
 /* Solve_PCG, ilu_sparse.cpp:628-709: VEC_R (destroyed) -> VEC_X.  conv_ratio / iteration: nscene values,
  * in = tolerance / iteration cap (element 0 is used for all scenes), out = achieved ratio / iterations */
 int clothgpu_pcg(clothgpu_ctx* ctx, double* conv_ratio, int* iteration);
