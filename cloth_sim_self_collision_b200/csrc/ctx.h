@@ -37,24 +37,26 @@ static_assert(sizeof(RawElem) == 40, "RawElem layout");
 
 enum { NSCAL = 16, NCNT = 96 };
 // strip-pipelined triangular solves / factorisation (trisolve.cu, ilufactor.cu)
-enum { TS_ROWS = 10, TS_NST = 8, TS_META_HDR = 48, TS_MAXD = 8, TS_SMEM_HDR = 256 };
+enum { TS_ROWS = 10, TS_NST = 3, TS_K = 4, TS_META_HDR = 16, TS_MAXD = 8, TS_SMEM_HDR = 256 };
 
 // host-side plan of one sweep direction (pure host data: built and verified without a GPU)
 struct TriPlanHost {
   bool fwd = true;
   int np = 0, ns = 0, R = 0, nms = 0, max_meta_bytes = 0, max_val_bytes = 0, max_ghost = 0, max_steps = 0;
-  int nfast = 0;  // micro-steps that take the software-pipelined path
+  int nfast = 0;  // micro-steps whose operands all fit the software pipeline (<= TS_MAXD)
+  int ndmax = 0, meta_stride = 0, val_stride = 0;  // largest operand count; ints / doubles per micro-step
   long long nval = 0;
   double sim_makespan = 0;
-  std::vector<int> strip_ms, strip_gh, ms_rows, meta_off, val_off, pk_src, gh_row, gh_src, gh_need, meta;
+  std::vector<int> strip_ms, strip_gh, ms_rows, pk_src, gh_row, gh_src, gh_need, meta;
 };
 // its device image plus the per-context pipeline state
 struct TriPlan {
   bool fwd = true;
   int ns = 0, R = 0, nms = 0, max_meta_bytes = 0, max_val_bytes = 0, max_ghost = 0, max_steps = 0, smem_bytes = 0;
+  int meta_stride = 0, val_stride = 0, ndmax = 0;
   long long nval = 0;
   double sim_makespan = 0;
-  int *strip_ms = nullptr, *strip_gh = nullptr, *ms_rows = nullptr, *meta_off = nullptr, *val_off = nullptr;
+  int *strip_ms = nullptr, *strip_gh = nullptr, *ms_rows = nullptr;
   int *meta = nullptr, *pk_src = nullptr, *gh_row = nullptr, *gh_src = nullptr, *gh_need = nullptr;
   double* packed = nullptr;                // B x nval: factor blocks in lane order
   unsigned long long* progress = nullptr;  // B x ns: micro-steps published per strip (monotone across launches)

@@ -14,8 +14,13 @@
 //     row, one per vector component).  A single compute warp walks the micro-steps; consecutive micro-steps are
 //     ordered by __syncwarp only.  The strip's slice of the solution vector lives in shared memory.
 //   * the matrix blocks a micro-step needs are packed once per factorisation into the exact order the lanes read
-//     them (k_pack) and streamed into a 4-stage shared-memory ring by 1-D TMA bulk copies (cp.async.bulk +
-//     mbarrier complete_tx) issued by a loader warp that runs ahead of the compute warp.
+//     them (k_pack) and streamed into a shared-memory ring (TS_NST stages of TS_K micro-steps, fixed strides so the
+//     lanes address them with immediates) by 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx) issued by
+//     a loader warp that runs ahead of the compute warp.
+//   * the compute warp is software pipelined: a single warp retires ~0.25 instructions per cycle, so the cost of
+//     a micro-step is its dynamic instruction count.  Operand slots are stored as byte offsets, padding operands
+//     point at a zero row with zero coefficients (no per-lane predicates), and the products of operands that were
+//     produced two or more micro-steps ago are issued in the shadow of the previous step's dependent chain.
 //   * values produced by other strips ("ghosts") are imported into shared memory by an import warp that polls the
 //     producer strip's progress counter (ld.acquire.gpu) ahead of need; finished rows are written back to global
 //     memory and the strip's own progress counter is advanced (fence + st.release.gpu) by a publisher warp.
@@ -70,6 +75,7 @@ static void make_sched(int np, const std::vector<int>& lev, bool fwd, int R, Sch
       }
       i = j;
     }
+    while ((S.ms_rows.size() / TS_ROWS - S.strip_ms[k]) % TS_K) S.ms_rows.insert(S.ms_rows.end(), TS_ROWS, -1);
     S.strip_ms[k + 1] = (int)(S.ms_rows.size() / TS_ROWS);
   }
   S.nms = S.strip_ms[S.ns];
@@ -127,7 +133,11 @@ int build_triplan_host(int np, const int* rowptr, const int* colidx, const int* 
     }
   }
   // choose the strip count: simulate the pipeline for a list of candidates, keep the shortest makespan
-  const int smem_budget = 200 * 1024;
+  int gmax0 = 0;
+  for (int i = 0; i < np; i++) gmax0 = std::max(gmax0, fwd ? dia[i] - rowptr[i] : rowptr[i + 1] - dia[i]);
+  const long long ring_bytes = (long long)TS_NST * TS_K * (round_up(TS_META_HDR + gmax0 * TS_ROWS, 4) * 4 +
+                                                            std::max(1, gmax0 + (fwd ? 1 : 0)) * 768) + TS_SMEM_HDR;
+  const long long smem_budget = 224 * 1024;
   static const int cand[] = {1, 2, 3, 4, 6, 8, 10, 12, 14, 16, 18, 20, 22, 24, 26, 28, 32, 36, 40, 44, 48, 52, 56,
                              64, 72, 80, 88, 96, 104, 112, 128, 144};
   Sched best;
@@ -141,7 +151,7 @@ int build_triplan_host(int np, const int* rowptr, const int* colidx, const int* 
     make_sched(np, lev, fwd, R, S);
     int mg = 0;
     const double t = simulate(np, rowptr, colidx, dia, fwd, S, 8.0, &mg);
-    const long long smem = (long long)(R + mg) * 32 + 56 * 1024;
+    const long long smem = (long long)(R + mg + 2) * 32 + ring_bytes;
     const bool fits = smem <= smem_budget;
     if (fits && (best_t < 0 || t < best_t)) {
       best_t = t;
@@ -163,7 +173,7 @@ int build_triplan_host(int np, const int* rowptr, const int* colidx, const int* 
       make_sched(np, lev, fwd, R, S);
       int mg = 0;
       const double t = simulate(np, rowptr, colidx, dia, fwd, S, 8.0, &mg);
-      if ((long long)(R + mg) * 32 + 56 * 1024 <= smem_budget) { best_t = t; best = std::move(S); best_ghost = mg; break; }
+      if ((long long)(R + mg + 2) * 32 + ring_bytes <= smem_budget) { best_t = t; best = std::move(S); best_ghost = mg; break; }
     }
   }
   const Sched& S = best;
@@ -179,166 +189,182 @@ int build_triplan_host(int np, const int* rowptr, const int* colidx, const int* 
   P.max_steps = 0;
   for (int k = 0; k < S.ns; k++) P.max_steps = std::max(P.max_steps, S.strip_ms[k + 1] - S.strip_ms[k]);
 
-  // materialise: per micro-step meta chunk, packed-value source map, ghost lists
-  P.meta.clear(); P.meta_off.assign(1, 0); P.val_off.assign(1, 0); P.pk_src.clear();
+  // materialise: per micro-step meta block and packed-value source map (fixed strides), ghost lists
+  int gmax = 0;  // largest operand count of any row
+  for (int i = 0; i < np; i++) gmax = std::max(gmax, fwd ? dia[i] - rowptr[i] : rowptr[i + 1] - dia[i]);
+  P.ndmax = gmax;
+  P.meta_stride = round_up(TS_META_HDR + gmax * TS_ROWS, 4);           // ints per micro-step
+  P.val_stride = (gmax + (fwd ? 1 : 0)) * 96;                           // doubles per micro-step
+  if (P.val_stride == 0) P.val_stride = 96;
+  P.meta.assign((size_t)S.nms * P.meta_stride, 0);
+  P.pk_src.assign((size_t)S.nms * P.val_stride, -1);
   P.strip_gh.assign(S.ns + 1, 0); P.gh_row.clear(); P.gh_src.clear(); P.gh_need.clear();
-  P.max_meta_bytes = 0; P.max_val_bytes = 0; P.nfast = 0;
+  P.nfast = 0;
   std::vector<int> ghost_slot(np, -1), ghost_owner(np, -1);
+  // first pass: ghost lists (the row count of the shared-memory vector depends on max_ghost)
+  for (int k = 0; k < S.ns; k++) {
+    int nghost = 0;
+    for (int m = S.strip_ms[k]; m < S.strip_ms[k + 1]; m++)
+      for (int q = 0; q < TS_ROWS; q++) {
+        const int row = S.ms_rows[(size_t)m * TS_ROWS + q];
+        if (row < 0) continue;
+        const int j0 = fwd ? rowptr[row] : dia[row], j1 = fwd ? dia[row] : rowptr[row + 1];
+        for (int j = j0; j < j1; j++) {
+          const int c = colidx[j], cp = plan_pos(fwd, np, c);
+          if (cp / S.R == k || ghost_owner[c] == k) continue;
+          ghost_owner[c] = k;
+          ghost_slot[c] = nghost++;
+          P.gh_row.push_back(c);
+          P.gh_src.push_back(cp / S.R);
+          P.gh_need.push_back(S.ms_of_row[c] - S.strip_ms[cp / S.R] + 1);
+        }
+      }
+    P.strip_gh[k + 1] = (int)P.gh_row.size();
+    P.max_ghost = std::max(P.max_ghost, nghost);
+  }
+  const int zero_off = (S.R + P.max_ghost) * 32, dummy_off = zero_off + 32;  // byte offsets of the two spare rows
+  std::fill(ghost_owner.begin(), ghost_owner.end(), -1);
   for (int k = 0; k < S.ns; k++) {
     const int p0 = k * S.R;
     int nghost = 0;
     for (int m = S.strip_ms[k]; m < S.strip_ms[k + 1]; m++) {
       const int* rows = &S.ms_rows[(size_t)m * TS_ROWS];
-      int ndep[TS_ROWS], ndmax = 0, nrows = 0;
-      for (int q = 0; q < TS_ROWS; q++) {
-        ndep[q] = 0;
-        if (rows[q] < 0) continue;
-        nrows++;
-        ndep[q] = fwd ? dia[rows[q]] - rowptr[rows[q]] : rowptr[rows[q] + 1] - dia[rows[q]];
-        ndmax = std::max(ndmax, ndep[q]);
-      }
-      const int nint = round_up(TS_META_HDR + ndmax * TS_ROWS, 4);
-      const size_t mbase = P.meta.size();
-      P.meta.resize(mbase + nint, 0);
-      int* M = &P.meta[mbase];
-      const int nlayer = ndmax + (fwd ? 1 : 0);
-      const size_t vbase = P.pk_src.size();
-      P.pk_src.resize(vbase + (size_t)nlayer * 96, -1);
-      int* V = &P.pk_src[vbase];
-      int fmin = ndmax, fast = ndmax <= TS_MAXD ? 1 : 0;
+      int* M = &P.meta[(size_t)m * P.meta_stride];
+      int* V = &P.pk_src[(size_t)m * P.val_stride];
+      const int lay0 = fwd ? 1 : 0;  // layer 0 of a forward step holds the D^-1 rows
+      int ndmax = 0, nearmask = 0;
+      for (int q = 0; q <= TS_ROWS; q++) M[4 + q] = dummy_off;
+      for (int d = 0; d < gmax; d++)
+        for (int q = 0; q < TS_ROWS; q++) M[TS_META_HDR + d * TS_ROWS + q] = zero_off;
       for (int q = 0; q < TS_ROWS; q++) {
         const int row = rows[q];
-        M[q] = row < 0 ? -1 : plan_pos(fwd, np, row) - p0;
-        M[TS_ROWS + q] = ndep[q];
-        M[28 + q] = M[38 + q] = -1;
         if (row < 0) continue;
-        const int j0 = fwd ? rowptr[row] : dia[row];
-        int nnear = 0;
-        for (int d = 0; d < ndep[q]; d++) {
+        M[4 + q] = (plan_pos(fwd, np, row) - p0) * 32;
+        const int j0 = fwd ? rowptr[row] : dia[row], j1 = fwd ? dia[row] : rowptr[row + 1];
+        ndmax = std::max(ndmax, j1 - j0);
+        for (int d = 0; d < j1 - j0; d++) {
           const int j = j0 + d, c = colidx[j];
           const int cp = plan_pos(fwd, np, c);
           int slot;
           if (cp / S.R == k) {
             slot = cp - p0;
-            if (S.ms_of_row[c] == m - 1) {  // produced by the immediately preceding micro-step: a "near" operand
-              if (nnear == 0) M[28 + q] = d;
-              else if (nnear == 1) M[38 + q] = d;
-              else fast = 0;
-              if (nnear == 0) fmin = std::min(fmin, d);
-              nnear++;
-            }
+            // an operand produced by the immediately preceding micro-step must be read after that step's barrier
+            if (S.ms_of_row[c] == m - 1) nearmask |= 1 << std::min(d, 30);
           } else {
-            if (ghost_owner[c] != k) {
-              ghost_owner[c] = k;
-              ghost_slot[c] = nghost++;
-              P.gh_row.push_back(c);
-              P.gh_src.push_back(cp / S.R);
-              P.gh_need.push_back(S.ms_of_row[c] - S.strip_ms[cp / S.R] + 1);
-            }
+            if (ghost_owner[c] != k) { ghost_owner[c] = k; ghost_slot[c] = nghost++; }  // same order as the first pass
             slot = S.R + ghost_slot[c];
           }
-          M[TS_META_HDR + d * TS_ROWS + q] = slot;
+          M[TS_META_HDR + d * TS_ROWS + q] = slot * 32;
           for (int kk = 0; kk < 3; kk++)
-            for (int r = 0; r < 3; r++) V[(d * 3 + kk) * 32 + q * 3 + r] = j * 9 + r * 3 + kk;
+            for (int r = 0; r < 3; r++) V[((lay0 + d) * 3 + kk) * 32 + q * 3 + r] = j * 9 + r * 3 + kk;
         }
         if (fwd)
           for (int kk = 0; kk < 3; kk++)
-            for (int r = 0; r < 3; r++) V[(ndmax * 3 + kk) * 32 + q * 3 + r] = ncrs * 9 + row * 9 + r * 3 + kk;
+            for (int r = 0; r < 3; r++) V[kk * 32 + q * 3 + r] = ncrs * 9 + row * 9 + r * 3 + kk;
       }
-      M[2 * TS_ROWS + 0] = ndmax;
-      M[2 * TS_ROWS + 1] = nghost;  // ghosts that must have been imported before this micro-step runs
-      M[2 * TS_ROWS + 2] = nrows;
-      M[2 * TS_ROWS + 3] = fast;
-      M[2 * TS_ROWS + 4] = fmin;
-      P.nfast += fast;
-      P.meta_off.push_back((int)(P.meta.size() * sizeof(int)));
-      P.val_off.push_back((int)P.pk_src.size());
-      P.max_meta_bytes = std::max(P.max_meta_bytes, nint * (int)sizeof(int));
-      P.max_val_bytes = std::max(P.max_val_bytes, nlayer * 96 * (int)sizeof(double));
+      // operands beyond TS_MAXD are handled by the un-pipelined tail loop, i.e. always after the barrier
+      int fmin = std::min(ndmax, (int)TS_MAXD);
+      for (int d = 0; d < std::min(ndmax, (int)TS_MAXD); d++)
+        if (nearmask >> d & 1) { fmin = d; break; }
+      M[0] = ndmax;
+      M[1] = nghost;  // ghosts that must have been imported before this micro-step runs
+      M[2] = nearmask & ((1 << TS_MAXD) - 1);
+      M[3] = fmin;
+      P.nfast += ndmax <= TS_MAXD;
     }
-    P.strip_gh[k + 1] = (int)P.gh_row.size();
-    P.max_ghost = std::max(P.max_ghost, nghost);
   }
+  P.max_meta_bytes = P.meta_stride * 4;
+  P.max_val_bytes = P.val_stride * 8;
   P.nval = (long long)P.pk_src.size();
   if (P.pk_src.size() > (size_t)0x7fffffff) { set_error("triangular-solve plan exceeds 2^31 packed values"); return CLOTHGPU_ERR_CAPACITY; }
   return CLOTHGPU_OK;
 }
 
 // Structural self-check of a plan (host logic, no GPU): every row is scheduled exactly once, every dependency is
-// either an own row of an earlier micro-step or a ghost whose producer strip is earlier and whose import is
-// required in time, and every packed value maps to the right matrix entry.
+// either an own row of an earlier micro-step (flagged "near" when it is the immediately preceding one) or a ghost
+// whose producer strip is earlier and whose import is required in time, padding points at the zero row with no
+// matrix value, and every packed value maps to the right matrix entry.
 int verify_triplan_host(int np, const int* rowptr, const int* colidx, const int* dia, const TriPlanHost& P) {
   const bool fwd = P.fwd;
   const int ncrs = rowptr[np];
+#define PLAN_FAIL(msg) do { set_error(std::string("plan: ") + msg); return CLOTHGPU_ERR_STATE; } while (0)
   std::vector<int> ms_of_row(np, -1);
+  if ((long long)P.ms_rows.size() != (long long)P.nms * TS_ROWS) PLAN_FAIL("ms_rows size");
   for (int m = 0; m < P.nms; m++)
     for (int q = 0; q < TS_ROWS; q++) {
       const int row = P.ms_rows[(size_t)m * TS_ROWS + q];
       if (row < 0) continue;
-      if (row >= np || ms_of_row[row] != -1) { set_error("plan: row scheduled twice or out of range"); return CLOTHGPU_ERR_STATE; }
+      if (row >= np || ms_of_row[row] != -1) PLAN_FAIL("row scheduled twice or out of range");
       ms_of_row[row] = m;
     }
   for (int i = 0; i < np; i++)
-    if (ms_of_row[i] < 0) { set_error("plan: row not scheduled"); return CLOTHGPU_ERR_STATE; }
-  if ((int)P.meta_off.size() != P.nms + 1 || (int)P.val_off.size() != P.nms + 1) { set_error("plan: offset tables"); return CLOTHGPU_ERR_STATE; }
+    if (ms_of_row[i] < 0) PLAN_FAIL("row not scheduled");
+  if ((long long)P.meta.size() != (long long)P.nms * P.meta_stride || (long long)P.pk_src.size() != (long long)P.nms * P.val_stride ||
+      P.meta_stride % 4 || P.val_stride % 2)
+    PLAN_FAIL("array sizes / strides");
+  const int zero_off = (P.R + P.max_ghost) * 32, dummy_off = zero_off + 32, lay0 = fwd ? 1 : 0;
   for (int k = 0; k < P.ns; k++) {
     const int p0 = k * P.R, g0 = P.strip_gh[k], ng = P.strip_gh[k + 1] - g0;
+    if ((P.strip_ms[k + 1] - P.strip_ms[k]) % TS_K) PLAN_FAIL("strip length not a multiple of the stage size");
     int prev_need = 0;
     for (int m = P.strip_ms[k]; m < P.strip_ms[k + 1]; m++) {
-      if (P.meta_off[m] % 16 || P.val_off[m] % 2) { set_error("plan: chunk alignment"); return CLOTHGPU_ERR_STATE; }
-      const int* M = &P.meta[P.meta_off[m] / 4];
-      const int* V = &P.pk_src[P.val_off[m]];
-      const int ndmax = M[2 * TS_ROWS], gneed = M[2 * TS_ROWS + 1];
-      if (gneed < prev_need || gneed > ng) { set_error("plan: ghost requirement not monotone"); return CLOTHGPU_ERR_STATE; }
+      const int* M = &P.meta[(size_t)m * P.meta_stride];
+      const int* V = &P.pk_src[(size_t)m * P.val_stride];
+      const int ndmax = M[0], gneed = M[1], nearmask = M[2], fmin = M[3];
+      if (gneed < prev_need || gneed > ng) PLAN_FAIL("ghost requirement not monotone");
       prev_need = gneed;
-      const int nlayer = ndmax + (fwd ? 1 : 0);
-      if (P.val_off[m + 1] - P.val_off[m] != nlayer * 96) { set_error("plan: value chunk size"); return CLOTHGPU_ERR_STATE; }
-      if (P.meta_off[m + 1] - P.meta_off[m] != round_up(TS_META_HDR + ndmax * TS_ROWS, 4) * 4) { set_error("plan: meta chunk size"); return CLOTHGPU_ERR_STATE; }
+      if (ndmax > P.ndmax || fmin < 0 || fmin > std::min(ndmax, (int)TS_MAXD)) PLAN_FAIL("operand count / chain split");
+      for (int d = 0; d < fmin; d++)
+        if (nearmask >> d & 1) PLAN_FAIL("near operand inside the early chain prefix");
+      std::vector<char> used((size_t)P.val_stride, 0);
       for (int q = 0; q < TS_ROWS; q++) {
         const int row = P.ms_rows[(size_t)m * TS_ROWS + q];
+        const int nd = row < 0 ? 0 : (fwd ? dia[row] - rowptr[row] : rowptr[row + 1] - dia[row]);
         if (row < 0) {
-          if (M[q] != -1 || M[TS_ROWS + q] != 0) { set_error("plan: unused lane not blank"); return CLOTHGPU_ERR_STATE; }
-          continue;
+          if (M[4 + q] != dummy_off) PLAN_FAIL("unused lane must write the dummy row");
+        } else {
+          const int pos = plan_pos(fwd, np, row);
+          if (pos / P.R != k || M[4 + q] != (pos - p0) * 32) PLAN_FAIL("own slot");
+          if (nd > ndmax) PLAN_FAIL("dependency count");
         }
-        const int pos = plan_pos(fwd, np, row);
-        if (pos / P.R != k || M[q] != pos - p0) { set_error("plan: own slot"); return CLOTHGPU_ERR_STATE; }
-        const int j0 = fwd ? rowptr[row] : dia[row], j1 = fwd ? dia[row] : rowptr[row + 1];
-        if (M[TS_ROWS + q] != j1 - j0 || j1 - j0 > ndmax) { set_error("plan: dependency count"); return CLOTHGPU_ERR_STATE; }
-        const int fast = M[2 * TS_ROWS + 3], fmin = M[2 * TS_ROWS + 4];
-        if (fast && ndmax > TS_MAXD) { set_error("plan: fast step with too many operands"); return CLOTHGPU_ERR_STATE; }
-        int nnear = 0;
-        for (int d = 0; d < j1 - j0; d++) {
+        const int j0 = row < 0 ? 0 : (fwd ? rowptr[row] : dia[row]);
+        for (int d = 0; d < P.ndmax; d++) {
+          const int off = M[TS_META_HDR + d * TS_ROWS + q];
+          if (d >= nd) {
+            if (off != zero_off) PLAN_FAIL("padding operand must read the zero row");
+            continue;
+          }
           const int c = colidx[j0 + d], cp = plan_pos(fwd, np, c);
-          const bool is_near = cp / P.R == k && ms_of_row[c] == m - 1;
-          if (!is_near) continue;
-          nnear++;
-          if (fast && (d < fmin || (M[28 + q] != d && M[38 + q] != d))) { set_error("plan: near operand not marked"); return CLOTHGPU_ERR_STATE; }
-        }
-        if (fast && nnear > 2) { set_error("plan: fast step with more than two near operands"); return CLOTHGPU_ERR_STATE; }
-        if (fast && (fmin < 0 || fmin > ndmax)) { set_error("plan: chain split"); return CLOTHGPU_ERR_STATE; }
-        for (int d = 0; d < j1 - j0; d++) {
-          const int c = colidx[j0 + d], cp = plan_pos(fwd, np, c), slot = M[TS_META_HDR + d * TS_ROWS + q];
           if (cp / P.R == k) {
-            if (slot != cp - p0 || ms_of_row[c] >= m) { set_error("plan: own dependency not earlier"); return CLOTHGPU_ERR_STATE; }
+            if (off != (cp - p0) * 32 || ms_of_row[c] >= m) PLAN_FAIL("own dependency not earlier");
+            if (ms_of_row[c] == m - 1 && d < TS_MAXD && !(nearmask >> d & 1)) PLAN_FAIL("near operand not flagged");
           } else {
-            const int gi = slot - P.R;
+            const int gi = off / 32 - P.R;
             if (cp / P.R > k || gi < 0 || gi >= gneed || P.gh_row[g0 + gi] != c || P.gh_src[g0 + gi] != cp / P.R ||
-                P.gh_need[g0 + gi] != ms_of_row[c] - P.strip_ms[cp / P.R] + 1) {
-              set_error("plan: ghost dependency");
-              return CLOTHGPU_ERR_STATE;
-            }
+                P.gh_need[g0 + gi] != ms_of_row[c] - P.strip_ms[cp / P.R] + 1)
+              PLAN_FAIL("ghost dependency");
           }
           for (int kk = 0; kk < 3; kk++)
-            for (int r = 0; r < 3; r++)
-              if (V[(d * 3 + kk) * 32 + q * 3 + r] != (j0 + d) * 9 + r * 3 + kk) { set_error("plan: packed value map"); return CLOTHGPU_ERR_STATE; }
+            for (int r = 0; r < 3; r++) {
+              const int idx = ((lay0 + d) * 3 + kk) * 32 + q * 3 + r;
+              if (V[idx] != (j0 + d) * 9 + r * 3 + kk) PLAN_FAIL("packed value map");
+              used[idx] = 1;
+            }
         }
-        if (fwd)
+        if (fwd && row >= 0)
           for (int kk = 0; kk < 3; kk++)
-            for (int r = 0; r < 3; r++)
-              if (V[(ndmax * 3 + kk) * 32 + q * 3 + r] != ncrs * 9 + row * 9 + r * 3 + kk) { set_error("plan: packed diagonal map"); return CLOTHGPU_ERR_STATE; }
+            for (int r = 0; r < 3; r++) {
+              const int idx = kk * 32 + q * 3 + r;
+              if (V[idx] != ncrs * 9 + row * 9 + r * 3 + kk) PLAN_FAIL("packed diagonal map");
+              used[idx] = 1;
+            }
       }
+      if (M[4 + TS_ROWS] != dummy_off) PLAN_FAIL("idle lanes must write the dummy row");
+      for (int i = 0; i < P.val_stride; i++)
+        if (!used[i] && V[i] != -1) PLAN_FAIL("padding value must be empty");
     }
   }
+#undef PLAN_FAIL
   return CLOTHGPU_OK;
 }
 
@@ -353,9 +379,9 @@ static int up(T** p, const std::vector<T>& h) {
 int upload_triplan(Ctx* c, const TriPlanHost& H, TriPlan& D) {
   D.fwd = H.fwd; D.ns = H.ns; D.R = H.R; D.nms = H.nms; D.max_meta_bytes = H.max_meta_bytes;
   D.max_val_bytes = H.max_val_bytes; D.max_ghost = H.max_ghost; D.max_steps = H.max_steps; D.nval = H.nval;
-  D.sim_makespan = H.sim_makespan;
+  D.sim_makespan = H.sim_makespan; D.meta_stride = H.meta_stride; D.val_stride = H.val_stride; D.ndmax = H.ndmax;
   CG_CHECK(up(&D.strip_ms, H.strip_ms)); CG_CHECK(up(&D.strip_gh, H.strip_gh)); CG_CHECK(up(&D.ms_rows, H.ms_rows));
-  CG_CHECK(up(&D.meta_off, H.meta_off)); CG_CHECK(up(&D.val_off, H.val_off)); CG_CHECK(up(&D.meta, H.meta));
+  CG_CHECK(up(&D.meta, H.meta));
   CG_CHECK(up(&D.pk_src, H.pk_src)); CG_CHECK(up(&D.gh_row, H.gh_row)); CG_CHECK(up(&D.gh_src, H.gh_src));
   CG_CHECK(up(&D.gh_need, H.gh_need));
   CG_CUDA(cudaMalloc((void**)&D.packed, sizeof(double) * (size_t)std::max<long long>(H.nval, 1) * c->B));
@@ -365,13 +391,12 @@ int upload_triplan(Ctx* c, const TriPlanHost& H, TriPlan& D) {
   CG_CUDA(cudaMemset(D.ticket, 0, sizeof(unsigned long long)));
   D.pbase = 0;
   D.tbase = 0;
-  const int stage_meta = round_up(D.max_meta_bytes, 128), stage_val = round_up(std::max(D.max_val_bytes, 16), 128);
-  D.smem_bytes = TS_SMEM_HDR + TS_NST * (stage_meta + stage_val) + (D.R + D.max_ghost) * 32 + 64;
+  D.smem_bytes = TS_SMEM_HDR + (D.R + D.max_ghost + 2) * 32 + TS_NST * TS_K * (D.meta_stride * 4 + D.val_stride * 8);
   return CLOTHGPU_OK;
 }
 
 void free_triplan(TriPlan& D) {
-  void* ptrs[] = {D.strip_ms, D.strip_gh, D.ms_rows, D.meta_off, D.val_off, D.meta, D.pk_src, D.gh_row, D.gh_src,
+  void* ptrs[] = {D.strip_ms, D.strip_gh, D.ms_rows, D.meta, D.pk_src, D.gh_row, D.gh_src,
                   D.gh_need, D.packed, D.progress, D.ticket};
   for (void* p : ptrs) cudaFree(p);
   D = TriPlan();
@@ -428,9 +453,10 @@ __device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned l
 
 struct TriArgs {
   int np, ns, R, B;
-  int stage_meta, stage_bytes;
+  int meta_stride, val_stride;  // ints / doubles per micro-step
+  int xs_rows;                  // rows of the shared-memory vector (own + ghosts + zero row + dummy row)
   long long nval;
-  const int *strip_ms, *strip_gh, *ms_rows, *meta_off, *val_off, *gh_row, *gh_src, *gh_need;
+  const int *strip_ms, *strip_gh, *ms_rows, *gh_row, *gh_src, *gh_need;
   const int* meta;
   const double* packed;
   unsigned long long *progress, *ticket;
@@ -463,14 +489,18 @@ __global__ void __launch_bounds__(256) k_pack(long long nval, const int* __restr
 }
 
 // one CTA per (strip, scene): warp 0 computes, warp 1 streams matrix chunks, warp 2 publishes, warp 3 imports
-template <bool FWD>
-__global__ void __launch_bounds__(128) k_trisolve(const TriArgs A) {
+template <bool FWD, int ND>
+__global__ void __launch_bounds__(128, 1) k_trisolve(const TriArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + TS_NST;
-  uint32_t* flags = reinterpret_cast<uint32_t*>(smem + 16 * TS_NST);  // [0] micro-steps done, [1] ghosts imported, [2] ticket
-  unsigned char* stages = smem + TS_SMEM_HDR;
-  double* xs = reinterpret_cast<double*>(stages + TS_NST * A.stage_bytes);
+  uint32_t* flags = reinterpret_cast<uint32_t*>(smem + 128);  // [0] micro-steps done, [1] ghosts imported, [2] ticket
+  unsigned char* xsc = smem + TS_SMEM_HDR;                    // the strip's slice of the vector, 32 bytes per row
+  double* xs = reinterpret_cast<double*>(xsc);
+  const int meta_bytes = A.meta_stride * 4, val_bytes = A.val_stride * 8;
+  const int stage_bytes = TS_K * (meta_bytes + val_bytes);
+  unsigned char* stages = xsc + (size_t)A.xs_rows * 32;
+  constexpr int LAY0 = FWD ? 1 : 0;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
@@ -482,7 +512,7 @@ __global__ void __launch_bounds__(128) k_trisolve(const TriArgs A) {
   const int strip = (int)(ticket / (uint32_t)A.B), scene = (int)(ticket % (uint32_t)A.B);
   if (A.cnt && A.cnt[scene * NCNT + CNT_PCG_DONE]) return;
 
-  const int ms0 = A.strip_ms[strip], nsteps = A.strip_ms[strip + 1] - ms0;
+  const int ms0 = A.strip_ms[strip], nsteps = A.strip_ms[strip + 1] - ms0;  // a multiple of TS_K
   const int p0 = strip * A.R, nown = min(A.R, A.np - p0);
   double* out = A.vec + (size_t)scene * A.np * 3;
   const double* in = (FWD && A.src) ? A.src + (size_t)scene * A.np * 3 : out;
@@ -493,6 +523,7 @@ __global__ void __launch_bounds__(128) k_trisolve(const TriArgs A) {
     const int row = FWD ? p : A.np - 1 - p;
     xs[(idx / 3) * 4 + comp] = in[(size_t)row * 3 + comp];
   }
+  if (tid < 8) xs[(A.xs_rows - 2) * 4 + tid] = 0.0;  // zero row (padding operands) and dummy row (idle lanes)
   if (tid == 0) {
     for (int i = 0; i < TS_NST; i++) {
       mbar_init(&full[i], 1);
@@ -507,229 +538,188 @@ __global__ void __launch_bounds__(128) k_trisolve(const TriArgs A) {
 
   if (warp == 0) {
     // ---------------------------------------------------------------- compute warp
-    // Software pipeline over the micro-steps.  Everything of step s+1 that does not depend on step s ("phase A":
-    // matrix values, far operands, their products, the prefix of the subtraction chain) is issued in the shadow of
-    // the dependent chain of step s ("phase B": operands produced by step s-1..s, the rest of the chain, the D^-1
-    // multiply).  The plan marks per row which (at most two) operands are "near" = produced by the immediately
-    // preceding micro-step of this strip; steps that do not fit (more than TS_MAXD operands or more than two near
-    // ones in a row) take the generic path.
+    // A single warp retires ~0.25 dependent instructions per cycle, so a micro-step costs what its longest
+    // dependent chain costs -- provided the independent work is in ONE basic block for the scheduler to overlap.
+    // Hence: the operand count ND is a template parameter, every row executes all ND products (padding operands
+    // read the zero row with zero coefficients: exact), and there is no branch between the barrier of the
+    // previous micro-step and the store of this one except the (rarely taken) ghost wait.
     const int g = lane / 3, r = lane - g * 3;
-    const bool act = g < TS_ROWS;
-    const int gq = act ? g : TS_ROWS - 1;
+    const int gq = g < TS_ROWS ? g : TS_ROWS - 1;
     const int l0 = (gq * 3) & 31;
     uint32_t seen = 0;
     const bool dbg = A.dbg != nullptr;
     unsigned long long t_begin = 0, w_mbar = 0, w_ghost = 0, w_comp = 0, w_sig = 0;
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
     if (dbg) t_begin = gtime_ns();
-
-    // state of the step in flight (filled by phase A)
-    int fast = 0, myslot = -1, ndmax = 0, fmin = 0, n0 = -1, n1 = -1, ns0 = 0, ns1 = 0;
-    double tp = 0.0, p[TS_MAXD], an0[3], an1[3], dd[3];
-#pragma unroll
-    for (int d = 0; d < TS_MAXD; d++) p[d] = 0.0;
-    an0[0] = an0[1] = an0[2] = an1[0] = an1[1] = an1[2] = dd[0] = dd[1] = dd[2] = 0.0;
-
-    // waits of a step: its matrix chunk and its imported operands
-    auto wait_step = [&](int s) {
+    // register image of the micro-step about to run: operand offsets and coefficients do not depend on the
+    // solution, so they are fetched one micro-step ahead, in the shadow of the previous step's subtraction chain
+    int myoff = 0, off[ND];
+    uint32_t gneed = 0;
+    int ndmax = 0;
+    double av[ND][3], dd0 = 0.0, dd1 = 0.0, dd2 = 0.0;
+#define TS_LOAD_STEP(MP_, VP_)                                                                   \
+    {                                                                                            \
+      const int* Mp = (MP_);                                                                     \
+      const double* Vp = (VP_);                                                                  \
+      gneed = (uint32_t)Mp[1];                                                                   \
+      ndmax = Mp[0];                                                                             \
+      myoff = Mp[4 + g] + r * 8;                                                                 \
+      _Pragma("unroll") for (int d = 0; d < ND; d++) {                                           \
+        off[d] = Mp[TS_META_HDR + d * TS_ROWS + gq];                                             \
+        av[d][0] = Vp[((LAY0 + d) * 3 + 0) * 32 + lane];                                         \
+        av[d][1] = Vp[((LAY0 + d) * 3 + 1) * 32 + lane];                                         \
+        av[d][2] = Vp[((LAY0 + d) * 3 + 2) * 32 + lane];                                         \
+      }                                                                                          \
+      if (FWD) { dd0 = Vp[0 * 32 + lane]; dd1 = Vp[1 * 32 + lane]; dd2 = Vp[2 * 32 + lane]; }    \
+    }
+    const int nstage = nsteps / TS_K;
+    if (nstage > 0) {
       if (dbg) c0 = clock64();
-      mbar_wait(&full[s % TS_NST], (uint32_t)(s / TS_NST) & 1u);
-      if (dbg) c1 = clock64();
-      const int* M = reinterpret_cast<const int*>(stages + (size_t)(s % TS_NST) * A.stage_bytes);
-      const uint32_t gneed = (uint32_t)M[2 * TS_ROWS + 1];
-      if (gneed > seen) {
-        do { seen = ld_acquire_cta(&flags[1]); } while (seen < gneed);
-      }
-      if (dbg) { c2 = clock64(); w_mbar += (unsigned long long)(c1 - c0); w_ghost += (unsigned long long)(c2 - c1); }
-    };
-    // phase A of a fast step: loads and products of the far operands, chain prefix
-#define TS_PHASE_A(S_)                                                                                          \
-    {                                                                                                           \
-      const int* M = reinterpret_cast<const int*>(stages + (size_t)((S_) % TS_NST) * A.stage_bytes);           \
-      const double* V = reinterpret_cast<const double*>(stages + (size_t)((S_) % TS_NST) * A.stage_bytes + A.stage_meta); \
-      fast = M[2 * TS_ROWS + 3];                                                                                \
-      if (fast) {                                                                                               \
-        myslot = act ? M[gq] : -1;                                                                              \
-        const int nd = act ? M[TS_ROWS + gq] : 0;                                                               \
-        ndmax = M[2 * TS_ROWS];                                                                                 \
-        fmin = M[2 * TS_ROWS + 4];                                                                              \
-        n0 = act ? M[28 + gq] : -1;                                                                             \
-        n1 = act ? M[38 + gq] : -1;                                                                             \
-        tp = myslot >= 0 ? xs[myslot * 4 + r] : 0.0;                                                            \
-        _Pragma("unroll") for (int d = 0; d < TS_MAXD; d++) {                                                   \
-          if (d < ndmax) {                                                                                      \
-            const int sl = M[TS_META_HDR + d * TS_ROWS + gq];                                                   \
-            const double a0 = V[(d * 3 + 0) * 32 + lane], a1 = V[(d * 3 + 1) * 32 + lane], a2 = V[(d * 3 + 2) * 32 + lane]; \
-            const double2 x01 = *reinterpret_cast<const double2*>(xs + sl * 4);                                 \
-            const double x2 = xs[sl * 4 + 2];                                                                   \
-            const double pd = a0 * x01.x + a1 * x01.y + a2 * x2;                                                \
-            const bool is_near = (d == n0) || (d == n1);                                                           \
-            p[d] = (d < nd && !is_near) ? pd : 0.0;                                                                \
-            if (d == n0) { an0[0] = a0; an0[1] = a1; an0[2] = a2; ns0 = sl; }                                   \
-            if (d == n1) { an1[0] = a0; an1[1] = a1; an1[2] = a2; ns1 = sl; }                                   \
-          }                                                                                                     \
-        }                                                                                                       \
-        _Pragma("unroll") for (int d = 0; d < TS_MAXD; d++) {                                                   \
-          if (d < fmin) tp -= p[d];                                                                             \
-        }                                                                                                       \
-        if (FWD) {                                                                                              \
-          dd[0] = V[(ndmax * 3 + 0) * 32 + lane]; dd[1] = V[(ndmax * 3 + 1) * 32 + lane]; dd[2] = V[(ndmax * 3 + 2) * 32 + lane]; \
-        }                                                                                                       \
-      }                                                                                                         \
+      mbar_wait(&full[0], 0);
+      if (dbg) w_mbar += (unsigned long long)(clock64() - c0);
+      TS_LOAD_STEP(reinterpret_cast<const int*>(stages), reinterpret_cast<const double*>(stages + TS_K * meta_bytes))
     }
-
-    if (nsteps > 0) {
-      wait_step(0);
-      TS_PHASE_A(0)
-    }
-    for (int s = 0; s < nsteps; s++) {
-      const int st = s % TS_NST;
-      const bool more = s + 1 < nsteps;
-      if (more) wait_step(s + 1);
-      if (dbg) c2 = clock64();
-      double t;
-      int slot_out;
-      if (fast) {
-        // ---- phase B of step s: near operands, rest of the chain
-        const int b_slot = myslot, b_n0 = n0, b_n1 = n1, b_fmin = fmin, b_ndmax = ndmax;
-        const double2 y01 = *reinterpret_cast<const double2*>(xs + ns0 * 4);
-        const double y2 = xs[ns0 * 4 + 2];
-        const double2 z01 = *reinterpret_cast<const double2*>(xs + ns1 * 4);
-        const double z2 = xs[ns1 * 4 + 2];
-        const double pn0 = an0[0] * y01.x + an0[1] * y01.y + an0[2] * y2;
-        const double pn1 = an1[0] * z01.x + an1[1] * z01.y + an1[2] * z2;
-        double q[TS_MAXD];
+    for (int sg = 0; sg < nstage; sg++) {
+      const int st = sg % TS_NST;
+      const unsigned char* sb = stages + (size_t)st * stage_bytes;
+      const unsigned char* nb = stages + (size_t)((sg + 1) % TS_NST) * stage_bytes;
+      const bool more_stages = sg + 1 < nstage;
 #pragma unroll
-        for (int d = 0; d < TS_MAXD; d++) q[d] = (d == b_n0) ? pn0 : ((d == b_n1) ? pn1 : p[d]);
-        t = tp;
-        const double b_dd0 = dd[0], b_dd1 = dd[1], b_dd2 = dd[2];
-        // ---- phase A of step s+1 (independent of the chain below: scheduled into its stalls)
-        if (more) TS_PHASE_A(s + 1)
+      for (int k = 0; k < TS_K; k++) {
+        const int* Mk = reinterpret_cast<const int*>(sb + k * meta_bytes);
+        const double* Vk = reinterpret_cast<const double*>(sb + TS_K * meta_bytes + k * val_bytes);
+        const bool last = (k == TS_K - 1);
+        if (dbg) c0 = clock64();
+        if (last && more_stages) mbar_wait(&full[(sg + 1) % TS_NST], (uint32_t)((sg + 1) / TS_NST) & 1u);
+        if (dbg) c1 = clock64();
+        if (gneed > seen) {
+          do { seen = ld_acquire_cta(&flags[1]); } while (seen < gneed);
+        }
+        if (dbg) { c2 = clock64(); w_mbar += (unsigned long long)(c1 - c0); w_ghost += (unsigned long long)(c2 - c1); }
+        const int cur_off = myoff, cur_ndmax = ndmax;
+        const double e0 = dd0, e1 = dd1, e2 = dd2;
+        double t = *reinterpret_cast<const double*>(xsc + cur_off);
+        double pr[ND];
 #pragma unroll
-        for (int d = 0; d < TS_MAXD; d++) {
-          if (d >= b_fmin && d < b_ndmax) t -= q[d];
+        for (int d = 0; d < ND; d++) {
+          const double2 x01 = *reinterpret_cast<const double2*>(xsc + off[d]);
+          const double x2 = *reinterpret_cast<const double*>(xsc + off[d] + 16);
+          pr[d] = av[d][0] * x01.x + av[d][1] * x01.y + av[d][2] * x2;
+        }
+        // fetch the next micro-step's image (same stage, or the first step of the next stage)
+        if (!last) {
+          TS_LOAD_STEP(reinterpret_cast<const int*>(sb + (k + 1) * meta_bytes),
+                       reinterpret_cast<const double*>(sb + TS_K * meta_bytes + (k + 1) * val_bytes))
+        } else if (more_stages) {
+          TS_LOAD_STEP(reinterpret_cast<const int*>(nb), reinterpret_cast<const double*>(nb + TS_K * meta_bytes))
+        }
+#pragma unroll
+        for (int d = 0; d < ND; d++) t -= pr[d];
+        if (cur_ndmax > ND) {  // rows with more operands than the unrolled body holds (ND == TS_MAXD only)
+          for (int d = ND; d < cur_ndmax; d++) {
+            const int o = Mk[TS_META_HDR + d * TS_ROWS + gq];
+            const double a0 = Vk[((LAY0 + d) * 3 + 0) * 32 + lane], a1 = Vk[((LAY0 + d) * 3 + 1) * 32 + lane],
+                         a2 = Vk[((LAY0 + d) * 3 + 2) * 32 + lane];
+            const double x0 = *reinterpret_cast<const double*>(xsc + o), x1 = *reinterpret_cast<const double*>(xsc + o + 8),
+                         x2 = *reinterpret_cast<const double*>(xsc + o + 16);
+            t -= a0 * x0 + a1 * x1 + a2 * x2;
+          }
         }
         if (FWD) {  // v_i = D_i^-1 t
           const double t0 = __shfl_sync(0xffffffffu, t, l0);
           const double t1 = __shfl_sync(0xffffffffu, t, (l0 + 1) & 31);
           const double t2 = __shfl_sync(0xffffffffu, t, (l0 + 2) & 31);
-          t = b_dd0 * t0 + b_dd1 * t1 + b_dd2 * t2;
+          t = e0 * t0 + e1 * t1 + e2 * t2;
         }
-        slot_out = b_slot;
-      } else {
-        // ---- generic path: everything after the previous step has completed
-        const int* M = reinterpret_cast<const int*>(stages + (size_t)st * A.stage_bytes);
-        const double* V = reinterpret_cast<const double*>(stages + (size_t)st * A.stage_bytes + A.stage_meta);
-        slot_out = act ? M[gq] : -1;
-        const int nd = act ? M[TS_ROWS + gq] : 0;
-        const int ndm = M[2 * TS_ROWS];
-        t = slot_out >= 0 ? xs[slot_out * 4 + r] : 0.0;
-        for (int d = 0; d < ndm; d++) {
-          const int sl = M[TS_META_HDR + d * TS_ROWS + gq];
-          const double a0 = V[(d * 3 + 0) * 32 + lane], a1 = V[(d * 3 + 1) * 32 + lane], a2 = V[(d * 3 + 2) * 32 + lane];
-          const double x0 = xs[sl * 4 + 0], x1 = xs[sl * 4 + 1], x2 = xs[sl * 4 + 2];
-          const double pd = a0 * x0 + a1 * x1 + a2 * x2;
-          t -= (d < nd) ? pd : 0.0;
-        }
-        if (FWD) {
-          const double t0 = __shfl_sync(0xffffffffu, t, l0);
-          const double t1 = __shfl_sync(0xffffffffu, t, (l0 + 1) & 31);
-          const double t2 = __shfl_sync(0xffffffffu, t, (l0 + 2) & 31);
-          const double d0 = V[(ndm * 3 + 0) * 32 + lane], d1 = V[(ndm * 3 + 1) * 32 + lane], d2 = V[(ndm * 3 + 2) * 32 + lane];
-          t = d0 * t0 + d1 * t1 + d2 * t2;
-        }
-        if (more) TS_PHASE_A(s + 1)
-      }
-      if (slot_out >= 0) xs[slot_out * 4 + r] = t;
-      __syncwarp();
-      if (dbg) c3 = clock64();
-      if (lane == 0) {
-        st_release_cta(&flags[0], (uint32_t)(s + 1));
-        mbar_arrive(&empty[st]);
-      }
-      if (dbg) {
+        *reinterpret_cast<double*>(xsc + cur_off) = t;
         __syncwarp();
-        w_comp += (unsigned long long)(c3 - c2);
-        w_sig += (unsigned long long)(clock64() - c3);
+        if (dbg) c3 = clock64();
+        if ((k & 1) == 1 && lane == 0) st_release_cta(&flags[0], (uint32_t)(sg * TS_K + k + 1));
+        if (last && lane == 0) mbar_arrive(&empty[st]);
+        if (dbg) {
+          __syncwarp();
+          w_comp += (unsigned long long)(c3 - c2);
+          w_sig += (unsigned long long)(clock64() - c3);
+        }
       }
     }
+#undef TS_LOAD_STEP
     if (dbg && lane == 0) {
       unsigned long long* o = A.dbg + (size_t)blockIdx.x * 8;
       o[0] = t_begin; o[1] = gtime_ns(); o[2] = w_mbar; o[3] = w_ghost; o[4] = w_comp; o[5] = w_sig;
       o[6] = (unsigned long long)nsteps; o[7] = (unsigned long long)strip;
     }
-#undef TS_PHASE_A
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- loader warp: TMA bulk copies, NST ahead
-    const unsigned char* meta = reinterpret_cast<const unsigned char*>(A.meta);
-    const double* packed = A.packed + (size_t)scene * A.nval;
-    for (int s0 = 0; s0 < nsteps; s0 += 32) {
-      const int n = min(32, nsteps - s0);
-      const int m = ms0 + s0 + min(lane, n - 1);
-      const int mo = A.meta_off[m], mo1 = A.meta_off[m + 1], vo = A.val_off[m], vo1 = A.val_off[m + 1];
-      for (int j = 0; j < n; j++) {
-        const int mo_j = __shfl_sync(0xffffffffu, mo, j), mb = __shfl_sync(0xffffffffu, mo1, j) - mo_j;
-        const int vo_j = __shfl_sync(0xffffffffu, vo, j), vb = (__shfl_sync(0xffffffffu, vo1, j) - vo_j) * 8;
-        if (lane == 0) {
-          const int s = s0 + j, st = s % TS_NST;
-          if (s >= TS_NST) mbar_wait(&empty[st], (uint32_t)(s / TS_NST - 1) & 1u);
-          unsigned char* dst = stages + (size_t)st * A.stage_bytes;
-          mbar_expect_tx(&full[st], (uint32_t)(mb + vb));
-          bulk_g2s(dst, meta + mo_j, (uint32_t)mb, &full[st]);
-          if (vb > 0) bulk_g2s(dst + A.stage_meta, packed + vo_j, (uint32_t)vb, &full[st]);
-        }
-        __syncwarp();
+    // ---------------------------------------------------------------- loader warp: TMA bulk copies, TS_NST stages ahead
+    if (lane == 0) {
+      const unsigned char* meta = reinterpret_cast<const unsigned char*>(A.meta) + (size_t)ms0 * meta_bytes;
+      const unsigned char* packed = reinterpret_cast<const unsigned char*>(A.packed + (size_t)scene * A.nval) + (size_t)ms0 * val_bytes;
+      const int nstage = nsteps / TS_K;
+      for (int sg = 0; sg < nstage; sg++) {
+        const int st = sg % TS_NST;
+        if (sg >= TS_NST) mbar_wait(&empty[st], (uint32_t)(sg / TS_NST - 1) & 1u);
+        unsigned char* dst = stages + (size_t)st * stage_bytes;
+        mbar_expect_tx(&full[st], (uint32_t)stage_bytes);
+        bulk_g2s(dst, meta + (size_t)sg * TS_K * meta_bytes, (uint32_t)(TS_K * meta_bytes), &full[st]);
+        bulk_g2s(dst + TS_K * meta_bytes, packed + (size_t)sg * TS_K * val_bytes, (uint32_t)(TS_K * val_bytes), &full[st]);
       }
     }
   } else if (warp == 2) {
     // ---------------------------------------------------------------- publisher warp
+    // copies finished rows to global memory and advances the strip's progress counter; the row ids of the next
+    // four micro-steps are prefetched while it waits, so a wake-up costs one store + one release
     unsigned long long* prog = A.progress + (size_t)scene * A.ns + strip;
+    const int q3 = lane / 3, qc = lane - q3 * 3;
+    const bool on = lane < 30;
     uint32_t pub = 0;
     while (pub < (uint32_t)nsteps) {
+      int rows[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        rows[j] = (on && pub + j < (uint32_t)nsteps) ? A.ms_rows[(size_t)(ms0 + pub + j) * TS_ROWS + q3] : -1;
       uint32_t d;
-      do { d = ld_acquire_cta(&flags[0]); } while (d <= pub);
-      const int items = (int)(d - pub) * 30;
-#pragma unroll 4
-      for (int it = lane; it < items; it += 32) {
-        const int s = (int)pub + it / 30, q = it - (it / 30) * 30;
-        const int row = A.ms_rows[(size_t)(ms0 + s) * TS_ROWS + q / 3];
-        if (row >= 0) {
-          const int p = FWD ? row : A.np - 1 - row;
-          out[(size_t)row * 3 + (q % 3)] = xs[(p - p0) * 4 + (q % 3)];
+      while ((d = ld_acquire_cta(&flags[0])) <= pub) __nanosleep(20);
+      d = min(d, pub + 4u);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (pub + j < d && rows[j] >= 0) {
+          const int p = FWD ? rows[j] : A.np - 1 - rows[j];
+          out[(size_t)rows[j] * 3 + qc] = xs[(p - p0) * 4 + qc];
         }
       }
       __syncwarp();
-      if (lane == 0) {
-        __threadfence();
-        st_release_gpu(prog, A.pbase + d);
-      }
+      if (lane == 0) st_release_gpu(prog, A.pbase + d);
       pub = d;
     }
   } else {
     // ---------------------------------------------------------------- import warp
+    // sliding window over the strip's ghost list (ordered by first use): every poll of the producer's progress
+    // counter imports ALL leading ghosts that are already published, so the import rate is not tied to the
+    // latency of one poll
     const int g0 = A.strip_gh[strip], ngh = A.strip_gh[strip + 1] - g0;
-    const int gl = lane / 3, comp = lane - gl * 3;
     const unsigned long long* prog = A.progress + (size_t)scene * A.ns;
-    const bool on = gl < TS_ROWS;
-    int row = 0, srcs = 0, need = 0;
-    if (on && gl < ngh) { row = A.gh_row[g0 + gl]; srcs = A.gh_src[g0 + gl]; need = A.gh_need[g0 + gl]; }
-    int cached_src = -1;
-    unsigned long long cached = 0;
-    for (int b = 0; b < ngh; b += TS_ROWS) {
-      const int gi = b + gl;
-      const bool mine = on && gi < ngh;
-      const int crow = row, csrc = srcs, cneed = need;
-      // prefetch the next batch's description before waiting on this one
-      const int gn = gi + TS_ROWS;
-      if (on && gn < ngh) { row = A.gh_row[g0 + gn]; srcs = A.gh_src[g0 + gn]; need = A.gh_need[g0 + gn]; }
-      if (mine) {
-        const unsigned long long want = A.pbase + (unsigned long long)cneed;
-        if (cached_src != csrc) { cached_src = csrc; cached = 0; }
-        while (cached < want) cached = ld_acquire_gpu(prog + csrc);
-        xs[(A.R + gi) * 4 + comp] = __ldcg(out + (size_t)crow * 3 + comp);
+    int w0 = 0;
+    while (w0 < ngh) {
+      const int gi = w0 + lane;
+      const bool in = gi < ngh;
+      const int row = in ? A.gh_row[g0 + gi] : 0, srcs = in ? A.gh_src[g0 + gi] : 0, need = in ? A.gh_need[g0 + gi] : 0;
+      const int src0 = __shfl_sync(0xffffffffu, srcs, 0);
+      int nlead = 0;
+      do {
+        const unsigned long long have = ld_acquire_gpu(prog + src0);
+        const bool ready = in && srcs == src0 && A.pbase + (unsigned long long)need <= have;
+        const unsigned m = __ballot_sync(0xffffffffu, ready);
+        nlead = __ffs(~m) - 1;  // number of leading ready ghosts (32 if all)
+        if (nlead < 0) nlead = 32;
+      } while (nlead == 0);
+      if (lane < nlead) {
+        const double v0 = __ldcg(out + (size_t)row * 3), v1 = __ldcg(out + (size_t)row * 3 + 1), v2 = __ldcg(out + (size_t)row * 3 + 2);
+        double* dst = xs + (size_t)(A.R + gi) * 4;
+        dst[0] = v0; dst[1] = v1; dst[2] = v2;
       }
       __syncwarp();
-      if (lane == 0) st_release_cta(&flags[1], (uint32_t)min(b + TS_ROWS, ngh));
+      w0 += nlead;
+      if (lane == 0) st_release_cta(&flags[1], (uint32_t)w0);
     }
   }
 }
@@ -743,14 +733,21 @@ static int pack_plan(Ctx* c, TriPlan& P) {
   return CLOTHGPU_OK;
 }
 
+template <bool FWD, int ND>
+static int launch_tri_nd(Ctx* c, const TriPlan& P, const TriArgs& A, int grid) {
+  CG_CUDA(cudaFuncSetAttribute(k_trisolve<FWD, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
+  k_trisolve<FWD, ND><<<grid, 128, P.smem_bytes, KS(c, FWD ? "k_trisolve_fwd" : "k_trisolve_bwd")>>>(A);
+  CG_LAUNCH_CHECK(c);
+  return CLOTHGPU_OK;
+}
+
 template <bool FWD>
 static int launch_tri(Ctx* c, TriPlan& P, double* vec, const double* src, bool skip_done) {
   TriArgs A;
   A.np = c->np; A.ns = P.ns; A.R = P.R; A.B = c->B;
-  A.stage_meta = round_up(P.max_meta_bytes, 128);
-  A.stage_bytes = A.stage_meta + round_up(std::max(P.max_val_bytes, 16), 128);
+  A.meta_stride = P.meta_stride; A.val_stride = P.val_stride; A.xs_rows = P.R + P.max_ghost + 2;
   A.nval = P.nval;
-  A.strip_ms = P.strip_ms; A.strip_gh = P.strip_gh; A.ms_rows = P.ms_rows; A.meta_off = P.meta_off; A.val_off = P.val_off;
+  A.strip_ms = P.strip_ms; A.strip_gh = P.strip_gh; A.ms_rows = P.ms_rows;
   A.gh_row = P.gh_row; A.gh_src = P.gh_src; A.gh_need = P.gh_need; A.meta = P.meta; A.packed = P.packed;
   A.progress = P.progress; A.ticket = P.ticket;
   A.pbase = P.pbase; A.tbase = P.tbase;
@@ -762,9 +759,16 @@ static int launch_tri(Ctx* c, TriPlan& P, double* vec, const double* src, bool s
     if (grid <= 4096) A.dbg = c->tri_dbg_buf + (FWD ? 0 : 8 * 4096);
     c->tri_dbg_grid[FWD ? 0 : 1] = grid;
   }
-  CG_CUDA(cudaFuncSetAttribute(k_trisolve<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
-  k_trisolve<FWD><<<grid, 128, P.smem_bytes, KS(c, FWD ? "k_trisolve_fwd" : "k_trisolve_bwd")>>>(A);
-  CG_LAUNCH_CHECK(c);
+  switch (std::min(std::max(P.ndmax, 1), (int)TS_MAXD)) {  // operand layers per micro-step
+    case 1: CG_CHECK((launch_tri_nd<FWD, 1>(c, P, A, grid))); break;
+    case 2: CG_CHECK((launch_tri_nd<FWD, 2>(c, P, A, grid))); break;
+    case 3: CG_CHECK((launch_tri_nd<FWD, 3>(c, P, A, grid))); break;
+    case 4: CG_CHECK((launch_tri_nd<FWD, 4>(c, P, A, grid))); break;
+    case 5: CG_CHECK((launch_tri_nd<FWD, 5>(c, P, A, grid))); break;
+    case 6: CG_CHECK((launch_tri_nd<FWD, 6>(c, P, A, grid))); break;
+    case 7: CG_CHECK((launch_tri_nd<FWD, 7>(c, P, A, grid))); break;
+    default: CG_CHECK((launch_tri_nd<FWD, 8>(c, P, A, grid))); break;
+  }
   P.pbase += (unsigned long long)P.max_steps + 2;
   P.tbase += (unsigned long long)grid;
   return CLOTHGPU_OK;
