@@ -249,6 +249,11 @@ static int build_topology(Ctx* c, const int* tri, const int* quad, const int* ro
       TriPlanHost H;
       CG_CHECK(build_triplan_host(np, rowptr, colidx, dia.data(), dir == 0, force_ns, H));
       CG_CHECK(upload_triplan(c, H, dir == 0 ? c->plan_f : c->plan_b));
+      if (dir == 0) {
+        FacPlanHost F;
+        CG_CHECK(build_facplan_host(np, rowptr, colidx, dia.data(), H, F));
+        CG_CHECK(upload_facplan(c, F, c->plan_fac));
+      }
     }
   }
 
@@ -512,6 +517,7 @@ void clothgpu_destroy(clothgpu_ctx* c) {
                   c->scratch, c->sort_keys, c->sort_keys2, c->sort_vals, c->sort_vals2};
   for (void* p : ptrs) cudaFree(p);
   cudaFree(c->tri_dbg_buf);
+  free_facplan(c->plan_fac);
   free_triplan(c->plan_f);
   free_triplan(c->plan_b);
   free_queues(c);

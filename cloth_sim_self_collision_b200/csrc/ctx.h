@@ -49,6 +49,23 @@ struct TriPlanHost {
   double sim_makespan = 0;
   std::vector<int> strip_ms, strip_gh, ms_rows, pk_src, gh_row, gh_src, gh_need, meta;
 };
+// strip-pipelined factorisation (ilufactor.cu): follows the forward sweep's strips and micro-steps
+enum { FC_H = 8, FC_NST = 3, FC_NIB = 3, FC_META_HDR = 48, FC_SMEM_HDR = 256 };
+struct FacPlanHost {
+  int ns = 0, R = 0, nms = 0, H = 0, gmaxB = 0, gmaxU = 0, gmaxOps = 0, max_imp = 0, meta_stride = 0, row_stride = 0;
+  int max_steps = 0;
+  std::vector<int> strip_ms, ms_rows, meta, pk_src, imp_ptr, imp_row, imp_src, imp_need;
+};
+struct FacPlan {
+  int ns = 0, R = 0, nms = 0, gmaxB = 0, gmaxU = 0, gmaxOps = 0, max_imp = 0, meta_stride = 0, row_stride = 0;
+  int max_steps = 0, smem_bytes = 0;
+  long long nval = 0;
+  int *strip_ms = nullptr, *meta = nullptr, *pk_src = nullptr, *imp_ptr = nullptr, *imp_row = nullptr, *imp_src = nullptr,
+      *imp_need = nullptr;
+  double *packed = nullptr, *uexp = nullptr;  // B x nval packed row blocks; B x np x gmaxU x 12 exported upper parts
+  unsigned long long *progress = nullptr, *ticket = nullptr;
+  unsigned long long pbase = 0, tbase = 0;
+};
 // its device image plus the per-context pipeline state
 struct TriPlan {
   bool fwd = true;
@@ -112,6 +129,7 @@ struct Ctx {
   int *lev_f_ptr = nullptr, *lev_f_rows = nullptr, *lev_b_ptr = nullptr, *lev_b_rows = nullptr;
   // strip-pipelined triangular solves
   TriPlan plan_f, plan_b;
+  FacPlan plan_fac;
   bool ilu_packed_valid = false;  // plan_*.packed mirrors iluDia / iluCrs
   bool tri_debug = false;         // clothgpu_debug_trisolve: per-CTA wait / compute cycle counters
   unsigned long long* tri_dbg_buf = nullptr;
@@ -218,6 +236,11 @@ int build_triplan_host(int np, const int* rowptr, const int* colidx, const int* 
 int verify_triplan_host(int np, const int* rowptr, const int* colidx, const int* dia, const TriPlanHost& P);
 int upload_triplan(Ctx* c, const TriPlanHost& H, TriPlan& D);
 void free_triplan(TriPlan& D);
+int build_facplan_host(int np, const int* rowptr, const int* colidx, const int* dia, const TriPlanHost& T, FacPlanHost& F);
+int verify_facplan_host(int np, const int* rowptr, const int* colidx, const int* dia, const TriPlanHost& T, const FacPlanHost& F);
+int upload_facplan(Ctx* c, const FacPlanHost& H, FacPlan& D);
+void free_facplan(FacPlan& D);
+int launch_ilu_factor_strips(Ctx* c);
 int run_pcg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out);
 int run_cg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out);
 int run_step_internal(Ctx* c, const clothgpu_params& p, bool use_ilu, double* conv_out, int* iter_out);

@@ -816,6 +816,11 @@ extern "C" int clothgpu_selftest_triplan(int np, const int* crs_rowptr, const in
     TriPlanHost P;
     CG_CHECK(build_triplan_host(np, crs_rowptr, crs_colidx, dia.data(), dir == 0, force_ns, P));
     CG_CHECK(verify_triplan_host(np, crs_rowptr, crs_colidx, dia.data(), P));
+    if (dir == 0) {  // the factorisation follows the forward sweep's schedule
+      FacPlanHost F;
+      CG_CHECK(build_facplan_host(np, crs_rowptr, crs_colidx, dia.data(), P, F));
+      CG_CHECK(verify_facplan_host(np, crs_rowptr, crs_colidx, dia.data(), P, F));
+    }
     if (stats) {
       int* o = stats + dir * 8;
       o[0] = P.ns; o[1] = P.R; o[2] = P.nms; o[3] = P.max_steps; o[4] = P.max_ghost; o[5] = (int)P.sim_makespan;

@@ -51,10 +51,32 @@ def main():
         for _ in range(reps):
             g.ilu_solve(G.BUF_VEC_Z)
         ms = g.timer_stop() / reps
+        g.timer_start()
+        for _ in range(5):
+            g.ilu_setvalue()
+            g.ilu_factor()
+        fms = g.timer_stop() / 5
+        print("grid %3d^2: setvalue + factor %.3f ms" % (n, fms))
         cyc = ms * 1e-3 * 1.965e9
         print("grid %3d^2 strips f/b %3d/%3d  R %5d  longest strip %4d ms  sim makespan %5d/%5d : %.3f ms per solve "
               "(fwd+bwd), %.0f cycles per simulated micro-step" %
               (n, st[0, 0], st[1, 0], st[0, 1], st[0, 3], st[0, 5], st[1, 5], ms, cyc / (st[0, 5] + st[1, 5])))
+        if os.environ.get("PROBE_DEBUG_FACTOR"):
+            cap = 256
+            out = np.zeros(2 * cap * 8, dtype=np.uint64)
+            nct = np.zeros(2, dtype=np.int32)
+            lib.clothgpu_debug_trisolve(g.h, 1, None, 0, None)
+            g.ilu_setvalue()
+            g.ilu_factor()
+            lib.clothgpu_debug_trisolve(g.h, 0, out.ctypes.data_as(C.c_void_p), cap, nct.ctypes.data_as(C.c_void_p))
+            rows = out.reshape(2, cap, 8)[0, :nct[0]]
+            rows = rows[np.argsort(rows[:, 7])]
+            t0 = rows[:, 0].min()
+            print("  factor: strip start_us end_us | per-step cycles: wait rows, wait imports, updates, tail | steps")
+            for r in rows[:: max(1, len(rows) // 8)]:
+                n_ = max(int(r[6]), 1)
+                print("   %3d %8.1f %8.1f | %6.0f %6.0f %6.0f %6.0f | %d" %
+                      (r[7], (r[0] - t0) / 1e3, (r[1] - t0) / 1e3, r[2] / n_, r[3] / n_, r[4] / n_, r[5] / n_, n_))
         if os.environ.get("PROBE_DEBUG"):
             cap = 256
             out = np.zeros(2 * cap * 8, dtype=np.uint64)
