@@ -131,10 +131,18 @@ def algorithmic_bytes(sc, nleaf):
     Cc = int(sc["rowptr"][-1])
     N = 2 * T - 1
     return {
-        # ILU values once + column indices + vector read/write (forward + backward) + fused copy of r
+        # level-scheduled single-CTA kernels (CLOTHGPU_TRISOLVE=levels): ILU values once + column indices + vector
         "k_ilu_solve": 72 * (P + Cc) + 4 * Cc + 8 * P + 48 * P + 24 * P,
-        # every ILU block read and written once
         "k_ilu_factor": 2 * 72 * (P + Cc),
+        # strip-pipelined sweeps: forward reads the lower blocks + D^-1, backward the upper blocks; column indices
+        # (4 B per block) and the vector read + written once each (24 B per row each way)
+        "k_trisolve_fwd": 72 * (Cc // 2 + P) + 4 * (Cc // 2) + 48 * P,
+        "k_trisolve_bwd": 72 * (Cc // 2) + 4 * (Cc // 2) + 48 * P,
+        # every ILU block read and written once, every finished upper block read once more by its consumers
+        "k_ilu_factor_strips": 2 * 72 * (P + Cc) + 72 * (Cc // 2),
+        # gather of the factor into lane order: every block read and written once
+        "k_pack": 2 * 72 * (P + Cc),
+        "k_pack_rows": 2 * 72 * (P + Cc),
         "k_matvec": 72 * (P + Cc) + 4 * Cc + 4 * P + 48 * P,
         # leaf pair entry (32 B) + 2 triangles (24 B) + 6 vertices x (x, v) (288 B)
         "k_narrow": nleaf * 344,
@@ -236,9 +244,10 @@ def run_ours(args):
                       c["clearance"], c["col_kind"], c["col_par"])
     Sn = args.scenes_per_gpu
     g = G.ClothGPU(sc, nscene=Sn, device=local)
-    for s in range(Sn):
-        gs = rank * Sn + s  # global scene index: config-5 style gravity-y perturbation (scene 0 = config 3 itself)
-        g.set_scene_gravity(s, (c["gravity"][0], 0.05 + 0.001 * gs, c["gravity"][2]))
+    from cloth_sim_self_collision_b200 import batch as BT
+    mine = BT.shard_scenes(world * Sn, world, rank)  # contiguous block of global scene indices of this rank
+    for s, gs in enumerate(mine):  # config-5 style gravity-y perturbation (scene 0 = config 3 itself)
+        g.set_scene_gravity(s, BT.scene_gravity(c["gravity"], gs))
     K, W = args.steps, args.warmup
     setup = max(0, args.setup_steps - W)
 
@@ -286,21 +295,16 @@ def run_ours(args):
     # ---- max over ranks
     if dist is not None:
         import torch
-        t = torch.tensor([ms_dev, ms_e2e, float(launches)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, ms_e2e = float(t[0]), float(t[1])
+        ms_dev, ms_e2e = BT.max_over_ranks(dist, [ms_dev, ms_e2e], device="cuda")
         tl = torch.tensor([float(launches)], device="cuda", dtype=torch.float64)
         dist.all_reduce(tl, op=dist.ReduceOp.SUM)
         launches_total = int(tl[0])
         # NCCL gathers the results (one checksum per scene; the north star's only collective)
-        chk = torch.tensor([float(np.dot(x, 1.0 + (np.arange(x.size) % 7))) for x, _ in end_state], device="cuda",
-                           dtype=torch.float64)
-        allchk = [torch.zeros_like(chk) for _ in range(world)]
-        dist.all_gather(allchk, chk)
-        checksums = [float(v) for tt in allchk for v in tt]
+        checksums = [float(v) for v in BT.gather_scene_values(dist, [BT.state_checksum(x) for x, _ in end_state],
+                                                              world * Sn, device="cuda")]
     else:
         launches_total = launches
-        checksums = [float(np.dot(x, 1.0 + (np.arange(x.size) % 7))) for x, _ in end_state]
+        checksums = [BT.state_checksum(x) for x, _ in end_state]
 
     nscene_total = world * Sn
     line = None
