@@ -50,15 +50,15 @@ struct TriPlanHost {
   std::vector<int> strip_ms, strip_gh, ms_rows, pk_src, gh_row, gh_src, gh_need, meta;
 };
 // strip-pipelined factorisation (ilufactor.cu): follows the forward sweep's strips and micro-steps
-enum { FC_H = 8, FC_NST = 3, FC_NIB = 3, FC_META_HDR = 48, FC_SMEM_HDR = 256 };
+enum { FC_H = 8, FC_NST = 3, FC_NIB = 3, FC_META_HDR = 48, FC_SMEM_HDR = 256, FC_BUNDLE = 3 };
 struct FacPlanHost {
   int ns = 0, R = 0, nms = 0, H = 0, gmaxB = 0, gmaxU = 0, gmaxOps = 0, max_imp = 0, meta_stride = 0, row_stride = 0;
-  int max_steps = 0;
+  int max_steps = 0, gmaxLo = 0, gT = 0, kg_stride = 0;
   std::vector<int> strip_ms, ms_rows, meta, pk_src, imp_ptr, imp_row, imp_src, imp_need;
 };
 struct FacPlan {
   int ns = 0, R = 0, nms = 0, gmaxB = 0, gmaxU = 0, gmaxOps = 0, max_imp = 0, meta_stride = 0, row_stride = 0;
-  int max_steps = 0, smem_bytes = 0;
+  int max_steps = 0, smem_bytes = 0, kg_stride = 0, gT = 0;
   long long nval = 0;
   int *strip_ms = nullptr, *meta = nullptr, *pk_src = nullptr, *imp_ptr = nullptr, *imp_row = nullptr, *imp_src = nullptr,
       *imp_need = nullptr;

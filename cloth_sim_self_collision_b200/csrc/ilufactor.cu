@@ -7,7 +7,9 @@
 // reuses the forward sweep's strips and micro-steps (trisolve.cu): one CTA per strip, <= 10 rows per micro-step,
 // three lanes per row -- lane r owns block-row r of every 3x3 block of its matrix row, so the update
 // A_ij -= A_ik U'_kj needs no cross-lane traffic.  Per micro-step
-//   * the row's blocks (packed by k_pack into 32-byte padded block rows) arrive by one TMA bulk copy per stage;
+//   * the row's blocks arrive by one TMA bulk copy per stage, packed by k_pack_rows into a lane-major layout
+//     ([block][column][lane], 8-byte lane stride): whatever block each row group addresses, the 16 lanes of a
+//     half-warp hit 16 distinct bank pairs, so the dynamic per-row block indices cost no bank conflicts;
 //   * the update list (ik, kj, ij) in the reference's order is applied in shared memory;
 //   * operands U'_k produced by this strip within the last FC_H micro-steps are read from a shared-memory ring;
 //     older ones and those of other strips are fetched by an import lane with TMA bulk copies from a padded
@@ -39,8 +41,8 @@ int build_facplan_host(int np, const int* rowptr, const int* colidx, const int* 
   }
   F.gmaxB = gB;
   F.gmaxU = std::max(gU, 1);
-  const int gstride = (gB + 1) * 96;  // bytes of one row group in the scratch: its blocks + one dummy block
-  const int urow = F.gmaxU * 96;       // bytes of one exported upper part
+  const int blk = 768;                 // bytes of one block of the scratch: [3 columns][32 lanes] doubles
+  const int urow = round_up(F.gmaxU * 72, 16);  // bytes of one exported upper part (dense 3x3 blocks, TMA granule)
   // update lists in the reference's order (DoILUDecomp, ilu_sparse.cpp:507-540)
   std::vector<int> op_ptr(np + 1, 0);
   std::vector<int> op_ik, op_kj, op_ij;  // crs slots; ij == -1: diagonal
@@ -63,11 +65,23 @@ int build_facplan_host(int np, const int* rowptr, const int* colidx, const int* 
       op_ptr[i + 1] = (int)op_ik.size();
     }
   }
-  int gOps = 0;
-  for (int i = 0; i < np; i++) gOps = std::max(gOps, op_ptr[i + 1] - op_ptr[i]);
-  F.gmaxOps = gOps;
-  F.meta_stride = round_up(FC_META_HDR + gOps * TS_ROWS * 4, 4);
-  F.row_stride = TS_ROWS * (gB + 1) * 12;  // doubles per micro-step of packed row data
+  // the updates of one row grouped by their lower block k ("k-group"): all updates of a group read the same A_ik
+  // and hit distinct targets, so they are mutually independent and can be issued as one bundle
+  int gOps = 0, gLo = 0, gT = 0;
+  for (int i = 0; i < np; i++) {
+    gOps = std::max(gOps, op_ptr[i + 1] - op_ptr[i]);
+    gLo = std::max(gLo, dia[i] - rowptr[i]);
+    int run = 0;
+    for (int o = op_ptr[i]; o < op_ptr[i + 1]; o++) {
+      run = (o > op_ptr[i] && op_ik[o] == op_ik[o - 1]) ? run + 1 : 1;
+      gT = std::max(gT, run);
+    }
+  }
+  gT = round_up(std::max(gT, 1), FC_BUNDLE);
+  F.gmaxOps = gOps; F.gmaxLo = gLo; F.gT = gT;
+  F.kg_stride = 12 + gT * TS_ROWS * 2;  // ints per k-group: A_ik offsets (10), bundle count, pad, then (kj, ij) pairs
+  F.meta_stride = round_up(FC_META_HDR + gLo * F.kg_stride, 4);
+  F.row_stride = (gB + 1) * 96;  // doubles per micro-step of packed row data: gB blocks + one dummy block
   F.meta.assign((size_t)F.nms * F.meta_stride, 0);
   F.pk_src.assign((size_t)F.nms * F.row_stride, -1);
   F.imp_ptr.assign(F.nms + 1, 0);
@@ -80,7 +94,8 @@ int build_facplan_host(int np, const int* rowptr, const int* colidx, const int* 
       const int row = F.ms_rows[(size_t)m * TS_ROWS + q];
       if (row >= 0) { ms_of_row[row] = m; q_of_row[row] = q; }
     }
-  const int ring_bytes = FC_H * TS_ROWS * urow;
+  // ring of finished upper parts: [step mod FC_H][upper block][9 entries][16 row slots] doubles, then a zero slot
+  const int ring_bytes = FC_H * F.gmaxU * 9 * 128;
   std::vector<int> imp_slot(np, -1), imp_stamp(np, -1);
   for (int k = 0; k < F.ns; k++) {
     for (int m = F.strip_ms[k]; m < F.strip_ms[k + 1]; m++) {
@@ -95,43 +110,55 @@ int build_facplan_host(int np, const int* rowptr, const int* colidx, const int* 
         M[24 + q] = row < 0 ? 0 : dia[row] - rowptr[row];
         M[34 + q] = row < 0 ? 0 : rowptr[row + 1] - dia[row];
         if (row < 0) continue;
-        nops = std::max(nops, op_ptr[row + 1] - op_ptr[row]);
         nupmax = std::max(nupmax, M[34 + q]);
         lomax = std::max(lomax, M[24 + q]);
-        // packed row data: blocks in crs order, the diagonal at block index gB-1, block rows padded to 4 doubles
+        // packed row data: blocks in crs order, the diagonal at block index gB-1; entry (r, c) of block b of row
+        // group q sits at [(b*3 + c)*32 + q*3 + r]
         const int nb = rowptr[row + 1] - rowptr[row];
         for (int b = 0; b < nb; b++)
           for (int r = 0; r < 3; r++)
-            for (int c = 0; c < 3; c++) V[(q * (gB + 1) + b) * 12 + r * 4 + c] = (rowptr[row] + b) * 9 + r * 3 + c;
+            for (int c = 0; c < 3; c++) V[(b * 3 + c) * 32 + q * 3 + r] = (rowptr[row] + b) * 9 + r * 3 + c;
         for (int r = 0; r < 3; r++)
-          for (int c = 0; c < 3; c++) V[(q * (gB + 1) + gB - 1) * 12 + r * 4 + c] = ncrs * 9 + row * 9 + r * 3 + c;
+          for (int c = 0; c < 3; c++) V[((gB - 1) * 3 + c) * 32 + q * 3 + r] = ncrs * 9 + row * 9 + r * 3 + c;
       }
-      for (int o = 0; o < gOps; o++)
+      for (int kg = 0; kg < gLo; kg++) {
+        int* K = &M[FC_META_HDR + kg * F.kg_stride];
+        int ntk = 0;
         for (int q = 0; q < TS_ROWS; q++) {
-          int* E = &M[FC_META_HDR + (o * TS_ROWS + q) * 4];
           const int row = F.ms_rows[(size_t)m * TS_ROWS + q];
-          const int dummy = q * gstride + gB * 96;
-          E[0] = dummy; E[1] = ring_bytes; E[2] = dummy; E[3] = 0;  // padding: dummy -= dummy * 0
-          if (row < 0 || o >= op_ptr[row + 1] - op_ptr[row]) continue;
-          const int ik = op_ik[op_ptr[row] + o], kj = op_kj[op_ptr[row] + o], ij = op_ij[op_ptr[row] + o];
-          const int kr = colidx[ik], u = kj - dia[kr];
-          E[0] = q * gstride + (ik - rowptr[row]) * 96;
-          E[2] = q * gstride + (ij < 0 ? gB - 1 : ij - rowptr[row]) * 96;
-          const int mk = ms_of_row[kr];
-          const bool same = kr / T.R == k;  // the factorisation follows the forward sweep: position == row index
-          if (same && mk < m && m - mk <= FC_H - 1) {
-            E[1] = (((mk - F.strip_ms[k]) % FC_H) * TS_ROWS + q_of_row[kr]) * urow + u * 96;
-          } else {
-            if (imp_stamp[kr] != m) {
-              imp_stamp[kr] = m;
-              imp_slot[kr] = nimp++;
-              F.imp_row.push_back(kr);
-              F.imp_src.push_back(kr / T.R);
-              F.imp_need.push_back(mk - F.strip_ms[kr / T.R] + 1);
+          const int dummy = gB * blk;
+          K[q] = dummy;
+          for (int t = 0; t < gT; t++) { K[12 + (t * TS_ROWS + q) * 2] = ring_bytes; K[12 + (t * TS_ROWS + q) * 2 + 1] = dummy; }
+          if (row < 0 || kg >= dia[row] - rowptr[row]) continue;
+          const int ik = rowptr[row] + kg, kr = colidx[ik];
+          K[q] = kg * blk;
+          int t = 0;
+          for (int o = op_ptr[row]; o < op_ptr[row + 1]; o++) {
+            if (op_ik[o] != ik) continue;
+            const int kj = op_kj[o], ij = op_ij[o], u = kj - dia[kr];
+            int* E = &K[12 + (t * TS_ROWS + q) * 2];
+            E[1] = (ij < 0 ? gB - 1 : ij - rowptr[row]) * blk;
+            const int mk = ms_of_row[kr];
+            const bool same = kr / T.R == k;  // the factorisation follows the forward sweep: position == row index
+            if (same && mk < m && m - mk <= FC_H - 1) {
+              E[0] = ((((mk - F.strip_ms[k]) % FC_H) * F.gmaxU + u) * 9 * 16 + q_of_row[kr]) * 8;
+            } else {
+              if (imp_stamp[kr] != m) {
+                imp_stamp[kr] = m;
+                imp_slot[kr] = nimp++;
+                F.imp_row.push_back(kr);
+                F.imp_src.push_back(kr / T.R);
+                F.imp_need.push_back(mk - F.strip_ms[kr / T.R] + 1);
+              }
+              E[0] = -1 - (imp_slot[kr] * urow + u * 72);
             }
-            E[1] = -1 - (imp_slot[kr] * urow + u * 96);
+            t++;
           }
+          ntk = std::max(ntk, t);
         }
+        K[10] = round_up(ntk, FC_BUNDLE);
+      }
+      nops = lomax;  // number of k-groups this micro-step runs
       M[0] = nops; M[1] = nimp; M[2] = nupmax; M[3] = lomax;
       (void)ml;
       F.imp_ptr[m + 1] = (int)F.imp_row.size();
@@ -149,7 +176,7 @@ int verify_facplan_host(int np, const int* rowptr, const int* colidx, const int*
                         const FacPlanHost& F) {
 #define PLAN_FAIL(msg) do { set_error(std::string("factor plan: ") + msg); return CLOTHGPU_ERR_STATE; } while (0)
   const int ncrs = rowptr[np];
-  const int gB = F.gmaxB, gstride = (gB + 1) * 96, urow = F.gmaxU * 96, ring_bytes = FC_H * TS_ROWS * urow;
+  const int gB = F.gmaxB, blk = 768, urow = round_up(F.gmaxU * 72, 16), ring_bytes = FC_H * F.gmaxU * 9 * 128;
   std::vector<int> ms_of_row(np, -1), q_of_row(np, -1);
   for (int m = 0; m < F.nms; m++)
     for (int q = 0; q < TS_ROWS; q++) {
@@ -172,50 +199,60 @@ int verify_facplan_host(int np, const int* rowptr, const int* colidx, const int*
         const int row = F.ms_rows[(size_t)m * TS_ROWS + q];
         if (M[4 + q] != row) PLAN_FAIL("row id");
         if (row < 0) {
-          for (int o = 0; o < F.gmaxOps; o++) {
-            const int* E = &M[FC_META_HDR + (o * TS_ROWS + q) * 4];
-            if (E[0] != q * gstride + gB * 96 || E[1] != ring_bytes || E[2] != E[0]) PLAN_FAIL("padding op");
+          for (int kg = 0; kg < F.gmaxLo; kg++) {
+            const int* K = &M[FC_META_HDR + kg * F.kg_stride];
+            if (K[q] != gB * blk) PLAN_FAIL("padding k-group of an unused lane");
+            for (int t = 0; t < F.gT; t++)
+              if (K[12 + (t * TS_ROWS + q) * 2] != ring_bytes || K[12 + (t * TS_ROWS + q) * 2 + 1] != K[q]) PLAN_FAIL("padding update of an unused lane");
           }
           continue;
         }
         if (M[14 + q] != rowptr[row] || M[24 + q] != dia[row] - rowptr[row] || M[34 + q] != rowptr[row + 1] - dia[row]) PLAN_FAIL("row header");
         for (int b = 0; b < rowptr[row + 1] - rowptr[row]; b++)
           for (int r = 0; r < 3; r++)
-            for (int c = 0; c < 4; c++)
-              if (V[(q * (gB + 1) + b) * 12 + r * 4 + c] != (c < 3 ? (rowptr[row] + b) * 9 + r * 3 + c : -1)) PLAN_FAIL("packed block");
+            for (int c = 0; c < 3; c++)
+              if (V[(b * 3 + c) * 32 + q * 3 + r] != (rowptr[row] + b) * 9 + r * 3 + c) PLAN_FAIL("packed block");
         for (int r = 0; r < 3; r++)
-          for (int c = 0; c < 3; c++)
-            if (V[(q * (gB + 1) + gB - 1) * 12 + r * 4 + c] != ncrs * 9 + row * 9 + r * 3 + c) PLAN_FAIL("packed diagonal");
-        // replay the reference's update order
+          for (int c = 0; c < 3; c++) {
+            if (V[((gB - 1) * 3 + c) * 32 + q * 3 + r] != ncrs * 9 + row * 9 + r * 3 + c) PLAN_FAIL("packed diagonal");
+            if (V[(gB * 3 + c) * 32 + q * 3 + r] != -1) PLAN_FAIL("dummy block must be empty");
+          }
+        // replay the reference's update order: k ascending, within k the upper blocks of row k ascending
         for (int j = rowptr[row]; j < rowptr[row + 1]; j++) slot[colidx[j]] = j;
-        int o = 0;
         for (int ik = rowptr[row]; ik < dia[row]; ik++) {
-          const int kr = colidx[ik];
+          const int kr = colidx[ik], kg = ik - rowptr[row];
+          if (kg >= M[0]) PLAN_FAIL("k-group count");
+          const int* K = &M[FC_META_HDR + kg * F.kg_stride];
+          if (K[q] != kg * blk) PLAN_FAIL("A_ik offset");
+          int t = 0;
           for (int kj = dia[kr]; kj < rowptr[kr + 1]; kj++) {
             const int jc = colidx[kj];
             int ij;
             if (jc == row) ij = -1;
             else if (slot[jc] >= 0) ij = slot[jc];
             else continue;
-            if (o >= M[0]) PLAN_FAIL("update list too short");
-            const int* E = &M[FC_META_HDR + (o * TS_ROWS + q) * 4];
-            if (E[0] != q * gstride + (ik - rowptr[row]) * 96) PLAN_FAIL("op ik");
-            if (E[2] != q * gstride + (ij < 0 ? gB - 1 : ij - rowptr[row]) * 96) PLAN_FAIL("op ij");
+            if (t >= K[10] || t >= F.gT) PLAN_FAIL("bundle too short");
+            const int* E = &K[12 + (t * TS_ROWS + q) * 2];
+            if (E[1] != (ij < 0 ? gB - 1 : ij - rowptr[row]) * blk) PLAN_FAIL("op ij");
             const int u = kj - dia[kr], mk = ms_of_row[kr];
-            if (E[1] >= 0) {
+            if (E[0] >= 0) {
               if (kr / T.R != k || mk >= m || m - mk > FC_H - 1) PLAN_FAIL("ring operand out of reach");
-              if (E[1] != (((mk - F.strip_ms[k]) % FC_H) * TS_ROWS + q_of_row[kr]) * urow + u * 96) PLAN_FAIL("ring operand offset");
+              if (E[0] != ((((mk - F.strip_ms[k]) % FC_H) * F.gmaxU + u) * 9 * 16 + q_of_row[kr]) * 8) PLAN_FAIL("ring operand offset");
             } else {
-              const int off = -1 - E[1], e = off / urow;
-              if (e >= nimp || F.imp_row[i0 + e] != kr || off % urow != u * 96) PLAN_FAIL("import operand");
+              const int off = -1 - E[0], e = off / urow;
+              if (e >= nimp || F.imp_row[i0 + e] != kr || off % urow != u * 72) PLAN_FAIL("import operand");
             }
-            o++;
+            t++;
+          }
+          for (; t < F.gT; t++) {
+            const int* E = &K[12 + (t * TS_ROWS + q) * 2];
+            if (E[0] != ring_bytes || E[1] != gB * blk) PLAN_FAIL("padding update");
           }
         }
         for (int j = rowptr[row]; j < rowptr[row + 1]; j++) slot[colidx[j]] = -1;
-        for (; o < F.gmaxOps; o++) {
-          const int* E = &M[FC_META_HDR + (o * TS_ROWS + q) * 4];
-          if (E[0] != q * gstride + gB * 96 || E[1] != ring_bytes || E[2] != E[0]) PLAN_FAIL("padding op after the list");
+        for (int kg = dia[row] - rowptr[row]; kg < F.gmaxLo; kg++) {
+          const int* K = &M[FC_META_HDR + kg * F.kg_stride];
+          if (K[q] != gB * blk) PLAN_FAIL("padding k-group");
         }
       }
     }
@@ -234,19 +271,21 @@ static int up(T** p, const std::vector<T>& h) {
 int upload_facplan(Ctx* c, const FacPlanHost& H, FacPlan& D) {
   D.ns = H.ns; D.R = H.R; D.nms = H.nms; D.gmaxB = H.gmaxB; D.gmaxU = H.gmaxU; D.gmaxOps = H.gmaxOps;
   D.max_imp = H.max_imp; D.meta_stride = H.meta_stride; D.row_stride = H.row_stride; D.max_steps = H.max_steps;
+  D.kg_stride = H.kg_stride; D.gT = H.gT;
   D.nval = (long long)H.pk_src.size();
   CG_CHECK(up(&D.strip_ms, H.strip_ms)); CG_CHECK(up(&D.meta, H.meta)); CG_CHECK(up(&D.pk_src, H.pk_src));
   CG_CHECK(up(&D.imp_ptr, H.imp_ptr)); CG_CHECK(up(&D.imp_row, H.imp_row)); CG_CHECK(up(&D.imp_src, H.imp_src));
   CG_CHECK(up(&D.imp_need, H.imp_need));
   CG_CUDA(cudaMalloc((void**)&D.packed, sizeof(double) * (size_t)std::max<long long>(D.nval, 1) * c->B));
-  CG_CUDA(cudaMalloc((void**)&D.uexp, sizeof(double) * (size_t)c->np * D.gmaxU * 12 * c->B));
-  CG_CUDA(cudaMemset(D.uexp, 0, sizeof(double) * (size_t)c->np * D.gmaxU * 12 * c->B));
+  const size_t uexp_bytes = (size_t)c->np * round_up(D.gmaxU * 72, 16) * c->B;
+  CG_CUDA(cudaMalloc((void**)&D.uexp, uexp_bytes));
+  CG_CUDA(cudaMemset(D.uexp, 0, uexp_bytes));
   CG_CUDA(cudaMalloc((void**)&D.progress, sizeof(unsigned long long) * (size_t)H.ns * c->B));
   CG_CUDA(cudaMemset(D.progress, 0, sizeof(unsigned long long) * (size_t)H.ns * c->B));
   CG_CUDA(cudaMalloc((void**)&D.ticket, sizeof(unsigned long long)));
   CG_CUDA(cudaMemset(D.ticket, 0, sizeof(unsigned long long)));
-  const int urow = D.gmaxU * 96;
-  D.smem_bytes = FC_SMEM_HDR + FC_H * TS_ROWS * urow + 96 + FC_NIB * std::max(D.max_imp, 1) * urow +
+  const int urow = round_up(D.gmaxU * 72, 16);
+  D.smem_bytes = FC_SMEM_HDR + FC_H * D.gmaxU * 9 * 128 + 9 * 128 + FC_NIB * round_up(std::max(D.max_imp, 1) * urow, 128) +
                  FC_NST * (D.meta_stride * 4 + D.row_stride * 8);
   if (D.smem_bytes > 227 * 1024) { set_error("factor plan does not fit shared memory"); return CLOTHGPU_ERR_CAPACITY; }
   return CLOTHGPU_OK;
@@ -309,7 +348,7 @@ __device__ __forceinline__ void f_st_release_gpu(unsigned long long* p, unsigned
 
 struct FacArgs {
   int np, ncrs, ns, B;
-  int gmaxB, gmaxU, meta_stride, row_stride, max_imp;
+  int gmaxB, gmaxU, meta_stride, row_stride, max_imp, kg_stride;
   long long nval;
   const int *strip_ms, *meta, *imp_ptr, *imp_row, *imp_src, *imp_need;
   const double* packed;
@@ -327,14 +366,13 @@ __global__ void __launch_bounds__(128, 1) k_ilu_factor_strips(const FacArgs A) {
   uint64_t* empty = full + FC_NST;                            // FC_NST
   uint64_t* ifull = empty + FC_NST;                           // FC_NIB
   uint32_t* flags = reinterpret_cast<uint32_t*>(smem + 128);  // [0] micro-steps done, [2] ticket
-  const int urow = A.gmaxU * 96;
-  const int ring_bytes = FC_H * TS_ROWS * urow;
-  unsigned char* ring = smem + FC_SMEM_HDR;          // + zero block right behind it
-  unsigned char* imp = ring + ring_bytes + 96;
-  const int imp_bytes = max(A.max_imp, 1) * urow;
+  const int urow = (A.gmaxU * 72 + 15) / 16 * 16;     // bytes of one exported upper part (dense 3x3 blocks)
+  const int ring_bytes = FC_H * A.gmaxU * 9 * 128;    // [step mod FC_H][upper block][entry][16 row slots] doubles
+  unsigned char* ring = smem + FC_SMEM_HDR;          // + a zero slot (9 entries, 128-byte stride) right behind it
+  unsigned char* imp = ring + ring_bytes + 9 * 128;
+  const int imp_bytes = (max(A.max_imp, 1) * urow + 127) / 128 * 128;
   unsigned char* stages = imp + (size_t)FC_NIB * imp_bytes;
   const int meta_bytes = A.meta_stride * 4, row_bytes = A.row_stride * 8, stage_bytes = meta_bytes + row_bytes;
-  const int gstride = (A.gmaxB + 1) * 96;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
@@ -347,8 +385,8 @@ __global__ void __launch_bounds__(128, 1) k_ilu_factor_strips(const FacArgs A) {
   const int ms0 = A.strip_ms[strip], nsteps = A.strip_ms[strip + 1] - ms0;
   double* dia = A.iluDia + (size_t)scene * A.np * 9;
   double* crs = A.iluCrs + (size_t)scene * A.ncrs * 9;
-  double* uexp = A.uexp + (size_t)scene * A.np * A.gmaxU * 12;
-  if (tid < 12) reinterpret_cast<double*>(ring + ring_bytes)[tid] = 0.0;  // zero operand of the padding updates
+  double* uexp = A.uexp + (size_t)scene * A.np * (urow / 8);
+  for (int i = tid; i < 9 * 16; i += blockDim.x) reinterpret_cast<double*>(ring + ring_bytes)[i] = 0.0;  // zero operand of the padding updates
   if (tid == 0) {
     for (int i = 0; i < FC_NST; i++) { f_mbar_init(&full[i], 1); f_mbar_init(&empty[i], 1); }
     for (int i = 0; i < FC_NIB; i++) f_mbar_init(&ifull[i], 1);
@@ -379,29 +417,41 @@ __global__ void __launch_bounds__(128, 1) k_ilu_factor_strips(const FacArgs A) {
       const unsigned char* ib = imp + (size_t)(m % FC_NIB) * imp_bytes;
       const int nops = M[0], nupmax = M[2], lomax = M[3];
       const int row = act ? M[4 + gq] : -1;
-      // ---- updates A_ij -= A_ik U'_kj in the reference's order; lane r owns block-row r
-      int4 e_next = *reinterpret_cast<const int4*>(M + FC_META_HDR + gq * 4);
-      for (int o = 0; o < nops; o++) {
-        const int4 e = e_next;
-        // the next update's addresses do not depend on this update's stores: fetch them first
-        e_next = *reinterpret_cast<const int4*>(M + FC_META_HDR + ((o + 1 < nops ? o + 1 : o) * TS_ROWS + gq) * 4);
-        const unsigned char* pk = sc + e.x + r * 32;
-        const unsigned char* pb = e.y >= 0 ? ring + e.y : ib + (-1 - e.y);
-        unsigned char* pt = sc + e.z + r * 32;
-        const double2 a01 = *reinterpret_cast<const double2*>(pk);
-        const double a2 = *reinterpret_cast<const double*>(pk + 16);
-        const double2 b00 = *reinterpret_cast<const double2*>(pb), b10 = *reinterpret_cast<const double2*>(pb + 32),
-                      b20 = *reinterpret_cast<const double2*>(pb + 64);
-        const double b02 = *reinterpret_cast<const double*>(pb + 16), b12 = *reinterpret_cast<const double*>(pb + 48),
-                     b22 = *reinterpret_cast<const double*>(pb + 80);
-        double2 t01 = *reinterpret_cast<const double2*>(pt);
-        double t2 = *reinterpret_cast<const double*>(pt + 16);
-        t01.x = t01.x - (a01.x * b00.x + a01.y * b10.x + a2 * b20.x);
-        t01.y = t01.y - (a01.x * b00.y + a01.y * b10.y + a2 * b20.y);
-        t2 = t2 - (a01.x * b02 + a01.y * b12 + a2 * b22);
-        if (act) {
-          *reinterpret_cast<double2*>(pt) = t01;
-          *reinterpret_cast<double*>(pt + 16) = t2;
+      // ---- updates A_ij -= A_ik U'_kj in the reference's order; lane r owns block-row r.  The updates of one lower
+      // block k hit distinct targets: they are issued FC_BUNDLE at a time (loads, then math, then stores) so that
+      // their latencies overlap; consecutive k-groups are ordered by program order (a later A_ik may be a target)
+      for (int kg = 0; kg < nops; kg++) {
+        const int* K = M + FC_META_HDR + kg * A.kg_stride;
+        const unsigned char* pk = sc + K[gq] + lane * 8;  // entry (r, c) of a block: [(c*32 + lane)*8]
+        const int ntk = K[10];
+        const double a0 = *reinterpret_cast<const double*>(pk), a1 = *reinterpret_cast<const double*>(pk + 256),
+                     a2 = *reinterpret_cast<const double*>(pk + 512);
+        for (int t0 = 0; t0 < ntk; t0 += FC_BUNDLE) {
+          unsigned char* pt[FC_BUNDLE];
+          double b[FC_BUNDLE][9], t[FC_BUNDLE][3];
+#pragma unroll
+          for (int j = 0; j < FC_BUNDLE; j++) {
+            const int2 e = *reinterpret_cast<const int2*>(K + 12 + ((t0 + j) * TS_ROWS + gq) * 2);
+            // operand U'_kj: ring entries are 128 bytes apart (one slot per producer row), imported ones are dense
+            const unsigned char* pb = e.x >= 0 ? ring + e.x : ib + (-1 - e.x);
+            const int es = e.x >= 0 ? 128 : 8;
+            pt[j] = sc + e.y + lane * 8;
+#pragma unroll
+            for (int k = 0; k < 9; k++) b[j][k] = *reinterpret_cast<const double*>(pb + k * es);
+#pragma unroll
+            for (int k = 0; k < 3; k++) t[j][k] = *reinterpret_cast<const double*>(pt[j] + k * 256);
+          }
+#pragma unroll
+          for (int j = 0; j < FC_BUNDLE; j++) {
+            t[j][0] = t[j][0] - (a0 * b[j][0] + a1 * b[j][3] + a2 * b[j][6]);
+            t[j][1] = t[j][1] - (a0 * b[j][1] + a1 * b[j][4] + a2 * b[j][7]);
+            t[j][2] = t[j][2] - (a0 * b[j][2] + a1 * b[j][5] + a2 * b[j][8]);
+          }
+#pragma unroll
+          for (int j = 0; j < FC_BUNDLE; j++) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) *reinterpret_cast<double*>(pt[j] + k * 256) = t[j][k];
+          }
         }
       }
       __syncwarp();
@@ -409,13 +459,11 @@ __global__ void __launch_bounds__(128, 1) k_ilu_factor_strips(const FacArgs A) {
       // ---- D_i <- D_i^-1 by cofactors (CalcInvMat3, ilu_sparse.cpp:77-97); a singular pivot is left as is (:541-551)
       double a[9];
       {
-        const unsigned char* pd = sc + gq * gstride + (A.gmaxB - 1) * 96;
+        const unsigned char* pd = sc + (A.gmaxB - 1) * 768 + gq * 24;
 #pragma unroll
-        for (int rr = 0; rr < 3; rr++) {
-          const double2 v01 = *reinterpret_cast<const double2*>(pd + rr * 32);
-          a[rr * 3 + 0] = v01.x; a[rr * 3 + 1] = v01.y;
-          a[rr * 3 + 2] = *reinterpret_cast<const double*>(pd + rr * 32 + 16);
-        }
+        for (int rr = 0; rr < 3; rr++)
+#pragma unroll
+          for (int cc = 0; cc < 3; cc++) a[rr * 3 + cc] = *reinterpret_cast<const double*>(pd + cc * 256 + rr * 8);
         const double det = +a[0] * a[4] * a[8] + a[3] * a[7] * a[2] + a[6] * a[1] * a[5] - a[0] * a[7] * a[5] -
                            a[6] * a[4] * a[2] - a[3] * a[1] * a[8];
         if (fabs(det) > 1.0e-30) {
@@ -445,34 +493,42 @@ __global__ void __launch_bounds__(128, 1) k_ilu_factor_strips(const FacArgs A) {
         o[0] = ar0; o[1] = ar1; o[2] = ar2;
       }
       // ---- U'_ij = D_i^-1 U_ij (:556-567): to the ring (next steps of this strip), the ILU array and the export copy
-      unsigned char* myring = ring + (size_t)((m % FC_H) * TS_ROWS + gq) * urow + r * 32;
-      for (int u = 0; u < nupmax; u++) {
-        const unsigned char* pu = sc + gq * gstride + (nlo + (u < nup ? u : 0)) * 96;
-        const double2 c0 = *reinterpret_cast<const double2*>(pu), c1 = *reinterpret_cast<const double2*>(pu + 32),
-                      c2 = *reinterpret_cast<const double2*>(pu + 64);
-        const double c02 = *reinterpret_cast<const double*>(pu + 16), c12 = *reinterpret_cast<const double*>(pu + 48),
-                     c22 = *reinterpret_cast<const double*>(pu + 80);
-        const double v0 = ar0 * c0.x + ar1 * c1.x + ar2 * c2.x;
-        const double v1 = ar0 * c0.y + ar1 * c1.y + ar2 * c2.y;
-        const double v2 = ar0 * c02 + ar1 * c12 + ar2 * c22;
-        if (row >= 0 && u < nup) {
-          *reinterpret_cast<double2*>(myring + u * 96) = make_double2(v0, v1);
-          *reinterpret_cast<double*>(myring + u * 96 + 16) = v2;
-          double* oc = crs + (size_t)(crs0 + nlo + u) * 9 + r * 3;
-          oc[0] = v0; oc[1] = v1; oc[2] = v2;
-          double* ou = uexp + ((size_t)row * A.gmaxU + u) * 12 + r * 4;
-          *reinterpret_cast<double2*>(ou) = make_double2(v0, v1);
-          ou[2] = v2;
+      unsigned char* myring = ring + (size_t)((m % FC_H) * A.gmaxU * 9 * 16 + gq) * 8 + r * 3 * 128;
+      for (int u0 = 0; u0 < nupmax; u0 += FC_BUNDLE) {
+        double v[FC_BUNDLE][3];
+#pragma unroll
+        for (int j = 0; j < FC_BUNDLE; j++) {
+          const int u = u0 + j;
+          const unsigned char* pu = sc + (nlo + (u < nup ? u : 0)) * 768 + gq * 24;  // entry (r', c): + c*256 + r'*8
+          double cb[9];
+#pragma unroll
+          for (int rr = 0; rr < 3; rr++)
+#pragma unroll
+            for (int cc = 0; cc < 3; cc++) cb[rr * 3 + cc] = *reinterpret_cast<const double*>(pu + cc * 256 + rr * 8);
+          v[j][0] = ar0 * cb[0] + ar1 * cb[3] + ar2 * cb[6];
+          v[j][1] = ar0 * cb[1] + ar1 * cb[4] + ar2 * cb[7];
+          v[j][2] = ar0 * cb[2] + ar1 * cb[5] + ar2 * cb[8];
+        }
+#pragma unroll
+        for (int j = 0; j < FC_BUNDLE; j++) {
+          const int u = u0 + j;
+          if (row >= 0 && u < nup) {
+#pragma unroll
+            for (int cc = 0; cc < 3; cc++) *reinterpret_cast<double*>(myring + (size_t)(u * 9 + cc) * 128) = v[j][cc];
+            double* oc = crs + (size_t)(crs0 + nlo + u) * 9 + r * 3;
+            oc[0] = v[j][0]; oc[1] = v[j][1]; oc[2] = v[j][2];
+            double* ou = uexp + (size_t)row * (urow / 8) + u * 9 + r * 3;
+            ou[0] = v[j][0]; ou[1] = v[j][1]; ou[2] = v[j][2];
+          }
         }
       }
       // ---- the finished lower part L_ik
       for (int b = 0; b < lomax; b++) {
         if (row >= 0 && b < nlo) {
-          const unsigned char* pl = sc + gq * gstride + b * 96 + r * 32;
-          const double2 l01 = *reinterpret_cast<const double2*>(pl);
-          const double l2 = *reinterpret_cast<const double*>(pl + 16);
+          const unsigned char* pl = sc + b * 768 + lane * 8;
           double* oc = crs + (size_t)(crs0 + b) * 9 + r * 3;
-          oc[0] = l01.x; oc[1] = l01.y; oc[2] = l2;
+          oc[0] = *reinterpret_cast<const double*>(pl); oc[1] = *reinterpret_cast<const double*>(pl + 256);
+          oc[2] = *reinterpret_cast<const double*>(pl + 512);
         }
       }
       __syncwarp();
@@ -544,7 +600,7 @@ __global__ void __launch_bounds__(128, 1) k_ilu_factor_strips(const FacArgs A) {
           while (cached < want) cached = f_ld_acquire_gpu(prog + src);
           // the producer's stores went through the generic proxy; order them before the async-proxy read
           asm volatile("fence.proxy.async.global;" ::: "memory");
-          f_bulk_g2s(imp + (size_t)ibuf * imp_bytes + (size_t)e * urow, uexp + (size_t)kr * A.gmaxU * 12, (uint32_t)urow, &ifull[ibuf]);
+          f_bulk_g2s(imp + (size_t)ibuf * imp_bytes + (size_t)e * urow, uexp + (size_t)kr * (urow / 8), (uint32_t)urow, &ifull[ibuf]);
         }
       }
     }
@@ -574,7 +630,7 @@ int launch_ilu_factor_strips(Ctx* c) {
   }
   FacArgs A;
   A.np = c->np; A.ncrs = c->ncrs; A.ns = P.ns; A.B = c->B;
-  A.gmaxB = P.gmaxB; A.gmaxU = P.gmaxU; A.meta_stride = P.meta_stride; A.row_stride = P.row_stride; A.max_imp = P.max_imp;
+  A.gmaxB = P.gmaxB; A.gmaxU = P.gmaxU; A.meta_stride = P.meta_stride; A.row_stride = P.row_stride; A.max_imp = P.max_imp; A.kg_stride = P.kg_stride;
   A.nval = P.nval;
   A.strip_ms = P.strip_ms; A.meta = P.meta; A.imp_ptr = P.imp_ptr; A.imp_row = P.imp_row; A.imp_src = P.imp_src;
   A.imp_need = P.imp_need; A.packed = P.packed; A.uexp = P.uexp; A.iluDia = c->iluDia; A.iluCrs = c->iluCrs;
