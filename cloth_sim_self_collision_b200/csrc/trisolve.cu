@@ -151,7 +151,9 @@ int build_triplan_host(int np, const int* rowptr, const int* colidx, const int* 
     make_sched(np, lev, fwd, R, S);
     int mg = 0;
     const double t = simulate(np, rowptr, colidx, dia, fwd, S, 8.0, &mg);
-    const long long smem = (long long)(R + mg + 2) * 32 + ring_bytes;
+    int longest = 0;
+    for (int k2 = 0; k2 < S.ns; k2++) longest = std::max(longest, S.strip_ms[k2 + 1] - S.strip_ms[k2]);
+    const long long smem = (long long)(R + mg + 2) * 32 + ring_bytes + (long long)longest * TS_ROWS * 4 + (long long)mg * 12 + 16;
     const bool fits = smem <= smem_budget;
     if (fits && (best_t < 0 || t < best_t)) {
       best_t = t;
@@ -173,7 +175,9 @@ int build_triplan_host(int np, const int* rowptr, const int* colidx, const int* 
       make_sched(np, lev, fwd, R, S);
       int mg = 0;
       const double t = simulate(np, rowptr, colidx, dia, fwd, S, 8.0, &mg);
-      if ((long long)(R + mg + 2) * 32 + ring_bytes <= smem_budget) { best_t = t; best = std::move(S); best_ghost = mg; break; }
+      int longest = 0;
+      for (int k2 = 0; k2 < S.ns; k2++) longest = std::max(longest, S.strip_ms[k2 + 1] - S.strip_ms[k2]);
+      if ((long long)(R + mg + 2) * 32 + ring_bytes + (long long)longest * TS_ROWS * 4 + (long long)mg * 12 + 16 <= smem_budget) { best_t = t; best = std::move(S); best_ghost = mg; break; }
     }
   }
   const Sched& S = best;
@@ -391,7 +395,8 @@ int upload_triplan(Ctx* c, const TriPlanHost& H, TriPlan& D) {
   CG_CUDA(cudaMemset(D.ticket, 0, sizeof(unsigned long long)));
   D.pbase = 0;
   D.tbase = 0;
-  D.smem_bytes = TS_SMEM_HDR + (D.R + D.max_ghost + 2) * 32 + TS_NST * TS_K * (D.meta_stride * 4 + D.val_stride * 8);
+  D.smem_bytes = TS_SMEM_HDR + (D.R + D.max_ghost + 2) * 32 + TS_NST * TS_K * (D.meta_stride * 4 + D.val_stride * 8) +
+                 D.max_steps * TS_ROWS * 4 + D.max_ghost * 12 + 16;
   return CLOTHGPU_OK;
 }
 
@@ -455,6 +460,7 @@ struct TriArgs {
   int np, ns, R, B;
   int meta_stride, val_stride;  // ints / doubles per micro-step
   int xs_rows;                  // rows of the shared-memory vector (own + ghosts + zero row + dummy row)
+  int max_steps;                // longest strip, in micro-steps
   long long nval;
   const int *strip_ms, *strip_gh, *ms_rows, *gh_row, *gh_src, *gh_need;
   const int* meta;
@@ -500,6 +506,8 @@ __global__ void __launch_bounds__(128, 1) k_trisolve(const TriArgs A) {
   const int meta_bytes = A.meta_stride * 4, val_bytes = A.val_stride * 8;
   const int stage_bytes = TS_K * (meta_bytes + val_bytes);
   unsigned char* stages = xsc + (size_t)A.xs_rows * 32;
+  int* s_rows = reinterpret_cast<int*>(stages + (size_t)TS_NST * stage_bytes);  // row ids of the strip's micro-steps
+  int* s_gh = s_rows + A.max_steps * TS_ROWS;                                    // ghost descriptors {row, src, need}
   constexpr int LAY0 = FWD ? 1 : 0;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -524,6 +532,16 @@ __global__ void __launch_bounds__(128, 1) k_trisolve(const TriArgs A) {
     xs[(idx / 3) * 4 + comp] = in[(size_t)row * 3 + comp];
   }
   if (tid < 8) xs[(A.xs_rows - 2) * 4 + tid] = 0.0;  // zero row (padding operands) and dummy row (idle lanes)
+  // topology-only lists of this strip, staged once so that the publisher / import loops never wait on global memory
+  {
+    const int g0 = A.strip_gh[strip], ngh = A.strip_gh[strip + 1] - g0;
+    for (int i = tid; i < nsteps * TS_ROWS; i += blockDim.x) s_rows[i] = A.ms_rows[(size_t)ms0 * TS_ROWS + i];
+    for (int i = tid; i < ngh; i += blockDim.x) {
+      s_gh[i * 3 + 0] = A.gh_row[g0 + i];
+      s_gh[i * 3 + 1] = A.gh_src[g0 + i];
+      s_gh[i * 3 + 2] = A.gh_need[g0 + i];
+    }
+  }
   if (tid == 0) {
     for (int i = 0; i < TS_NST; i++) {
       mbar_init(&full[i], 1);
@@ -676,7 +694,7 @@ __global__ void __launch_bounds__(128, 1) k_trisolve(const TriArgs A) {
       int rows[4];
 #pragma unroll
       for (int j = 0; j < 4; j++)
-        rows[j] = (on && pub + j < (uint32_t)nsteps) ? A.ms_rows[(size_t)(ms0 + pub + j) * TS_ROWS + q3] : -1;
+        rows[j] = (on && pub + j < (uint32_t)nsteps) ? s_rows[(pub + j) * TS_ROWS + q3] : -1;
       uint32_t d;
       while ((d = ld_acquire_cta(&flags[0])) <= pub) __nanosleep(20);
       d = min(d, pub + 4u);
@@ -702,7 +720,7 @@ __global__ void __launch_bounds__(128, 1) k_trisolve(const TriArgs A) {
     while (w0 < ngh) {
       const int gi = w0 + lane;
       const bool in = gi < ngh;
-      const int row = in ? A.gh_row[g0 + gi] : 0, srcs = in ? A.gh_src[g0 + gi] : 0, need = in ? A.gh_need[g0 + gi] : 0;
+      const int row = in ? s_gh[gi * 3] : 0, srcs = in ? s_gh[gi * 3 + 1] : 0, need = in ? s_gh[gi * 3 + 2] : 0;
       const int src0 = __shfl_sync(0xffffffffu, srcs, 0);
       int nlead = 0;
       do {
@@ -746,6 +764,7 @@ static int launch_tri(Ctx* c, TriPlan& P, double* vec, const double* src, bool s
   TriArgs A;
   A.np = c->np; A.ns = P.ns; A.R = P.R; A.B = c->B;
   A.meta_stride = P.meta_stride; A.val_stride = P.val_stride; A.xs_rows = P.R + P.max_ghost + 2;
+  A.max_steps = P.max_steps;
   A.nval = P.nval;
   A.strip_ms = P.strip_ms; A.strip_gh = P.strip_gh; A.ms_rows = P.ms_rows;
   A.gh_row = P.gh_row; A.gh_src = P.gh_src; A.gh_need = P.gh_need; A.meta = P.meta; A.packed = P.packed;
