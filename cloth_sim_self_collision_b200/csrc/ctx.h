@@ -50,7 +50,8 @@ struct TriPlanHost {
   std::vector<int> strip_ms, strip_gh, ms_rows, pk_src, gh_row, gh_src, gh_need, meta;
 };
 // strip-pipelined factorisation (ilufactor.cu): follows the forward sweep's strips and micro-steps
-enum { FC_H = 8, FC_NST = 3, FC_NIB = 3, FC_META_HDR = 48, FC_SMEM_HDR = 256, FC_BUNDLE = 3 };
+enum { FC_H = 8, FC_NST = 3, FC_NIB = 3, FC_META_HDR = 48, FC_SMEM_HDR = 256, FC_BUNDLE = 6,
+       FC_CWARPS = 4, FC_THREADS = (4 + 3) * 32 };
 struct FacPlanHost {
   int ns = 0, R = 0, nms = 0, H = 0, gmaxB = 0, gmaxU = 0, gmaxOps = 0, max_imp = 0, meta_stride = 0, row_stride = 0;
   int max_steps = 0, gmaxLo = 0, gT = 0, kg_stride = 0;

@@ -41,7 +41,7 @@ int build_facplan_host(int np, const int* rowptr, const int* colidx, const int* 
   }
   F.gmaxB = gB;
   F.gmaxU = std::max(gU, 1);
-  const int blk = 768;                 // bytes of one block of the scratch: [3 columns][32 lanes] doubles
+  const int blk = 768;                 // bytes of one block of the scratch: [96 lane slots] doubles
   const int urow = round_up(F.gmaxU * 72, 16);  // bytes of one exported upper part (dense 3x3 blocks, TMA granule)
   // update lists in the reference's order (DoILUDecomp, ilu_sparse.cpp:507-540)
   std::vector<int> op_ptr(np + 1, 0);
@@ -94,7 +94,7 @@ int build_facplan_host(int np, const int* rowptr, const int* colidx, const int* 
       const int row = F.ms_rows[(size_t)m * TS_ROWS + q];
       if (row >= 0) { ms_of_row[row] = m; q_of_row[row] = q; }
     }
-  // ring of finished upper parts: [step mod FC_H][upper block][9 entries][16 row slots] doubles, then a zero slot
+  // ring of finished upper parts: [step mod FC_H][upper block][16 row slots][9 entries] doubles, then a zero block
   const int ring_bytes = FC_H * F.gmaxU * 9 * 128;
   std::vector<int> imp_slot(np, -1), imp_stamp(np, -1);
   for (int k = 0; k < F.ns; k++) {
@@ -113,13 +113,13 @@ int build_facplan_host(int np, const int* rowptr, const int* colidx, const int* 
         nupmax = std::max(nupmax, M[34 + q]);
         lomax = std::max(lomax, M[24 + q]);
         // packed row data: blocks in crs order, the diagonal at block index gB-1; entry (r, c) of block b of row
-        // group q sits at [(b*3 + c)*32 + q*3 + r]
+        // group q sits at [b*96 + q*9 + r*3 + c] (one lane per entry, 9 lanes per row)
         const int nb = rowptr[row + 1] - rowptr[row];
         for (int b = 0; b < nb; b++)
           for (int r = 0; r < 3; r++)
-            for (int c = 0; c < 3; c++) V[(b * 3 + c) * 32 + q * 3 + r] = (rowptr[row] + b) * 9 + r * 3 + c;
+            for (int c = 0; c < 3; c++) V[b * 96 + q * 9 + r * 3 + c] = (rowptr[row] + b) * 9 + r * 3 + c;
         for (int r = 0; r < 3; r++)
-          for (int c = 0; c < 3; c++) V[((gB - 1) * 3 + c) * 32 + q * 3 + r] = ncrs * 9 + row * 9 + r * 3 + c;
+          for (int c = 0; c < 3; c++) V[(gB - 1) * 96 + q * 9 + r * 3 + c] = ncrs * 9 + row * 9 + r * 3 + c;
       }
       for (int kg = 0; kg < gLo; kg++) {
         int* K = &M[FC_META_HDR + kg * F.kg_stride];
@@ -141,7 +141,7 @@ int build_facplan_host(int np, const int* rowptr, const int* colidx, const int* 
             const int mk = ms_of_row[kr];
             const bool same = kr / T.R == k;  // the factorisation follows the forward sweep: position == row index
             if (same && mk < m && m - mk <= FC_H - 1) {
-              E[0] = ((((mk - F.strip_ms[k]) % FC_H) * F.gmaxU + u) * 9 * 16 + q_of_row[kr]) * 8;
+              E[0] = (((((mk - F.strip_ms[k]) % FC_H) * F.gmaxU + u) * 16 + q_of_row[kr]) * 9) * 8;
             } else {
               if (imp_stamp[kr] != m) {
                 imp_stamp[kr] = m;
@@ -211,11 +211,11 @@ int verify_facplan_host(int np, const int* rowptr, const int* colidx, const int*
         for (int b = 0; b < rowptr[row + 1] - rowptr[row]; b++)
           for (int r = 0; r < 3; r++)
             for (int c = 0; c < 3; c++)
-              if (V[(b * 3 + c) * 32 + q * 3 + r] != (rowptr[row] + b) * 9 + r * 3 + c) PLAN_FAIL("packed block");
+              if (V[b * 96 + q * 9 + r * 3 + c] != (rowptr[row] + b) * 9 + r * 3 + c) PLAN_FAIL("packed block");
         for (int r = 0; r < 3; r++)
           for (int c = 0; c < 3; c++) {
-            if (V[((gB - 1) * 3 + c) * 32 + q * 3 + r] != ncrs * 9 + row * 9 + r * 3 + c) PLAN_FAIL("packed diagonal");
-            if (V[(gB * 3 + c) * 32 + q * 3 + r] != -1) PLAN_FAIL("dummy block must be empty");
+            if (V[(gB - 1) * 96 + q * 9 + r * 3 + c] != ncrs * 9 + row * 9 + r * 3 + c) PLAN_FAIL("packed diagonal");
+            if (V[gB * 96 + q * 9 + r * 3 + c] != -1) PLAN_FAIL("dummy block must be empty");
           }
         // replay the reference's update order: k ascending, within k the upper blocks of row k ascending
         for (int j = rowptr[row]; j < rowptr[row + 1]; j++) slot[colidx[j]] = j;
@@ -237,7 +237,7 @@ int verify_facplan_host(int np, const int* rowptr, const int* colidx, const int*
             const int u = kj - dia[kr], mk = ms_of_row[kr];
             if (E[0] >= 0) {
               if (kr / T.R != k || mk >= m || m - mk > FC_H - 1) PLAN_FAIL("ring operand out of reach");
-              if (E[0] != ((((mk - F.strip_ms[k]) % FC_H) * F.gmaxU + u) * 9 * 16 + q_of_row[kr]) * 8) PLAN_FAIL("ring operand offset");
+              if (E[0] != (((((mk - F.strip_ms[k]) % FC_H) * F.gmaxU + u) * 16 + q_of_row[kr]) * 9) * 8) PLAN_FAIL("ring operand offset");
             } else {
               const int off = -1 - E[0], e = off / urow;
               if (e >= nimp || F.imp_row[i0 + e] != kr || off % urow != u * 72) PLAN_FAIL("import operand");
@@ -285,7 +285,7 @@ int upload_facplan(Ctx* c, const FacPlanHost& H, FacPlan& D) {
   CG_CUDA(cudaMalloc((void**)&D.ticket, sizeof(unsigned long long)));
   CG_CUDA(cudaMemset(D.ticket, 0, sizeof(unsigned long long)));
   const int urow = round_up(D.gmaxU * 72, 16);
-  D.smem_bytes = FC_SMEM_HDR + FC_H * D.gmaxU * 9 * 128 + 9 * 128 + FC_NIB * round_up(std::max(D.max_imp, 1) * urow, 128) +
+  D.smem_bytes = FC_SMEM_HDR + FC_H * D.gmaxU * 9 * 128 + 128 + FC_NIB * round_up(std::max(D.max_imp, 1) * urow, 128) +
                  FC_NST * (D.meta_stride * 4 + D.row_stride * 8);
   if (D.smem_bytes > 227 * 1024) { set_error("factor plan does not fit shared memory"); return CLOTHGPU_ERR_CAPACITY; }
   return CLOTHGPU_OK;
@@ -359,17 +359,18 @@ struct FacArgs {
   unsigned long long* dbg;  // optional: 8 counters per CTA (clothgpu_debug_trisolve, slot of the forward sweep)
 };
 
-// one CTA per (strip, scene): warp 0 computes, warp 1 lane 0 streams row data, warp 2 publishes, warp 3 lane 0 imports
-__global__ void __launch_bounds__(128, 1) k_ilu_factor_strips(const FacArgs A) {
+// one CTA per (strip, scene): warps 0-3 compute (three rows each, nine lanes per row = one lane per block entry),
+// warp 4 lane 0 streams row data, warp 5 lane 0 publishes, warp 6 lane 0 imports
+__global__ void __launch_bounds__(FC_THREADS, 1) k_ilu_factor_strips(const FacArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);        // FC_NST
   uint64_t* empty = full + FC_NST;                            // FC_NST
   uint64_t* ifull = empty + FC_NST;                           // FC_NIB
   uint32_t* flags = reinterpret_cast<uint32_t*>(smem + 128);  // [0] micro-steps done, [2] ticket
   const int urow = (A.gmaxU * 72 + 15) / 16 * 16;     // bytes of one exported upper part (dense 3x3 blocks)
-  const int ring_bytes = FC_H * A.gmaxU * 9 * 128;    // [step mod FC_H][upper block][entry][16 row slots] doubles
-  unsigned char* ring = smem + FC_SMEM_HDR;          // + a zero slot (9 entries, 128-byte stride) right behind it
-  unsigned char* imp = ring + ring_bytes + 9 * 128;
+  const int ring_bytes = FC_H * A.gmaxU * 9 * 128;    // [step mod FC_H][upper block][16 row slots][9 entries] doubles
+  unsigned char* ring = smem + FC_SMEM_HDR;          // + a zero block right behind it
+  unsigned char* imp = ring + ring_bytes + 128;
   const int imp_bytes = (max(A.max_imp, 1) * urow + 127) / 128 * 128;
   unsigned char* stages = imp + (size_t)FC_NIB * imp_bytes;
   const int meta_bytes = A.meta_stride * 4, row_bytes = A.row_stride * 8, stage_bytes = meta_bytes + row_bytes;
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(128, 1) k_ilu_factor_strips(const FacArgs A) {
   double* dia = A.iluDia + (size_t)scene * A.np * 9;
   double* crs = A.iluCrs + (size_t)scene * A.ncrs * 9;
   double* uexp = A.uexp + (size_t)scene * A.np * (urow / 8);
-  for (int i = tid; i < 9 * 16; i += blockDim.x) reinterpret_cast<double*>(ring + ring_bytes)[i] = 0.0;  // zero operand of the padding updates
+  if (tid < 16) reinterpret_cast<double*>(ring + ring_bytes)[tid] = 0.0;  // zero operand of the padding updates
   if (tid == 0) {
     for (int i = 0; i < FC_NST; i++) { f_mbar_init(&full[i], 1); f_mbar_init(&empty[i], 1); }
     for (int i = 0; i < FC_NIB; i++) f_mbar_init(&ifull[i], 1);
@@ -396,14 +397,18 @@ __global__ void __launch_bounds__(128, 1) k_ilu_factor_strips(const FacArgs A) {
   }
   __syncthreads();
 
-  if (warp == 0) {
-    // ---------------------------------------------------------------- compute warp
-    const int g = lane / 3, r = lane - g * 3;
-    const bool act = g < TS_ROWS;
-    const int gq = act ? g : TS_ROWS - 1;
-    const bool dbg = A.dbg != nullptr;
-    unsigned long long t_begin = 0, w_full = 0, w_imp = 0, w_ops = 0, w_tail = 0;
-    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  if (warp < FC_CWARPS) {
+    // ---------------------------------------------------------------- compute warps
+    // lane -> (row group q, block entry e = r*3 + c); lanes 27..31 idle on the slots of a spare group
+    const int gl = lane / 9, e9 = lane - gl * 9, r = e9 / 3, cc = e9 - r * 3;
+    const bool act = gl < 3 && warp * 3 + gl < TS_ROWS;
+    const int gq = act ? warp * 3 + gl : TS_ROWS;        // group TS_ROWS (slots 90..95 of every block) is scratch for idle lanes
+    const int gm = act ? gq : TS_ROWS - 1;               // metadata column the lane reads
+    const int slot8 = act ? (gq * 9 + e9) * 8 : (90 + (lane % 6)) * 8;  // byte offset of the lane's entry inside a block
+    const int rowbase8 = gq * 72;                         // byte offset of the group's entries inside a block
+    const bool dbg = A.dbg != nullptr && warp == 0;
+    unsigned long long t_begin = 0, w_full = 0, w_imp = 0, w_ops = 0, w_tail = 0, w_inv = 0, w_bar = 0;
+    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
     if (dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); t_begin = t; }
     for (int m = 0; m < nsteps; m++) {
       const int st = m % FC_NST;
@@ -416,54 +421,45 @@ __global__ void __launch_bounds__(128, 1) k_ilu_factor_strips(const FacArgs A) {
       unsigned char* sc = stages + (size_t)st * stage_bytes + meta_bytes;  // this step's row blocks
       const unsigned char* ib = imp + (size_t)(m % FC_NIB) * imp_bytes;
       const int nops = M[0], nupmax = M[2], lomax = M[3];
-      const int row = act ? M[4 + gq] : -1;
-      // ---- updates A_ij -= A_ik U'_kj in the reference's order; lane r owns block-row r.  The updates of one lower
-      // block k hit distinct targets: they are issued FC_BUNDLE at a time (loads, then math, then stores) so that
-      // their latencies overlap; consecutive k-groups are ordered by program order (a later A_ik may be a target)
+      const int row = act ? M[4 + gm] : -1;
+      // ---- updates A_ij -= A_ik U'_kj in the reference's order.  Lane (r, c) owns entry (r, c) of every block of
+      // its row.  The updates of one lower block k hit distinct targets: they are issued FC_BUNDLE at a time (loads,
+      // math, stores); consecutive k-groups are separated by __syncwarp (a later A_ik may be an earlier target,
+      // written by the other lanes of the row)
       for (int kg = 0; kg < nops; kg++) {
         const int* K = M + FC_META_HDR + kg * A.kg_stride;
-        const unsigned char* pk = sc + K[gq] + lane * 8;  // entry (r, c) of a block: [(c*32 + lane)*8]
+        const unsigned char* pk = sc + K[gm] + (act ? rowbase8 : 720) + r * 24;  // A_ik[r][0..2]
         const int ntk = K[10];
-        const double a0 = *reinterpret_cast<const double*>(pk), a1 = *reinterpret_cast<const double*>(pk + 256),
-                     a2 = *reinterpret_cast<const double*>(pk + 512);
+        // idle lanes run the same code on scratch slots with zero coefficients
+        const double a0 = act ? *reinterpret_cast<const double*>(pk) : 0.0, a1 = act ? *reinterpret_cast<const double*>(pk + 8) : 0.0,
+                     a2 = act ? *reinterpret_cast<const double*>(pk + 16) : 0.0;
         for (int t0 = 0; t0 < ntk; t0 += FC_BUNDLE) {
           unsigned char* pt[FC_BUNDLE];
-          double b[FC_BUNDLE][9], t[FC_BUNDLE][3];
+          double b0[FC_BUNDLE], b1[FC_BUNDLE], b2[FC_BUNDLE], t[FC_BUNDLE];
 #pragma unroll
           for (int j = 0; j < FC_BUNDLE; j++) {
-            const int2 e = *reinterpret_cast<const int2*>(K + 12 + ((t0 + j) * TS_ROWS + gq) * 2);
-            // operand U'_kj: ring entries are 128 bytes apart (one slot per producer row), imported ones are dense
-            const unsigned char* pb = e.x >= 0 ? ring + e.x : ib + (-1 - e.x);
-            const int es = e.x >= 0 ? 128 : 8;
-            pt[j] = sc + e.y + lane * 8;
-#pragma unroll
-            for (int k = 0; k < 9; k++) b[j][k] = *reinterpret_cast<const double*>(pb + k * es);
-#pragma unroll
-            for (int k = 0; k < 3; k++) t[j][k] = *reinterpret_cast<const double*>(pt[j] + k * 256);
+            const int2 e = *reinterpret_cast<const int2*>(K + 12 + ((t0 + j) * TS_ROWS + gm) * 2);
+            const unsigned char* pb = (e.x >= 0 ? ring + e.x : ib + (-1 - e.x)) + cc * 8;  // U'_kj[0..2][c]
+            pt[j] = sc + e.y + slot8;
+            b0[j] = *reinterpret_cast<const double*>(pb);
+            b1[j] = *reinterpret_cast<const double*>(pb + 24);
+            b2[j] = *reinterpret_cast<const double*>(pb + 48);
+            t[j] = *reinterpret_cast<const double*>(pt[j]);
           }
 #pragma unroll
-          for (int j = 0; j < FC_BUNDLE; j++) {
-            t[j][0] = t[j][0] - (a0 * b[j][0] + a1 * b[j][3] + a2 * b[j][6]);
-            t[j][1] = t[j][1] - (a0 * b[j][1] + a1 * b[j][4] + a2 * b[j][7]);
-            t[j][2] = t[j][2] - (a0 * b[j][2] + a1 * b[j][5] + a2 * b[j][8]);
-          }
+          for (int j = 0; j < FC_BUNDLE; j++) t[j] = t[j] - (a0 * b0[j] + a1 * b1[j] + a2 * b2[j]);
 #pragma unroll
-          for (int j = 0; j < FC_BUNDLE; j++) {
-#pragma unroll
-            for (int k = 0; k < 3; k++) *reinterpret_cast<double*>(pt[j] + k * 256) = t[j][k];
-          }
+          for (int j = 0; j < FC_BUNDLE; j++) *reinterpret_cast<double*>(pt[j]) = t[j];
         }
+        __syncwarp();
       }
-      __syncwarp();
       if (dbg) c3 = clock64();
       // ---- D_i <- D_i^-1 by cofactors (CalcInvMat3, ilu_sparse.cpp:77-97); a singular pivot is left as is (:541-551)
       double a[9];
       {
-        const unsigned char* pd = sc + (A.gmaxB - 1) * 768 + gq * 24;
+        const unsigned char* pd = sc + (A.gmaxB - 1) * 768 + (act ? rowbase8 : 720);
 #pragma unroll
-        for (int rr = 0; rr < 3; rr++)
-#pragma unroll
-          for (int cc = 0; cc < 3; cc++) a[rr * 3 + cc] = *reinterpret_cast<const double*>(pd + cc * 256 + rr * 8);
+        for (int k = 0; k < 9; k++) a[k] = *reinterpret_cast<const double*>(pd + k * 8);
         const double det = +a[0] * a[4] * a[8] + a[3] * a[7] * a[2] + a[6] * a[1] * a[5] - a[0] * a[7] * a[5] -
                            a[6] * a[4] * a[2] - a[3] * a[1] * a[8];
         if (fabs(det) > 1.0e-30) {
@@ -480,74 +476,61 @@ __global__ void __launch_bounds__(128, 1) k_ilu_factor_strips(const FacArgs A) {
           a[6] = inv_det * (t[3] * t[7] - t[4] * t[6]);
           a[7] = inv_det * (t[1] * t[6] - t[0] * t[7]);
           a[8] = inv_det * (t[0] * t[4] - t[1] * t[3]);
-        } else if (row >= 0 && r == 0) {
+        } else if (row >= 0 && e9 == 0) {
           atomicAdd(&A.cnt[scene * NCNT + CNT_NSING], 1);
         }
       }
       const double ar0 = r == 0 ? a[0] : (r == 1 ? a[3] : a[6]);
       const double ar1 = r == 0 ? a[1] : (r == 1 ? a[4] : a[7]);
       const double ar2 = r == 0 ? a[2] : (r == 1 ? a[5] : a[8]);
-      const int crs0 = act ? M[14 + gq] : 0, nlo = act ? M[24 + gq] : 0, nup = act ? M[34 + gq] : 0;
-      if (row >= 0) {
-        double* o = dia + (size_t)row * 9 + r * 3;
-        o[0] = ar0; o[1] = ar1; o[2] = ar2;
-      }
+      const int crs0 = act ? M[14 + gm] : 0, nlo = act ? M[24 + gm] : 0, nup = act ? M[34 + gm] : 0;
+      if (row >= 0) dia[(size_t)row * 9 + e9] = cc == 0 ? ar0 : (cc == 1 ? ar1 : ar2);
+      if (dbg) c4 = clock64();
       // ---- U'_ij = D_i^-1 U_ij (:556-567): to the ring (next steps of this strip), the ILU array and the export copy
-      unsigned char* myring = ring + (size_t)((m % FC_H) * A.gmaxU * 9 * 16 + gq) * 8 + r * 3 * 128;
+      unsigned char* myring = ring + (size_t)(((m % FC_H) * A.gmaxU * 16 + (act ? gq : 15)) * 9 + e9) * 8;
       for (int u0 = 0; u0 < nupmax; u0 += FC_BUNDLE) {
-        double v[FC_BUNDLE][3];
+        double v[FC_BUNDLE];
 #pragma unroll
         for (int j = 0; j < FC_BUNDLE; j++) {
           const int u = u0 + j;
-          const unsigned char* pu = sc + (nlo + (u < nup ? u : 0)) * 768 + gq * 24;  // entry (r', c): + c*256 + r'*8
-          double cb[9];
-#pragma unroll
-          for (int rr = 0; rr < 3; rr++)
-#pragma unroll
-            for (int cc = 0; cc < 3; cc++) cb[rr * 3 + cc] = *reinterpret_cast<const double*>(pu + cc * 256 + rr * 8);
-          v[j][0] = ar0 * cb[0] + ar1 * cb[3] + ar2 * cb[6];
-          v[j][1] = ar0 * cb[1] + ar1 * cb[4] + ar2 * cb[7];
-          v[j][2] = ar0 * cb[2] + ar1 * cb[5] + ar2 * cb[8];
+          const unsigned char* pu = sc + (nlo + (u < nup ? u : 0)) * 768 + (act ? rowbase8 : 720) + cc * 8;  // U_ij[0..2][c]
+          v[j] = ar0 * *reinterpret_cast<const double*>(pu) + ar1 * *reinterpret_cast<const double*>(pu + 24) +
+                 ar2 * *reinterpret_cast<const double*>(pu + 48);
         }
 #pragma unroll
         for (int j = 0; j < FC_BUNDLE; j++) {
           const int u = u0 + j;
           if (row >= 0 && u < nup) {
-#pragma unroll
-            for (int cc = 0; cc < 3; cc++) *reinterpret_cast<double*>(myring + (size_t)(u * 9 + cc) * 128) = v[j][cc];
-            double* oc = crs + (size_t)(crs0 + nlo + u) * 9 + r * 3;
-            oc[0] = v[j][0]; oc[1] = v[j][1]; oc[2] = v[j][2];
-            double* ou = uexp + (size_t)row * (urow / 8) + u * 9 + r * 3;
-            ou[0] = v[j][0]; ou[1] = v[j][1]; ou[2] = v[j][2];
+            *reinterpret_cast<double*>(myring + (size_t)u * 16 * 72) = v[j];
+            crs[(size_t)(crs0 + nlo + u) * 9 + e9] = v[j];
+            uexp[(size_t)row * (urow / 8) + u * 9 + e9] = v[j];
           }
         }
       }
       // ---- the finished lower part L_ik
       for (int b = 0; b < lomax; b++) {
-        if (row >= 0 && b < nlo) {
-          const unsigned char* pl = sc + b * 768 + lane * 8;
-          double* oc = crs + (size_t)(crs0 + b) * 9 + r * 3;
-          oc[0] = *reinterpret_cast<const double*>(pl); oc[1] = *reinterpret_cast<const double*>(pl + 256);
-          oc[2] = *reinterpret_cast<const double*>(pl + 512);
-        }
+        if (row >= 0 && b < nlo) crs[(size_t)(crs0 + b) * 9 + e9] = *reinterpret_cast<const double*>(sc + b * 768 + slot8);
       }
-      __syncwarp();
-      if (lane == 0) {
+      // ---- all compute warps have finished the step: ring visible, stage reusable, progress published
+      if (dbg) c5 = clock64();
+      asm volatile("bar.sync 1, %0;" ::"n"(FC_CWARPS * 32) : "memory");
+      if (warp == 0 && lane == 0) {
         f_st_release_cta(&flags[0], (uint32_t)(m + 1));
         f_mbar_arrive(&empty[st]);
       }
       if (dbg) {
         w_full += (unsigned long long)(c1 - c0); w_imp += (unsigned long long)(c2 - c1);
-        w_ops += (unsigned long long)(c3 - c2); w_tail += (unsigned long long)(clock64() - c3);
+        w_ops += (unsigned long long)(c3 - c2); w_inv += (unsigned long long)(c4 - c3); w_tail += (unsigned long long)(c5 - c4);
+        w_bar += (unsigned long long)(clock64() - c5);
       }
     }
     if (dbg && lane == 0) {
       unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       unsigned long long* o = A.dbg + (size_t)blockIdx.x * 8;
-      o[0] = t_begin; o[1] = t; o[2] = w_full; o[3] = w_imp; o[4] = w_ops; o[5] = w_tail;
+      o[0] = t_begin; o[1] = t; o[2] = w_inv; o[3] = w_full + w_imp; o[4] = w_ops; o[5] = w_tail + (w_bar << 32);
       o[6] = (unsigned long long)nsteps; o[7] = (unsigned long long)strip;
     }
-  } else if (warp == 1) {
+  } else if (warp == FC_CWARPS) {
     // ---------------------------------------------------------------- row-data loader: one TMA pair per micro-step
     if (lane == 0) {
       const unsigned char* meta = reinterpret_cast<const unsigned char*>(A.meta) + (size_t)ms0 * meta_bytes;
@@ -561,8 +544,8 @@ __global__ void __launch_bounds__(128, 1) k_ilu_factor_strips(const FacArgs A) {
         f_bulk_g2s(dst + meta_bytes, packed + (size_t)m * row_bytes, (uint32_t)row_bytes, &full[st]);
       }
     }
-  } else if (warp == 2) {
-    // ---------------------------------------------------------------- publisher: the compute warp stores its results itself
+  } else if (warp == FC_CWARPS + 1) {
+    // ---------------------------------------------------------------- publisher: the compute warps store its results itself
     // (fire and forget); this warp turns "step done" into a device-wide release of the strip's progress counter
     if (lane == 0) {
       unsigned long long* prog = A.progress + (size_t)scene * A.ns + strip;
@@ -643,7 +626,7 @@ int launch_ilu_factor_strips(Ctx* c) {
     c->tri_dbg_grid[0] = grid;
   }
   CG_CUDA(cudaFuncSetAttribute(k_ilu_factor_strips, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
-  k_ilu_factor_strips<<<grid, 128, P.smem_bytes, KS(c, "k_ilu_factor_strips")>>>(A);
+  k_ilu_factor_strips<<<grid, FC_THREADS, P.smem_bytes, KS(c, "k_ilu_factor_strips")>>>(A);
   CG_LAUNCH_CHECK(c);
   P.pbase += (unsigned long long)P.max_steps + 2;
   P.tbase += (unsigned long long)grid;

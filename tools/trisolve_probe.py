@@ -72,11 +72,12 @@ def main():
             rows = out.reshape(2, cap, 8)[0, :nct[0]]
             rows = rows[np.argsort(rows[:, 7])]
             t0 = rows[:, 0].min()
-            print("  factor: strip start_us end_us | per-step cycles: wait rows, wait imports, updates, tail | steps")
+            print("  factor: strip start_us end_us | per-step cycles: waits, updates, inverse, U'+L stores, barrier | steps")
             for r in rows[:: max(1, len(rows) // 8)]:
                 n_ = max(int(r[6]), 1)
-                print("   %3d %8.1f %8.1f | %6.0f %6.0f %6.0f %6.0f | %d" %
-                      (r[7], (r[0] - t0) / 1e3, (r[1] - t0) / 1e3, r[2] / n_, r[3] / n_, r[4] / n_, r[5] / n_, n_))
+                tail, bar = int(r[5]) & 0xffffffff, int(r[5]) >> 32
+                print("   %3d %8.1f %8.1f | %6.0f %6.0f %6.0f %6.0f %6.0f | %d" %
+                      (r[7], (r[0] - t0) / 1e3, (r[1] - t0) / 1e3, r[3] / n_, r[4] / n_, r[2] / n_, tail / n_, bar / n_, n_))
         if os.environ.get("PROBE_DEBUG"):
             cap = 256
             out = np.zeros(2 * cap * 8, dtype=np.uint64)
