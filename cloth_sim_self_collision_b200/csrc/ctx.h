@@ -131,6 +131,7 @@ struct Ctx {
   // strip-pipelined triangular solves
   TriPlan plan_f, plan_b;
   FacPlan plan_fac;
+  unsigned long long* tri_xch = nullptr;  // exchange vector of the triangular sweeps (trisolve.cu)
   bool ilu_packed_valid = false;  // plan_*.packed mirrors iluDia / iluCrs
   bool tri_debug = false;         // clothgpu_debug_trisolve: per-CTA wait / compute cycle counters
   unsigned long long* tri_dbg_buf = nullptr;
