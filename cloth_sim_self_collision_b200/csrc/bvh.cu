@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) k_refit(int nnode, int np, const int* __r
 __global__ void k_trav_reset(int* cnt) {
   int* c = cnt + blockIdx.x * NCNT;
   for (int k = threadIdx.x; k < NCNT - CNT_FRONT; k += blockDim.x) c[CNT_FRONT + k] = 0;
-  if (threadIdx.x == 0) { c[CNT_LEAF] = 0; c[CNT_RAW] = 0; c[CNT_ELEM] = 0; c[CNT_OVERFLOW] = 0; }
+  if (threadIdx.x == 0) { c[CNT_LEAF] = 0; c[CNT_RAW] = 0; c[CNT_ELEM] = 0; c[CNT_OVERFLOW] = 0; c[CNT_CAND] = 0; }
 }
 
 // the self() calls: every internal node starts one pair recursion on its two children
@@ -230,13 +230,48 @@ __device__ __forceinline__ void emit(const PairEnt& e, int slot, const int* key,
   raw[k] = r;
 }
 
-// the 6 face-vertex + 9 edge-edge tests of every leaf pair (bvh_aabb.cpp:476-535 proximity, 834-900 CCD)
-__global__ void __launch_bounds__(128) k_narrow(int ccd, int nnode, int np, const int* __restrict__ nodes,
-                                                 const int* __restrict__ tri, const double* __restrict__ boxes,
-                                                 const double* __restrict__ xyz, const double* __restrict__ uvw,
-                                                 double dt, double delta, const PairEnt* __restrict__ leaf,
-                                                 long long cap_leaf, RawElem* __restrict__ raw, long long cap_raw,
-                                                 int* cnt) {
+// The 6 face-vertex + 9 edge-edge tests of every leaf pair (bvh_aabb.cpp:476-535 proximity, 834-900 CCD), in two
+// passes.  k_cull: one thread per (leaf pair, test slot) runs the cheap prefix of the predicate (shared vertex, box /
+// slab / sign culls) and pushes the survivors into a candidate queue (warp-aggregated atomics).  k_narrow: one thread
+// per candidate runs the full predicate -- the cubic coplanarity solve of the CCD tests, which the reference pays
+// for every vertex-disjoint edge pair, is then executed by converged warps on a ~50x shorter list.
+struct SlotData {
+  int n[4];     // FV: face i0,i1,i2 + vertex i3 ; EE: edge i0,i1 + edge j0,j1
+  V3 p[4];      // positions at the start of the step
+  V3 q[4];      // positions at the end of the step (CCD only)
+  Box bb;       // box the FV tests cull against
+};
+
+__device__ __forceinline__ void load_slot(int ccd, int slot, const PairEnt& e, const int* __restrict__ nodes,
+                                          const int* __restrict__ tri, const double* __restrict__ bx,
+                                          const double* __restrict__ x, const double* __restrict__ v, double dt, SlotData& S) {
+  const int it = nodes[e.i0 * 3 + 1], jt = nodes[e.i1 * 3 + 1];
+  if (slot < 6) {
+    const bool first = slot < 3;
+    const int ft = first ? it : jt, vt = first ? jt : it, a = first ? slot : slot - 3;
+    S.n[0] = tri[ft * 3]; S.n[1] = tri[ft * 3 + 1]; S.n[2] = tri[ft * 3 + 2]; S.n[3] = tri[vt * 3 + a];
+    // reference quirk (bvh_aabb.cpp:490-505): the proximity FV test culls against the box of BVH node number
+    // <triangle index>, not against the box of the face's own leaf; the CCD test uses the leaf (:855)
+    S.bb = ld_box(bx, ccd ? (first ? e.i0 : e.i1) : ft);
+  } else {
+    const int k = slot - 6, a0 = k / 3, a1 = (a0 + 1) % 3, b0 = k - a0 * 3, b1 = (b0 + 1) % 3;
+    S.n[0] = tri[it * 3 + a0]; S.n[1] = tri[it * 3 + a1]; S.n[2] = tri[jt * 3 + b0]; S.n[3] = tri[jt * 3 + b1];
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int i = S.n[k];
+    S.p[k] = ld3(x, i);
+    if (ccd) S.q[k] = v3(x[i * 3] + dt * v[i * 3], x[i * 3 + 1] + dt * v[i * 3 + 1], x[i * 3 + 2] + dt * v[i * 3 + 2]);
+  }
+}
+
+// one thread per leaf pair: the six vertices are loaded once, the 15 cheap culls run on registers, the survivors'
+// slot mask is compacted with one atomic per warp
+__global__ void __launch_bounds__(256) k_cull(int ccd, int nnode, int np, const int* __restrict__ nodes,
+                                               const int* __restrict__ tri, const double* __restrict__ boxes,
+                                               const double* __restrict__ xyz, const double* __restrict__ uvw,
+                                               double dt, double delta, const PairEnt* __restrict__ leaf,
+                                               long long cap_leaf, int2* __restrict__ cand, long long cap_cand, int* cnt) {
   const int s = blockIdx.y;
   int* c = cnt + s * NCNT;
   if (!c[CNT_ACTIVE]) return;
@@ -245,70 +280,113 @@ __global__ void __launch_bounds__(128) k_narrow(int ccd, int nnode, int np, cons
   const double* x = xyz + (size_t)s * np * 3;
   const double* v = ccd ? uvw + (size_t)s * np * 3 : nullptr;
   const PairEnt* lf = leaf + (size_t)s * cap_leaf;
-  RawElem* rw = raw + (size_t)s * cap_raw;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nleaf; idx += gridDim.x * blockDim.x) {
-    const PairEnt e = lf[idx];
-    const int it = nodes[e.i0 * 3 + 1], jt = nodes[e.i1 * 3 + 1];
-    int in[3], jn[3];
-    V3 p[3], q[3], pe[3], qe[3];
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      in[a] = tri[it * 3 + a]; jn[a] = tri[jt * 3 + a];
-      p[a] = ld3(x, in[a]); q[a] = ld3(x, jn[a]);
-    }
-    int key[4];
-    if (ccd) {
+  int2* cd = cand + (size_t)s * cap_cand;
+  const int lane = threadIdx.x & 31;
+  for (int i0 = blockIdx.x * blockDim.x; i0 < nleaf; i0 += gridDim.x * blockDim.x) {
+    const int idx = i0 + threadIdx.x;
+    unsigned mask = 0;
+    if (idx < nleaf) {
+      const PairEnt e = lf[idx];
+      const int it = nodes[e.i0 * 3 + 1], jt = nodes[e.i1 * 3 + 1];
+      int in[3], jn[3];
+      V3 p[3], q[3], pe[3], qe[3];
 #pragma unroll
       for (int a = 0; a < 3; a++) {
-        const int i = in[a], j = jn[a];
-        pe[a] = v3(x[i * 3] + dt * v[i * 3], x[i * 3 + 1] + dt * v[i * 3 + 1], x[i * 3 + 2] + dt * v[i * 3 + 2]);
-        qe[a] = v3(x[j * 3] + dt * v[j * 3], x[j * 3 + 1] + dt * v[j * 3 + 1], x[j * 3 + 2] + dt * v[j * 3 + 2]);
+        in[a] = tri[it * 3 + a]; jn[a] = tri[jt * 3 + a];
+        p[a] = ld3(x, in[a]); q[a] = ld3(x, jn[a]);
       }
-      const Box b0 = ld_box(bx, e.i0), b1 = ld_box(bx, e.i1);
-#pragma unroll 1
-      for (int a = 0; a < 3; a++)
-        if (is_fv_ccd(in[0], in[1], in[2], jn[a], p[0], p[1], p[2], q[a], pe[0], pe[1], pe[2], qe[a], b0)) {
-          canon_fv(in[0], in[1], in[2], jn[a], key);
-          emit(e, a, key, rw, cap_raw, c);
+      if (ccd) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          const int i = in[a], j = jn[a];
+          pe[a] = v3(x[i * 3] + dt * v[i * 3], x[i * 3 + 1] + dt * v[i * 3 + 1], x[i * 3 + 2] + dt * v[i * 3 + 2]);
+          qe[a] = v3(x[j * 3] + dt * v[j * 3], x[j * 3 + 1] + dt * v[j * 3 + 1], x[j * 3 + 2] + dt * v[j * 3 + 2]);
         }
-#pragma unroll 1
-      for (int a = 0; a < 3; a++)
-        if (is_fv_ccd(jn[0], jn[1], jn[2], in[a], q[0], q[1], q[2], p[a], qe[0], qe[1], qe[2], pe[a], b1)) {
-          canon_fv(jn[0], jn[1], jn[2], in[a], key);
-          emit(e, 3 + a, key, rw, cap_raw, c);
+        const Box b0 = ld_box(bx, e.i0), b1 = ld_box(bx, e.i1);
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          if (maybe_fv_ccd(in[0], in[1], in[2], jn[a], p[0], p[1], p[2], q[a], pe[0], pe[1], pe[2], qe[a], b0)) mask |= 1u << a;
+          if (maybe_fv_ccd(jn[0], jn[1], jn[2], in[a], q[0], q[1], q[2], p[a], qe[0], qe[1], qe[2], pe[a], b1)) mask |= 1u << (3 + a);
         }
-#pragma unroll 1
-      for (int k = 0; k < 9; k++) {
-        const int a0 = k / 3, a1 = (a0 + 1) % 3, b0e = k - a0 * 3, b1e = (b0e + 1) % 3;
-        if (is_ee_ccd(in[a0], in[a1], jn[b0e], jn[b1e], p[a0], p[a1], q[b0e], q[b1e], pe[a0], pe[a1], qe[b0e], qe[b1e])) {
-          canon_ee(in[a0], in[a1], jn[b0e], jn[b1e], key);
-          emit(e, 6 + k, key, rw, cap_raw, c);
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+          const int a0 = k / 3, a1 = (a0 + 1) % 3, b0e = k - a0 * 3, b1e = (b0e + 1) % 3;
+          if (maybe_ee_ccd(in[a0], in[a1], jn[b0e], jn[b1e], p[a0], p[a1], q[b0e], q[b1e], pe[a0], pe[a1], qe[b0e], qe[b1e]))
+            mask |= 1u << (6 + k);
         }
-      }
-    } else {
-      // reference quirk (bvh_aabb.cpp:490-505): the vertex is tested against the box of BVH node number
-      // <triangle index>, not against the box of the face's own leaf
-      const Box b0 = ld_box(bx, it), b1 = ld_box(bx, jt);
-#pragma unroll 1
-      for (int a = 0; a < 3; a++)
-        if (is_fv_prx(in[0], in[1], in[2], jn[a], p[0], p[1], p[2], q[a], b0, delta)) {
-          canon_fv(in[0], in[1], in[2], jn[a], key);
-          emit(e, a, key, rw, cap_raw, c);
+      } else {
+        // reference quirk (bvh_aabb.cpp:490-505): box of BVH node number <triangle index>
+        const Box b0 = ld_box(bx, it), b1 = ld_box(bx, jt);
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          if (maybe_fv_prx(in[0], in[1], in[2], jn[a], q[a], b0)) mask |= 1u << a;
+          if (maybe_fv_prx(jn[0], jn[1], jn[2], in[a], p[a], b1)) mask |= 1u << (3 + a);
         }
-#pragma unroll 1
-      for (int a = 0; a < 3; a++)
-        if (is_fv_prx(jn[0], jn[1], jn[2], in[a], q[0], q[1], q[2], p[a], b1, delta)) {
-          canon_fv(jn[0], jn[1], jn[2], in[a], key);
-          emit(e, 3 + a, key, rw, cap_raw, c);
-        }
-#pragma unroll 1
-      for (int k = 0; k < 9; k++) {
-        const int a0 = k / 3, a1 = (a0 + 1) % 3, b0e = k - a0 * 3, b1e = (b0e + 1) % 3;
-        if (is_ee_prx(in[a0], in[a1], jn[b0e], jn[b1e], p[a0], p[a1], q[b0e], q[b1e], delta)) {
-          canon_ee(in[a0], in[a1], jn[b0e], jn[b1e], key);
-          emit(e, 6 + k, key, rw, cap_raw, c);
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+          const int a0 = k / 3, a1 = (a0 + 1) % 3, b0e = k - a0 * 3, b1e = (b0e + 1) % 3;
+          if (maybe_ee_prx(in[a0], in[a1], jn[b0e], jn[b1e], p[a0], p[a1], q[b0e], q[b1e], delta)) mask |= 1u << (6 + k);
         }
       }
+    }
+    // warp-level compaction: exclusive prefix of the survivor counts, one atomic per warp
+    const int n = __popc(mask);
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) continue;
+    int base = 0;
+    if (lane == 31) base = atomicAdd(&c[CNT_CAND], total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    long long pos = (long long)base + incl - n;
+    while (mask) {
+      const int slot = __ffs(mask) - 1;
+      mask &= mask - 1;
+      if (pos < cap_cand) cd[pos] = make_int2(idx, slot);
+      else atomicOr(&c[CNT_OVERFLOW], 2);
+      pos++;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_narrow(int ccd, int nnode, int np, const int* __restrict__ nodes,
+                                                 const int* __restrict__ tri, const double* __restrict__ boxes,
+                                                 const double* __restrict__ xyz, const double* __restrict__ uvw,
+                                                 double dt, double delta, const PairEnt* __restrict__ leaf,
+                                                 long long cap_leaf, const int2* __restrict__ cand, long long cap_cand,
+                                                 RawElem* __restrict__ raw, long long cap_raw, int* cnt) {
+  const int s = blockIdx.y;
+  int* c = cnt + s * NCNT;
+  if (!c[CNT_ACTIVE]) return;
+  const int ncand = (int)min((long long)c[CNT_CAND], cap_cand);
+  const double* bx = boxes + (size_t)s * nnode * 6;
+  const double* x = xyz + (size_t)s * np * 3;
+  const double* v = ccd ? uvw + (size_t)s * np * 3 : nullptr;
+  const PairEnt* lf = leaf + (size_t)s * cap_leaf;
+  const int2* cd = cand + (size_t)s * cap_cand;
+  RawElem* rw = raw + (size_t)s * cap_raw;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < ncand; k += gridDim.x * blockDim.x) {
+    const int2 cs = cd[k];
+    const int slot = cs.y;
+    const PairEnt e = lf[cs.x];
+    SlotData S;
+    load_slot(ccd, slot, e, nodes, tri, bx, x, v, dt, S);
+    bool hit;
+    if (ccd)
+      hit = slot < 6 ? is_fv_ccd(S.n[0], S.n[1], S.n[2], S.n[3], S.p[0], S.p[1], S.p[2], S.p[3], S.q[0], S.q[1], S.q[2], S.q[3], S.bb)
+                     : is_ee_ccd(S.n[0], S.n[1], S.n[2], S.n[3], S.p[0], S.p[1], S.p[2], S.p[3], S.q[0], S.q[1], S.q[2], S.q[3]);
+    else
+      hit = slot < 6 ? is_fv_prx(S.n[0], S.n[1], S.n[2], S.n[3], S.p[0], S.p[1], S.p[2], S.p[3], S.bb, delta)
+                     : is_ee_prx(S.n[0], S.n[1], S.n[2], S.n[3], S.p[0], S.p[1], S.p[2], S.p[3], delta);
+    if (hit) {
+      int key[4];
+      if (slot < 6) canon_fv(S.n[0], S.n[1], S.n[2], S.n[3], key);
+      else canon_ee(S.n[0], S.n[1], S.n[2], S.n[3], key);
+      emit(e, slot, key, rw, cap_raw, c);
     }
   }
 }
@@ -382,8 +460,12 @@ static int traverse_and_test(Ctx* c, const double* xyz, const double* uvw, doubl
   }
   {
     dim3 g(148 * 8, c->B);
-    k_narrow<<<g, 128, 0, KS(c, "k_narrow")>>>(ccd, c->nnode, c->np, c->nodes, c->tri, c->boxes, xyz, uvw, dt, delta, c->leaf,
-                                       c->cap_leaf, c->raw, c->cap_raw, c->cnt);
+    k_cull<<<g, 256, 0, KS(c, "k_cull")>>>(ccd, c->nnode, c->np, c->nodes, c->tri, c->boxes, xyz, uvw, dt, delta, c->leaf,
+                                   c->cap_leaf, c->cand, c->cap_leaf * 2, c->cnt);
+    CG_LAUNCH_CHECK(c);
+    dim3 g2(148 * 4, c->B);
+    k_narrow<<<g2, 128, 0, KS(c, "k_narrow")>>>(ccd, c->nnode, c->np, c->nodes, c->tri, c->boxes, xyz, uvw, dt, delta, c->leaf,
+                                        c->cap_leaf, c->cand, c->cap_leaf * 2, c->raw, c->cap_raw, c->cnt);
     CG_LAUNCH_CHECK(c);
   }
   return CLOTHGPU_OK;

@@ -52,7 +52,8 @@ static int dev_zeros(T** p, long long n) {
 }
 
 static void free_queues(Ctx* c) {
-  cudaFree(c->frontA); cudaFree(c->frontB); cudaFree(c->leaf); cudaFree(c->raw); cudaFree(c->raw_sorted);
+  cudaFree(c->frontA); cudaFree(c->frontB); cudaFree(c->leaf); cudaFree(c->cand); cudaFree(c->raw); cudaFree(c->raw_sorted);
+  c->cand = nullptr;
   cudaFree(c->elems); cudaFree(c->imp_level); cudaFree(c->imp_order); cudaFree(c->imp_pred); cudaFree(c->imp_lptr);
   c->frontA = c->frontB = c->leaf = nullptr;
   c->raw = c->raw_sorted = nullptr;
@@ -63,6 +64,7 @@ static int alloc_queues(Ctx* c) {
   CG_CHECK(dev_alloc(&c->frontA, c->cap_front * c->B));
   CG_CHECK(dev_alloc(&c->frontB, c->cap_front * c->B));
   CG_CHECK(dev_alloc(&c->leaf, c->cap_leaf * c->B));
+  CG_CHECK(dev_alloc(&c->cand, c->cap_leaf * 2 * c->B));
   CG_CHECK(dev_alloc(&c->raw, c->cap_raw * c->B));
   CG_CHECK(dev_alloc(&c->raw_sorted, c->cap_raw * c->B));
   CG_CHECK(dev_alloc(&c->elems, c->cap_elem * 5 * c->B));

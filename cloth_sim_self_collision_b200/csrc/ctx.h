@@ -94,6 +94,7 @@ enum {
   CNT_RIZ_NODES = 8,
   CNT_NLEVEL = 9,    // impulse dependency levels
   CNT_TICKET = 10,   // arrival counter of the "last block reduces" pattern
+  CNT_CAND = 11,     // narrow-phase candidates (leaf pair, test slot) that survived the cheap culls
   CNT_FRONT = 16     // frontier sizes per traversal depth: CNT_FRONT + depth  (depth < 72)
 };
 // per-scene device scalars (doubles): layout of scal[]
@@ -132,6 +133,7 @@ struct Ctx {
   TriPlan plan_f, plan_b;
   FacPlan plan_fac;
   unsigned long long* tri_xch = nullptr;  // exchange vector of the triangular sweeps (trisolve.cu)
+  int pcg_expect = 0;  // iterations the previous PCG solve needed (+1): when to start polling the convergence flag
   bool ilu_packed_valid = false;  // plan_*.packed mirrors iluDia / iluCrs
   bool tri_debug = false;         // clothgpu_debug_trisolve: per-CTA wait / compute cycle counters
   unsigned long long* tri_dbg_buf = nullptr;
@@ -165,6 +167,7 @@ struct Ctx {
   // traversal queues (capacities are per scene)
   long long cap_front = 0, cap_leaf = 0, cap_raw = 0, cap_elem = 0;
   PairEnt *frontA = nullptr, *frontB = nullptr, *leaf = nullptr;
+  int2* cand = nullptr;  // 2 x cap_leaf candidates per scene
   RawElem *raw = nullptr, *raw_sorted = nullptr;
   int* elems = nullptr;  // cap_elem x 5
   // impulse scheduling scratch

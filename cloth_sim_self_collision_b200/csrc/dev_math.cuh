@@ -320,4 +320,45 @@ __device__ __forceinline__ bool is_ee_ccd(int i0, int i1, int j0, int j1, V3 p0s
   return true;
 }
 
+// ---- cheap prefixes of the four predicates above (shared-vertex test and the box / slab / sign culls, in the same
+// order and with the same arithmetic): a conservative filter -- whatever survives is re-tested with the full
+// predicate, so the contact sets are unchanged
+__device__ __forceinline__ bool maybe_fv_prx(int i0, int i1, int i2, int i3, V3 p3, const Box& bb) {
+  if (i3 == i0 || i3 == i1 || i3 == i2) return false;
+  return box_inside(bb, p3);
+}
+__device__ __forceinline__ bool maybe_ee_prx(int i0, int i1, int j0, int j1, V3 p0, V3 p1, V3 q0, V3 q1, double delta) {
+  if (i0 == j0 || i0 == j1 || i1 == j0 || i1 == j1) return false;
+  if (q0.x + delta < p0.x && q0.x + delta < p1.x && q1.x + delta < p0.x && q1.x + delta < p1.x) return false;
+  if (q0.x - delta > p0.x && q0.x - delta > p1.x && q1.x - delta > p0.x && q1.x - delta > p1.x) return false;
+  if (q0.y + delta < p0.y && q0.y + delta < p1.y && q1.y + delta < p0.y && q1.y + delta < p1.y) return false;
+  if (q0.y - delta > p0.y && q0.y - delta > p1.y && q1.y - delta > p0.y && q1.y - delta > p1.y) return false;
+  if (q0.z + delta < p0.z && q0.z + delta < p1.z && q1.z + delta < p0.z && q1.z + delta < p1.z) return false;
+  if (q0.z - delta > p0.z && q0.z - delta > p1.z && q1.z - delta > p0.z && q1.z - delta > p1.z) return false;
+  return true;
+}
+__device__ __forceinline__ bool maybe_fv_ccd(int i0, int i1, int i2, int i3, V3 p0, V3 p1, V3 p2, V3 p3, V3 q0, V3 q1,
+                                             V3 q2, V3 q3, const Box& bb) {
+  const double eps = 1.0e-10;
+  if (i3 == i0 || i3 == i1 || i3 == i2) return false;
+  Box bbp;
+  box_init(bbp, p3, eps);
+  box_add(bbp, q3, eps);
+  if (!box_intersect(bb, bbp)) return false;
+  const V3 n = cross(p1 - p0, p2 - p0);
+  const double t0 = dot(p0 - p3, n), t1 = dot(q0 - q3, n);
+  const double t2 = dot(q1 - q3, n), t3 = dot(q2 - q3, n);
+  if (t0 * t1 > 0 && t0 * t2 > 0 && t0 * t3 > 0) return false;
+  return true;
+}
+__device__ __forceinline__ bool maybe_ee_ccd(int i0, int i1, int j0, int j1, V3 p0s, V3 p1s, V3 q0s, V3 q1s, V3 p0e,
+                                             V3 p1e, V3 q0e, V3 q1e) {
+  const double eps = 1.0e-10;
+  if (i0 == j0 || i0 == j1 || i1 == j0 || i1 == j1) return false;
+  Box bbq, bbp;
+  box_init(bbq, q0s, eps); box_add(bbq, q1s, eps); box_add(bbq, q0e, eps); box_add(bbq, q1e, eps);
+  box_init(bbp, p0s, eps); box_add(bbp, p1s, eps); box_add(bbp, p0e, eps); box_add(bbp, p1e, eps);
+  return box_intersect(bbp, bbq);
+}
+
 }  // namespace cg

@@ -453,8 +453,12 @@ int run_pcg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out) {
                                                          c->scal, c->cnt, c->npartial);
       CG_LAUNCH_CHECK(c);
     }
-    CG_CHECK(all_done(c, &done));
-    if (done) break;
+    // every kernel of the loop skips scenes whose convergence flag is set, so the host only has to look at the flags
+    // when the solve is likely over: not before the iteration count of the previous solve minus one
+    if (it + 2 >= c->pcg_expect) {
+      CG_CHECK(all_done(c, &done));
+      if (done) break;
+    }
     CG_CHECK(ilu_solve_launch(c, c->vec_z, c->vec_r, true));
     CG_CHECK(dot_launch(c, c->vec_r, c->vec_z, nxt, POST_STORE, 0, tol2, 1));
     k_xpay<<<vec_grid(c, n), 256, 0, KS(c, "k_xpay")>>>(n, nxt, cur, c->vec_z, c->vec_p, c->scal, c->cnt);
@@ -462,7 +466,10 @@ int run_pcg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out) {
     std::swap(cur, nxt);
   }
   if (!done) CG_CHECK(dot_launch(c, c->vec_r, c->vec_r, SC_SQ, POST_FINAL_CONV, 0, tol2, 1));
-  return fetch_solver_result(c, conv_out, iter_out);
+  CG_CHECK(fetch_solver_result(c, conv_out, iter_out));
+  c->pcg_expect = 0;
+  for (int s = 0; s < c->B; s++) c->pcg_expect = std::max(c->pcg_expect, c->h_cnt[s * NCNT + CNT_PCG_ITER] + 1);
+  return CLOTHGPU_OK;
 }
 
 // Solve_CG, matrix_square_sparse.cpp:338-406: the loop starts at 1 and on convergence reports the PREVIOUS ratio
