@@ -245,6 +245,7 @@ static int build_topology(Ctx* c, const int* tri, const int* quad, const int* ro
   {
     const char* mode = getenv("CLOTHGPU_TRISOLVE");
     c->use_strips = !(mode && strcmp(mode, "levels") == 0);
+    c->use_strips_fac = c->use_strips;
     const char* fs = getenv("CLOTHGPU_STRIPS");
     const int force_ns = fs ? atoi(fs) : 0;
     for (int dir = 0; dir < 2 && c->use_strips; dir++) {
@@ -252,9 +253,18 @@ static int build_topology(Ctx* c, const int* tri, const int* quad, const int* ro
       CG_CHECK(build_triplan_host(np, rowptr, colidx, dia.data(), dir == 0, force_ns, H));
       CG_CHECK(upload_triplan(c, H, dir == 0 ? c->plan_f : c->plan_b));
       if (dir == 0) {
+        // the strip-pipelined factorisation keeps the imports of FC_NIB micro-steps in shared memory; patterns
+        // without band structure (hundreds of far operands per micro-step) do not fit -- those contexts factorise
+        // with the level-scheduled kernel (k_ilu_factor) instead, same arithmetic
         FacPlanHost F;
         CG_CHECK(build_facplan_host(np, rowptr, colidx, dia.data(), H, F));
-        CG_CHECK(upload_facplan(c, F, c->plan_fac));
+        const int rc = upload_facplan(c, F, c->plan_fac);
+        if (rc == CLOTHGPU_ERR_CAPACITY) {
+          free_facplan(c->plan_fac);
+          c->use_strips_fac = false;
+        } else if (rc != CLOTHGPU_OK) {
+          return rc;
+        }
       }
     }
   }

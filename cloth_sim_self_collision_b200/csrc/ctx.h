@@ -138,6 +138,7 @@ struct Ctx {
   bool tri_debug = false;         // clothgpu_debug_trisolve: per-CTA wait / compute cycle counters
   unsigned long long* tri_dbg_buf = nullptr;
   int tri_dbg_grid[2] = {0, 0};
+  bool use_strips_fac = true;     // false: the factor plan did not fit shared memory (irregular patterns)
   bool use_strips = true;         // CLOTHGPU_TRISOLVE=levels selects the level-scheduled single-CTA kernels
   // ILU update lists: per row the (ik, kj, ij) slot triples in the reference's order (ij < 0: diagonal block)
   int *op_ptr = nullptr;

@@ -269,6 +269,13 @@ static int up(T** p, const std::vector<T>& h) {
 }
 
 int upload_facplan(Ctx* c, const FacPlanHost& H, FacPlan& D) {
+  {
+    const int urow0 = round_up(std::max(H.gmaxU, 1) * 72, 16);
+    const long long need = (long long)FC_SMEM_HDR + (long long)FC_H * std::max(H.gmaxU, 1) * 9 * 128 + 128 +
+                           (long long)FC_NIB * round_up(std::max(H.max_imp, 1) * urow0, 128) +
+                           (long long)FC_NST * ((long long)H.meta_stride * 4 + (long long)H.row_stride * 8);
+    if (need > 227 * 1024) { set_error("factor plan does not fit shared memory"); return CLOTHGPU_ERR_CAPACITY; }
+  }
   D.ns = H.ns; D.R = H.R; D.nms = H.nms; D.gmaxB = H.gmaxB; D.gmaxU = H.gmaxU; D.gmaxOps = H.gmaxOps;
   D.max_imp = H.max_imp; D.meta_stride = H.meta_stride; D.row_stride = H.row_stride; D.max_steps = H.max_steps;
   D.kg_stride = H.kg_stride; D.gT = H.gT;

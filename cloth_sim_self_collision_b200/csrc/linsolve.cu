@@ -391,7 +391,7 @@ int launch_ilu_setvalue(Ctx* c) {
 }
 int launch_ilu_factor(Ctx* c) {
   c->ilu_packed_valid = false;
-  if (c->use_strips) return launch_ilu_factor_strips(c);
+  if (c->use_strips_fac) return launch_ilu_factor_strips(c);
   k_ilu_factor<<<c->B, 1024, 0, KS(c, "k_ilu_factor")>>>(c->np, c->ncrs, c->nlev_f, c->lev_f_ptr, c->lev_f_rows, c->rowptr, c->diaind,
                                              c->op_ptr, c->ops, c->iluDia, c->iluCrs, c->cnt);
   CG_LAUNCH_CHECK(c);

@@ -177,3 +177,46 @@ def config1_default():
 def config3_256():
     """256 x 256 vertices, h = 0.1, self_contact_sparse constants."""
     return square_cloth_xz(255, 255, 0.1, SELF_CONTACT["areal_density"])
+
+
+def config4_512():
+    """512 x 512 vertices."""
+    return square_cloth_xz(511, 511, 0.1, SELF_CONTACT["areal_density"])
+
+
+def crumpled_state(sc, seed=7, amp_frac=3.0):
+    """Config 4's synthetic crumpled start: rest grid + a smooth out-of-plane displacement (sum of 8 seeded
+    sinusoids, amplitude 3h, wavelengths 8h..64h), zero velocity -- contact candidates from step 1."""
+    rng = np.random.default_rng(seed)
+    x = np.array(sc["xyz0"], dtype=np.float64).reshape(-1, 3).copy()
+    h = sc["h"]
+    normal_axis = int(np.argmin(np.ptp(x, axis=0)))
+    planar = [a for a in range(3) if a != normal_axis]
+    d = np.zeros(x.shape[0])
+    for _ in range(8):
+        lam = h * rng.uniform(8.0, 64.0)
+        ang = rng.uniform(0.0, 2.0 * np.pi)
+        ph = rng.uniform(0.0, 2.0 * np.pi)
+        k = 2.0 * np.pi / lam
+        d += np.sin(k * (np.cos(ang) * x[:, planar[0]] + np.sin(ang) * x[:, planar[1]]) + ph)
+    x[:, normal_axis] += amp_frac * h * d / 8.0
+    return x.ravel().copy(), np.zeros(x.size)
+
+
+def relabelled(sc, seed=11):
+    """The same mesh with its vertices renumbered by a random permutation: an irregular sparsity pattern (no band
+    structure, rows with scattered lower / upper neighbours) for the strip / micro-step plans."""
+    rng = np.random.default_rng(seed)
+    n = sc["np"]
+    perm = rng.permutation(n).astype(np.int32)  # new id of old vertex i
+    xyz0 = np.empty((n, 3))
+    xyz0[perm] = np.asarray(sc["xyz0"]).reshape(-1, 3)
+    bc = np.empty(n, dtype=np.int32)
+    bc[perm] = sc["bc"]
+    tri = perm[np.asarray(sc["tri"]).reshape(-1, 3)]
+    quad = perm[np.asarray(sc["quad"]).reshape(-1, 4)]
+    out = _finish(xyz0, bc, np.ascontiguousarray(tri, dtype=np.int32), np.ascontiguousarray(quad, dtype=np.int32), 1.0, 1.0)
+    out["mass_point"] = sc["mass_point"]
+    out["h"] = sc.get("h", 0.1)
+    out["perm"] = perm
+    return out
