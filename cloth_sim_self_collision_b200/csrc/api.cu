@@ -10,7 +10,6 @@
 
 namespace cg {
 
-int set_all_active(Ctx* c, int v);
 
 int set_active(Ctx* c, const int* active) {
   for (int s = 0; s < c->B; s++) c->h_cnt[s * NCNT + CNT_ACTIVE] = active ? (active[s] != 0) : 1;
@@ -26,7 +25,7 @@ static int copy_vec(Ctx* c, const double* src, double* dst) {
   return CLOTHGPU_OK;
 }
 
-int run_resolve(Ctx* c, const clothgpu_params& p, int* applied, int* stats) {
+int run_resolve(Ctx* c, const clothgpu_params& p, int* applied, int* stats, bool prox_prelaunched) {
   if (c->nnode == 0) { set_error("context has no BVH"); return CLOTHGPU_ERR_STATE; }
   const int B = c->B;
   std::vector<int> act(B, 1), n(B, 0), app(B, 0);
@@ -34,13 +33,17 @@ int run_resolve(Ctx* c, const clothgpu_params& p, int* applied, int* stats) {
   const double* x = c->xyz_prev;
   double* v = c->uvw;
   const double dt = p.dt, delta = p.contact_clearance;
-  CG_CHECK(set_active(c, nullptr));
-  // proximity pass, :369-395
-  phase_begin(c);
-  CG_CHECK(launch_refit(c, x, nullptr, delta, 0));
-  phase_end(c, 3);
+  // proximity pass, :369-395.  With prox_prelaunched the refit, traversal and narrow phase of this pass were issued
+  // on the second stream before the implicit solve (they only read the positions at the start of the step) and the
+  // main stream has already joined it.
+  if (!prox_prelaunched) {
+    CG_CHECK(set_active(c, nullptr));
+    phase_begin(c);
+    CG_CHECK(launch_refit(c, x, nullptr, delta, 0));
+    phase_end(c, 3);
+  }
   if (delta * 0.5 > 0) {  // CAABB3D::AddPoint ignores eps <= 0: all boxes stay empty and nothing intersects
-    CG_CHECK(run_contacts(c, x, nullptr, dt, delta, 0, n.data()));
+    CG_CHECK(run_contacts(c, x, nullptr, dt, delta, 0, n.data(), prox_prelaunched));
   }
   for (int s = 0; s < B; s++) {
     app[s] = n[s] > 0;
@@ -335,8 +338,24 @@ int clothgpu_step_self_contact(clothgpu_ctx* c, const clothgpu_params* p, int ns
   for (int step = 0; step < nsteps; step++) {
     // aXYZ1 = aXYZ (self_contact_sparse/main.cpp:224)
     CG_CUDA(cudaMemcpyAsync(c->xyz_prev, c->xyz, sizeof(double) * (size_t)c->B * c->ndof, cudaMemcpyDeviceToDevice, c->stream));
+    // The proximity detection (:369-395) reads only aXYZ1: it runs on the second stream while the latency-bound ILU
+    // sweeps of the implicit solve occupy 26 of the 148 SMs.  Measurement modes keep everything on one stream.
+    const bool overlap = !c->ktiming && !c->profiling && p->contact_clearance * 0.5 > 0;
+    if (overlap) {
+      CG_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+      CG_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+      cudaStream_t main_stream = c->stream;
+      c->stream = c->stream2;
+      int rc = set_all_active(c, 1);
+      if (rc == CLOTHGPU_OK) rc = launch_refit(c, c->xyz_prev, nullptr, p->contact_clearance, 0);
+      if (rc == CLOTHGPU_OK) rc = launch_contacts_async(c, c->xyz_prev, nullptr, p->dt, p->contact_clearance, 0);
+      c->stream = main_stream;
+      CG_CHECK(rc);
+      CG_CUDA(cudaEventRecord(c->ev_join, c->stream2));
+    }
     CG_CHECK(run_step_internal(c, *p, true, nullptr, iters.data()));
-    CG_CHECK(run_resolve(c, *p, applied.data(), stats));
+    if (overlap) CG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    CG_CHECK(run_resolve(c, *p, applied.data(), stats, overlap));
     if (stats)
       for (int s = 0; s < c->B; s++) stats[s * CLOTHGPU_NSTATS + 0] = iters[s];
     bool any = false;

@@ -500,11 +500,18 @@ static int canonical_set(Ctx* c, int s, int nraw) {
 }
 
 // GetContactElement_Proximity / _CCD for the scenes whose CNT_ACTIVE flag is set; counts[B] out (0 for inactive)
-int run_contacts(Ctx* c, const double* xyz, const double* uvw, double dt, double delta, int ccd, int* counts) {
+// the device side of a detection pass without any host synchronisation (used to run the proximity detection of a
+// step on a second stream, concurrently with the implicit solve)
+int launch_contacts_async(Ctx* c, const double* xyz, const double* uvw, double dt, double delta, int ccd) {
+  return traverse_and_test(c, xyz, uvw, dt, delta, ccd);
+}
+
+int run_contacts(Ctx* c, const double* xyz, const double* uvw, double dt, double delta, int ccd, int* counts,
+                 bool prelaunched) {
   if (c->nnode == 0) { set_error("context has no BVH"); return CLOTHGPU_ERR_STATE; }
   for (int attempt = 0;; attempt++) {
     phase_begin(c);
-    CG_CHECK(traverse_and_test(c, xyz, uvw, dt, delta, ccd));
+    if (!(prelaunched && attempt == 0)) CG_CHECK(traverse_and_test(c, xyz, uvw, dt, delta, ccd));
     CG_CHECK(fetch_counters(c));
     phase_end(c, 4);
     int bits = 0;

@@ -402,6 +402,9 @@ static int create_impl(Ctx* c, int nscene, int np, int ntri, int nquad, const in
   c->ndof = np * 3;
   const long long B = nscene;
   CG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CG_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  CG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   CG_CUDA(cudaEventCreate(&c->ev0)); CG_CUDA(cudaEventCreate(&c->ev1));
   CG_CUDA(cudaEventCreate(&c->evp0)); CG_CUDA(cudaEventCreate(&c->evp1));
   CG_CUDA(cudaEventCreate(&c->kt0)); CG_CUDA(cudaEventCreate(&c->kt1));
@@ -542,6 +545,9 @@ void clothgpu_destroy(clothgpu_ctx* c) {
   if (c->evp1) cudaEventDestroy(c->evp1);
   if (c->kt0) cudaEventDestroy(c->kt0);
   if (c->kt1) cudaEventDestroy(c->kt1);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }

@@ -105,6 +105,8 @@ struct Ctx {
   int device = 0;
   int B = 1, np = 0, ntri = 0, nquad = 0, ncrs = 0, nnode = 0, ndof = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // proximity detection of a step, concurrent with the implicit solve
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr;
   long long launches = 0;
   bool profiling = false;
@@ -251,13 +253,16 @@ int run_pcg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out);
 int run_cg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out);
 int run_step_internal(Ctx* c, const clothgpu_params& p, bool use_ilu, double* conv_out, int* iter_out);
 int launch_refit(Ctx* c, const double* xyz, const double* uvw, double par, int mode);
-int run_contacts(Ctx* c, const double* xyz, const double* uvw, double dt, double delta, int ccd, int* counts);
+int run_contacts(Ctx* c, const double* xyz, const double* uvw, double dt, double delta, int ccd, int* counts,
+                 bool prelaunched = false);
+int launch_contacts_async(Ctx* c, const double* xyz, const double* uvw, double dt, double delta, int ccd);
+int set_all_active(Ctx* c, int v);
 int launch_impulse(Ctx* c, const double* xyz, double* uvw, double delta, double stiffness, double dt, double mass,
                    int ccd);
 int launch_riz_reset(Ctx* c);
 int launch_riz_make(Ctx* c);
 int launch_riz_apply(Ctx* c, const double* xyz, double* uvw);
-int run_resolve(Ctx* c, const clothgpu_params& p, int* applied, int* stats);
+int run_resolve(Ctx* c, const clothgpu_params& p, int* applied, int* stats, bool prox_prelaunched = false);
 int fetch_counters(Ctx* c);  // cnt -> h_cnt, synchronous
 int ensure_scratch(Ctx* c, size_t bytes);
 int ensure_sort_capacity(Ctx* c, long long n);
