@@ -368,6 +368,7 @@ struct FacArgs {
 
 // one CTA per (strip, scene): warps 0-3 compute (three rows each, nine lanes per row = one lane per block entry),
 // warp 4 lane 0 streams row data, warp 5 lane 0 publishes, warp 6 lane 0 imports
+template <bool DBG>
 __global__ void __launch_bounds__(FC_THREADS, 1) k_ilu_factor_strips(const FacArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);        // FC_NST
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_ilu_factor_strips(const FacAr
     const int gm = act ? gq : TS_ROWS - 1;               // metadata column the lane reads
     const int slot8 = act ? (gq * 9 + e9) * 8 : (90 + (lane % 6)) * 8;  // byte offset of the lane's entry inside a block
     const int rowbase8 = gq * 72;                         // byte offset of the group's entries inside a block
-    const bool dbg = A.dbg != nullptr && warp == 0;
+    const bool dbg = DBG && warp == 0;  // cycle counters are compiled out of the production instantiation
     unsigned long long t_begin = 0, w_full = 0, w_imp = 0, w_ops = 0, w_tail = 0, w_inv = 0, w_bar = 0;
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
     if (dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); t_begin = t; }
@@ -632,8 +633,13 @@ int launch_ilu_factor_strips(Ctx* c) {
     if (grid <= 4096) A.dbg = c->tri_dbg_buf;
     c->tri_dbg_grid[0] = grid;
   }
-  CG_CUDA(cudaFuncSetAttribute(k_ilu_factor_strips, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
-  k_ilu_factor_strips<<<grid, FC_THREADS, P.smem_bytes, KS(c, "k_ilu_factor_strips")>>>(A);
+  if (A.dbg) {
+    CG_CUDA(cudaFuncSetAttribute(k_ilu_factor_strips<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
+    k_ilu_factor_strips<true><<<grid, FC_THREADS, P.smem_bytes, KS(c, "k_ilu_factor_strips")>>>(A);
+  } else {
+    CG_CUDA(cudaFuncSetAttribute(k_ilu_factor_strips<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
+    k_ilu_factor_strips<false><<<grid, FC_THREADS, P.smem_bytes, KS(c, "k_ilu_factor_strips")>>>(A);
+  }
   CG_LAUNCH_CHECK(c);
   P.pbase += (unsigned long long)P.max_steps + 2;
   P.tbase += (unsigned long long)grid;

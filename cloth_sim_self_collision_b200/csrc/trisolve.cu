@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(256) k_pack(long long nval, const int* __restr
 }
 
 // one CTA per (strip, scene): warp 0 computes, warp 1 streams matrix chunks, warp 2 publishes, warp 3 imports
-template <bool FWD, int ND>
+template <bool FWD, int ND, bool DBG>
 __global__ void __launch_bounds__(128, 1) k_trisolve(const TriArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(128, 1) k_trisolve(const TriArgs A) {
     const int gq = g < TS_ROWS ? g : TS_ROWS - 1;
     const int l0 = (gq * 3) & 31;
     uint32_t seen = 0;
-    const bool dbg = A.dbg != nullptr;
+    constexpr bool dbg = DBG;  // cycle counters are compiled out of the production instantiation
     unsigned long long t_begin = 0, w_mbar = 0, w_ghost = 0, w_comp = 0, w_sig = 0;
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
     if (dbg) t_begin = gtime_ns();
@@ -770,8 +770,13 @@ static int pack_plan(Ctx* c, TriPlan& P) {
 
 template <bool FWD, int ND>
 static int launch_tri_nd(Ctx* c, const TriPlan& P, const TriArgs& A, int grid) {
-  CG_CUDA(cudaFuncSetAttribute(k_trisolve<FWD, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
-  k_trisolve<FWD, ND><<<grid, 128, P.smem_bytes, KS(c, FWD ? "k_trisolve_fwd" : "k_trisolve_bwd")>>>(A);
+  if (A.dbg) {
+    CG_CUDA(cudaFuncSetAttribute(k_trisolve<FWD, ND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
+    k_trisolve<FWD, ND, true><<<grid, 128, P.smem_bytes, KS(c, FWD ? "k_trisolve_fwd" : "k_trisolve_bwd")>>>(A);
+  } else {
+    CG_CUDA(cudaFuncSetAttribute(k_trisolve<FWD, ND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
+    k_trisolve<FWD, ND, false><<<grid, 128, P.smem_bytes, KS(c, FWD ? "k_trisolve_fwd" : "k_trisolve_bwd")>>>(A);
+  }
   CG_LAUNCH_CHECK(c);
   return CLOTHGPU_OK;
 }

@@ -89,5 +89,35 @@ def full(path):
             print("   stall %-60s %.2f" % (re.sub(r"smsp__average_warps?_(latency_)?issue_stalled_", "", h), v))
 
 
+def to_bytes(val, unit):
+    v = float(val.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(unit, 1)
+
+
+def traffic(paths):
+    """{bench kernel name: DRAM bytes (read + write) per launch}, averaged over the captured launches."""
+    import json
+    acc = {}
+    for path in paths:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(out)))
+        hdr, units, data = rows[0], rows[1], rows[2:]
+        col = {h: i for i, h in enumerate(hdr)}
+        for r in data:
+            name = r[col["Kernel Name"]]
+            k = short(name)
+            m = re.match(r"k_trisolve<\(bool\)?(\d)", name.replace("void ", "").replace("cg::", ""))
+            if k.startswith("k_trisolve"):
+                k = "k_trisolve_fwd" if re.search(r"k_trisolve<(\(bool\))?1", name) else "k_trisolve_bwd"
+            k = re.sub(r"<.*", "", k)
+            b = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]]) + \
+                to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
+            acc.setdefault(k, []).append(b)
+    print(json.dumps({k: sum(v) / len(v) for k, v in sorted(acc.items())}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2:])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
