@@ -40,8 +40,6 @@ namespace cg {
 // ------------------------------------------------------------------------------------------------ host: plan
 namespace {
 
-inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
-
 struct Sched {                 // micro-step schedule of one candidate strip size
   int R = 0, ns = 0, nms = 0;
   std::vector<int> strip_ms;   // ns+1
@@ -52,6 +50,18 @@ struct Sched {                 // micro-step schedule of one candidate strip siz
 }  // namespace
 
 static inline int plan_pos(bool fwd, int np, int row) { return fwd ? row : np - 1 - row; }
+
+// ---- per-micro-step layouts shared by the planner, the verifier and the kernels
+// operand offsets: the first TS_MAXD operands of row group q are eight consecutive ints (two LDS.128 per lane), the
+// rest (rows with more operands) follow operand-major
+__host__ __device__ static inline int ts_slot_index(int d, int q) {
+  return d < TS_MAXD ? TS_META_HDR + q * TS_MAXD + d : TS_META_HDR + TS_ROWS * TS_MAXD + (d - TS_MAXD) * TS_ROWS + q;
+}
+// coefficients: element e of a lane (forward: 0..2 = its D^-1 row, then 3 per operand; backward: 3 per operand) is
+// half of a 16-byte unit, units are lane-major: one conflict-free LDS.128 fetches two elements
+__host__ __device__ static inline int ts_val_index(int e, int lane) { return ((e >> 1) * 32 + lane) * 2 + (e & 1); }
+static inline int ts_meta_ints(int gmax) { return (TS_META_HDR + TS_ROWS * TS_MAXD + std::max(0, gmax - TS_MAXD) * TS_ROWS + 3) / 4 * 4; }
+static inline int ts_val_doubles(int gmax, bool fwd) { return ((3 * (gmax + (fwd ? 1 : 0)) + 1) / 2) * 64; }
 
 static void make_sched(int np, const std::vector<int>& lev, bool fwd, int R, Sched& S) {
   S.R = R;
@@ -137,8 +147,7 @@ int build_triplan_host(int np, const int* rowptr, const int* colidx, const int* 
   // choose the strip count: simulate the pipeline for a list of candidates, keep the shortest makespan
   int gmax0 = 0;
   for (int i = 0; i < np; i++) gmax0 = std::max(gmax0, fwd ? dia[i] - rowptr[i] : rowptr[i + 1] - dia[i]);
-  const long long ring_bytes = (long long)TS_NST * TS_K * (round_up(TS_META_HDR + gmax0 * TS_ROWS, 4) * 4 +
-                                                            std::max(1, gmax0 + (fwd ? 1 : 0)) * 768) + TS_SMEM_HDR;
+  const long long ring_bytes = (long long)TS_NST * TS_K * (ts_meta_ints(gmax0) * 4 + std::max(64, ts_val_doubles(gmax0, fwd)) * 8) + TS_SMEM_HDR;
   const long long smem_budget = 224 * 1024;
   static const int cand[] = {1, 2, 3, 4, 6, 8, 10, 12, 14, 16, 18, 20, 22, 24, 26, 28, 32, 36, 40, 44, 48, 52, 56,
                              64, 72, 80, 88, 96, 104, 112, 128, 144};
@@ -199,9 +208,8 @@ int build_triplan_host(int np, const int* rowptr, const int* colidx, const int* 
   int gmax = 0;  // largest operand count of any row
   for (int i = 0; i < np; i++) gmax = std::max(gmax, fwd ? dia[i] - rowptr[i] : rowptr[i + 1] - dia[i]);
   P.ndmax = gmax;
-  P.meta_stride = round_up(TS_META_HDR + gmax * TS_ROWS, 4);           // ints per micro-step
-  P.val_stride = (gmax + (fwd ? 1 : 0)) * 96;                           // doubles per micro-step
-  if (P.val_stride == 0) P.val_stride = 96;
+  P.meta_stride = ts_meta_ints(gmax);                                   // ints per micro-step
+  P.val_stride = std::max(64, ts_val_doubles(gmax, fwd));               // doubles per micro-step
   P.meta.assign((size_t)S.nms * P.meta_stride, 0);
   P.pk_src.assign((size_t)S.nms * P.val_stride, -1);
   P.strip_gh.assign(S.ns + 1, 0); P.gh_row.clear(); P.gh_src.clear(); P.gh_need.clear();
@@ -240,8 +248,8 @@ int build_triplan_host(int np, const int* rowptr, const int* colidx, const int* 
       const int lay0 = fwd ? 1 : 0;  // layer 0 of a forward step holds the D^-1 rows
       int ndmax = 0, nearmask = 0;
       for (int q = 0; q <= TS_ROWS; q++) M[4 + q] = dummy_off;
-      for (int d = 0; d < gmax; d++)
-        for (int q = 0; q < TS_ROWS; q++) M[TS_META_HDR + d * TS_ROWS + q] = zero_off;
+      for (int d = 0; d < std::max(gmax, (int)TS_MAXD); d++)
+        for (int q = 0; q < TS_ROWS; q++) M[ts_slot_index(d, q)] = zero_off;
       for (int q = 0; q < TS_ROWS; q++) {
         const int row = rows[q];
         if (row < 0) continue;
@@ -260,13 +268,13 @@ int build_triplan_host(int np, const int* rowptr, const int* colidx, const int* 
             if (ghost_owner[c] != k) { ghost_owner[c] = k; ghost_slot[c] = nghost++; }  // same order as the first pass
             slot = S.R + ghost_slot[c];
           }
-          M[TS_META_HDR + d * TS_ROWS + q] = slot * 32;
+          M[ts_slot_index(d, q)] = slot * 32;
           for (int kk = 0; kk < 3; kk++)
-            for (int r = 0; r < 3; r++) V[((lay0 + d) * 3 + kk) * 32 + q * 3 + r] = j * 9 + r * 3 + kk;
+            for (int r = 0; r < 3; r++) V[ts_val_index((lay0 + d) * 3 + kk, q * 3 + r)] = j * 9 + r * 3 + kk;
         }
         if (fwd)
           for (int kk = 0; kk < 3; kk++)
-            for (int r = 0; r < 3; r++) V[kk * 32 + q * 3 + r] = ncrs * 9 + row * 9 + r * 3 + kk;
+            for (int r = 0; r < 3; r++) V[ts_val_index(kk, q * 3 + r)] = ncrs * 9 + row * 9 + r * 3 + kk;
       }
       // operands beyond TS_MAXD are handled by the un-pipelined tail loop, i.e. always after the barrier
       int fmin = std::min(ndmax, (int)TS_MAXD);
@@ -335,7 +343,7 @@ int verify_triplan_host(int np, const int* rowptr, const int* colidx, const int*
         }
         const int j0 = row < 0 ? 0 : (fwd ? rowptr[row] : dia[row]);
         for (int d = 0; d < P.ndmax; d++) {
-          const int off = M[TS_META_HDR + d * TS_ROWS + q];
+          const int off = M[ts_slot_index(d, q)];
           if (d >= nd) {
             if (off != zero_off) PLAN_FAIL("padding operand must read the zero row");
             continue;
@@ -352,7 +360,7 @@ int verify_triplan_host(int np, const int* rowptr, const int* colidx, const int*
           }
           for (int kk = 0; kk < 3; kk++)
             for (int r = 0; r < 3; r++) {
-              const int idx = ((lay0 + d) * 3 + kk) * 32 + q * 3 + r;
+              const int idx = ts_val_index((lay0 + d) * 3 + kk, q * 3 + r);
               if (V[idx] != (j0 + d) * 9 + r * 3 + kk) PLAN_FAIL("packed value map");
               used[idx] = 1;
             }
@@ -360,7 +368,7 @@ int verify_triplan_host(int np, const int* rowptr, const int* colidx, const int*
         if (fwd && row >= 0)
           for (int kk = 0; kk < 3; kk++)
             for (int r = 0; r < 3; r++) {
-              const int idx = kk * 32 + q * 3 + r;
+              const int idx = ts_val_index(kk, q * 3 + r);
               if (V[idx] != ncrs * 9 + row * 9 + r * 3 + kk) PLAN_FAIL("packed diagonal map");
               used[idx] = 1;
             }
@@ -587,6 +595,7 @@ __global__ void __launch_bounds__(128, 1) k_trisolve(const TriArgs A) {
     if (dbg) t_begin = gtime_ns();
     // register image of the micro-step about to run: operand offsets and coefficients do not depend on the
     // solution, so they are fetched one micro-step ahead, in the shadow of the previous step's subtraction chain
+    constexpr int NE = 3 * (ND + LAY0);  // coefficients per lane and micro-step
     int myoff = 0, off[ND];
     uint32_t gneed = 0;
     int ndmax = 0;
@@ -594,17 +603,29 @@ __global__ void __launch_bounds__(128, 1) k_trisolve(const TriArgs A) {
 #define TS_LOAD_STEP(MP_, VP_)                                                                   \
     {                                                                                            \
       const int* Mp = (MP_);                                                                     \
-      const double* Vp = (VP_);                                                                  \
+      const double2* Vp = reinterpret_cast<const double2*>(VP_) + lane;                          \
       gneed = (uint32_t)Mp[1];                                                                   \
       ndmax = Mp[0];                                                                             \
       myoff = Mp[4 + g] + r * 8;                                                                 \
-      _Pragma("unroll") for (int d = 0; d < ND; d++) {                                           \
-        off[d] = Mp[TS_META_HDR + d * TS_ROWS + gq];                                             \
-        av[d][0] = Vp[((LAY0 + d) * 3 + 0) * 32 + lane];                                         \
-        av[d][1] = Vp[((LAY0 + d) * 3 + 1) * 32 + lane];                                         \
-        av[d][2] = Vp[((LAY0 + d) * 3 + 2) * 32 + lane];                                         \
+      {                                                                                          \
+        const int4 s0 = *reinterpret_cast<const int4*>(Mp + TS_META_HDR + gq * TS_MAXD);         \
+        const int so[4] = {s0.x, s0.y, s0.z, s0.w};                                              \
+        _Pragma("unroll") for (int d = 0; d < 4 && d < ND; d++) off[d] = so[d];                  \
+        if (ND > 4) {                                                                            \
+          const int4 s1 = *reinterpret_cast<const int4*>(Mp + TS_META_HDR + gq * TS_MAXD + 4);   \
+          const int so1[4] = {s1.x, s1.y, s1.z, s1.w};                                           \
+          _Pragma("unroll") for (int d = 4; d < ND; d++) off[d] = so1[d - 4];                    \
+        }                                                                                        \
       }                                                                                          \
-      if (FWD) { dd0 = Vp[0 * 32 + lane]; dd1 = Vp[1 * 32 + lane]; dd2 = Vp[2 * 32 + lane]; }    \
+      double cv[NE + 1];                                                                         \
+      _Pragma("unroll") for (int u = 0; u < (NE + 1) / 2; u++) {                                 \
+        const double2 c2 = Vp[u * 32];                                                           \
+        cv[2 * u] = c2.x; cv[2 * u + 1] = c2.y;                                                  \
+      }                                                                                          \
+      _Pragma("unroll") for (int d = 0; d < ND; d++) {                                           \
+        av[d][0] = cv[(LAY0 + d) * 3 + 0]; av[d][1] = cv[(LAY0 + d) * 3 + 1]; av[d][2] = cv[(LAY0 + d) * 3 + 2]; \
+      }                                                                                          \
+      if (FWD) { dd0 = cv[0]; dd1 = cv[1]; dd2 = cv[2]; }                                        \
     }
     const int nstage = nsteps / TS_K;
     if (nstage > 0) {
@@ -651,9 +672,9 @@ __global__ void __launch_bounds__(128, 1) k_trisolve(const TriArgs A) {
         for (int d = 0; d < ND; d++) t -= pr[d];
         if (cur_ndmax > ND) {  // rows with more operands than the unrolled body holds (ND == TS_MAXD only)
           for (int d = ND; d < cur_ndmax; d++) {
-            const int o = Mk[TS_META_HDR + d * TS_ROWS + gq];
-            const double a0 = Vk[((LAY0 + d) * 3 + 0) * 32 + lane], a1 = Vk[((LAY0 + d) * 3 + 1) * 32 + lane],
-                         a2 = Vk[((LAY0 + d) * 3 + 2) * 32 + lane];
+            const int o = Mk[ts_slot_index(d, gq)];
+            const double a0 = Vk[ts_val_index((LAY0 + d) * 3 + 0, lane)], a1 = Vk[ts_val_index((LAY0 + d) * 3 + 1, lane)],
+                         a2 = Vk[ts_val_index((LAY0 + d) * 3 + 2, lane)];
             const double x0 = *reinterpret_cast<const double*>(xsc + o), x1 = *reinterpret_cast<const double*>(xsc + o + 8),
                          x2 = *reinterpret_cast<const double*>(xsc + o + 16);
             t -= a0 * x0 + a1 * x1 + a2 * x2;
