@@ -127,3 +127,23 @@ def test_trisolve_plan_irregular_pattern(lib):
         rp[i + 1] = len(ci)
     for force in (0, 1, 5, 33):
         _selftest(lib, (n, rp, np.array(ci, dtype=np.int32)), force)
+
+
+def test_trisolve_plan_degenerate_patterns(lib):
+    """Edge cases of the planner: a single row, a purely diagonal matrix (no dependencies at all: one level), a
+    dense-ish arrow pattern (one row depending on all others: more operands than the unrolled kernels hold)."""
+    st = _selftest(lib, (1, np.array([0, 0]), np.zeros(0, dtype=np.int32)))
+    assert st[0, 0] == 1 and st[0, 2] >= 1
+    n = 40
+    st = _selftest(lib, (n, np.zeros(n + 1, dtype=np.int32), np.zeros(0, dtype=np.int32)))
+    assert st[0, 2] % 4 == 0  # micro-steps are padded to whole TMA stages
+    # arrow: last row coupled to every other row (15 lower operands > TS_MAXD = 8)
+    n = 16
+    rows = [[n - 1] for _ in range(n - 1)] + [list(range(n - 1))]
+    rp = np.zeros(n + 1, dtype=np.int32)
+    ci = []
+    for i in range(n):
+        ci += rows[i]
+        rp[i + 1] = len(ci)
+    for force in (0, 1, 3):
+        _selftest(lib, (n, rp, np.array(ci, dtype=np.int32)), force)

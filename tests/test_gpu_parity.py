@@ -502,3 +502,39 @@ def test_config4_crumpled_512(oracle):
     assert np.array_equal(st[:5], ost[:5]), (st[:5], ost[:5])
     assert rel_err(gx, ox) < 1.0e-9 and rel_err(gv, ov) < 1.0e-7
     g.close()
+
+
+def test_tiny_and_ragged_scenes(oracle):
+    """The smallest meshes the reference's scene generator can make (2 x 2 and 2 x 3 vertices: one or two cells, a
+    single strip, rows without any dependency) and a 3 x 9 strip, three self-contact steps each."""
+    for nx, nz in ((1, 1), (1, 2), (2, 8)):
+        sc = S.square_cloth_xz(nx, nz, 0.1, S.SELF_CONTACT["areal_density"])
+        sc["bvh"] = S.median_split_bvh(sc)
+        p = T.params_for(sc, S.SELF_CONTACT)
+        g = G.ClothGPU(sc)
+        sim = oracle.sim(sc)
+        for _ in range(3):
+            st = g.step_self_contact(p)[0]
+            ost = sim.step_self_contact(p)
+            assert np.array_equal(st[:5], ost[:5]), (nx, nz, st[:5], ost[:5])
+        gx, gv = g.download_state()
+        ox, ov = sim.get_state()
+        assert rel_err(gx, ox) < 1.0e-9 and rel_err(gv, ov) < 1.0e-7, (nx, nz)
+        g.close()
+
+
+def test_contact_ops_need_a_bvh_and_zero_clearance_finds_nothing(oracle, sc_contact):
+    p = T.params_for(sc_contact, S.SELF_CONTACT)
+    g = G.ClothGPU(sc_contact, with_bvh=False)
+    with pytest.raises(G.ClothGPUError):
+        g.step_self_contact(p)  # CLOTHGPU_ERR_STATE: context created without a BVH
+    g.close()
+    # clearance 0: CAABB3D::AddPoint ignores eps <= 0, every proximity box stays empty (aabb.h:102-122)
+    x, v = T.folded_state(sc_contact)
+    g = G.ClothGPU(sc_contact)
+    g.upload_state(x, v)
+    g.write(G.BUF_XYZ_PREV, x)
+    p0 = T.params_for(sc_contact, S.SELF_CONTACT, clearance=0.0)
+    applied, stats = g.resolve_self_contact(p0)
+    assert stats[0][1] == 0  # no proximity elements
+    g.close()
