@@ -51,7 +51,10 @@ struct TriPlanHost {
 };
 // strip-pipelined factorisation (ilufactor.cu): follows the forward sweep's strips and micro-steps
 enum { FC_H = 8, FC_NST = 3, FC_NIB = 3, FC_META_HDR = 48, FC_SMEM_HDR = 256, FC_BUNDLE = 6,
-       FC_CWARPS = 4, FC_THREADS = (4 + 3) * 32 };
+       FC_RWARPS = 4,              // row triplets per micro-step (10 rows -> 4 triplets)
+       FC_CWARPS = 8,              // compute warps: two per triplet, each takes half of every bundle
+       FC_HB = 3,                  // FC_BUNDLE / 2
+       FC_THREADS = (8 + 3) * 32 };
 struct FacPlanHost {
   int ns = 0, R = 0, nms = 0, H = 0, gmaxB = 0, gmaxU = 0, gmaxOps = 0, max_imp = 0, meta_stride = 0, row_stride = 0;
   int max_steps = 0, gmaxLo = 0, gT = 0, kg_stride = 0;

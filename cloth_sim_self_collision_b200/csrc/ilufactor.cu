@@ -366,8 +366,9 @@ struct FacArgs {
   unsigned long long* dbg;  // optional: 8 counters per CTA (clothgpu_debug_trisolve, slot of the forward sweep)
 };
 
-// one CTA per (strip, scene): warps 0-3 compute (three rows each, nine lanes per row = one lane per block entry),
-// warp 4 lane 0 streams row data, warp 5 lane 0 publishes, warp 6 lane 0 imports
+// one CTA per (strip, scene): warps 0-7 compute -- warp w and warp w+4 share three rows (nine lanes per row = one lane
+// per block entry) and split every bundle of independent updates / upper blocks between them -- warp 8 lane 0 streams
+// row data, warp 9 lane 0 publishes, warp 10 lane 0 imports
 template <bool DBG>
 __global__ void __launch_bounds__(FC_THREADS, 1) k_ilu_factor_strips(const FacArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -408,9 +409,10 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_ilu_factor_strips(const FacAr
   if (warp < FC_CWARPS) {
     // ---------------------------------------------------------------- compute warps
     // lane -> (row group q, block entry e = r*3 + c); lanes 27..31 idle on the slots of a spare group
+    const int wq = warp % FC_RWARPS, half = warp / FC_RWARPS;  // row triplet, half of every bundle
     const int gl = lane / 9, e9 = lane - gl * 9, r = e9 / 3, cc = e9 - r * 3;
-    const bool act = gl < 3 && warp * 3 + gl < TS_ROWS;
-    const int gq = act ? warp * 3 + gl : TS_ROWS;        // group TS_ROWS (slots 90..95 of every block) is scratch for idle lanes
+    const bool act = gl < 3 && wq * 3 + gl < TS_ROWS;
+    const int gq = act ? wq * 3 + gl : TS_ROWS;        // group TS_ROWS (slots 90..95 of every block) is scratch for idle lanes
     const int gm = act ? gq : TS_ROWS - 1;               // metadata column the lane reads
     const int slot8 = act ? (gq * 9 + e9) * 8 : (90 + (lane % 6)) * 8;  // byte offset of the lane's entry inside a block
     const int rowbase8 = gq * 72;                         // byte offset of the group's entries inside a block
@@ -441,11 +443,11 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_ilu_factor_strips(const FacAr
         // idle lanes run the same code on scratch slots with zero coefficients
         const double a0 = act ? *reinterpret_cast<const double*>(pk) : 0.0, a1 = act ? *reinterpret_cast<const double*>(pk + 8) : 0.0,
                      a2 = act ? *reinterpret_cast<const double*>(pk + 16) : 0.0;
-        for (int t0 = 0; t0 < ntk; t0 += FC_BUNDLE) {
-          unsigned char* pt[FC_BUNDLE];
-          double b0[FC_BUNDLE], b1[FC_BUNDLE], b2[FC_BUNDLE], t[FC_BUNDLE];
+        for (int t0 = half * FC_HB; t0 < ntk; t0 += FC_BUNDLE) {
+          unsigned char* pt[FC_HB];
+          double b0[FC_HB], b1[FC_HB], b2[FC_HB], t[FC_HB];
 #pragma unroll
-          for (int j = 0; j < FC_BUNDLE; j++) {
+          for (int j = 0; j < FC_HB; j++) {
             const int2 e = *reinterpret_cast<const int2*>(K + 12 + ((t0 + j) * TS_ROWS + gm) * 2);
             const unsigned char* pb = (e.x >= 0 ? ring + e.x : ib + (-1 - e.x)) + cc * 8;  // U'_kj[0..2][c]
             pt[j] = sc + e.y + slot8;
@@ -455,11 +457,12 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_ilu_factor_strips(const FacAr
             t[j] = *reinterpret_cast<const double*>(pt[j]);
           }
 #pragma unroll
-          for (int j = 0; j < FC_BUNDLE; j++) t[j] = t[j] - (a0 * b0[j] + a1 * b1[j] + a2 * b2[j]);
+          for (int j = 0; j < FC_HB; j++) t[j] = t[j] - (a0 * b0[j] + a1 * b1[j] + a2 * b2[j]);
 #pragma unroll
-          for (int j = 0; j < FC_BUNDLE; j++) *reinterpret_cast<double*>(pt[j]) = t[j];
+          for (int j = 0; j < FC_HB; j++) *reinterpret_cast<double*>(pt[j]) = t[j];
         }
-        __syncwarp();
+        // the two warps of a row triplet have written disjoint targets: both must see all of them before the next A_ik
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + wq) : "memory");
       }
       if (dbg) c3 = clock64();
       // ---- D_i <- D_i^-1 by cofactors (CalcInvMat3, ilu_sparse.cpp:77-97); a singular pivot is left as is (:541-551)
@@ -492,21 +495,21 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_ilu_factor_strips(const FacAr
       const double ar1 = r == 0 ? a[1] : (r == 1 ? a[4] : a[7]);
       const double ar2 = r == 0 ? a[2] : (r == 1 ? a[5] : a[8]);
       const int crs0 = act ? M[14 + gm] : 0, nlo = act ? M[24 + gm] : 0, nup = act ? M[34 + gm] : 0;
-      if (row >= 0) dia[(size_t)row * 9 + e9] = cc == 0 ? ar0 : (cc == 1 ? ar1 : ar2);
+      if (row >= 0 && half == 0) dia[(size_t)row * 9 + e9] = cc == 0 ? ar0 : (cc == 1 ? ar1 : ar2);
       if (dbg) c4 = clock64();
       // ---- U'_ij = D_i^-1 U_ij (:556-567): to the ring (next steps of this strip), the ILU array and the export copy
       unsigned char* myring = ring + (size_t)(((m % FC_H) * A.gmaxU * 16 + (act ? gq : 15)) * 9 + e9) * 8;
-      for (int u0 = 0; u0 < nupmax; u0 += FC_BUNDLE) {
-        double v[FC_BUNDLE];
+      for (int u0 = half * FC_HB; u0 < nupmax; u0 += FC_BUNDLE) {
+        double v[FC_HB];
 #pragma unroll
-        for (int j = 0; j < FC_BUNDLE; j++) {
+        for (int j = 0; j < FC_HB; j++) {
           const int u = u0 + j;
           const unsigned char* pu = sc + (nlo + (u < nup ? u : 0)) * 768 + (act ? rowbase8 : 720) + cc * 8;  // U_ij[0..2][c]
           v[j] = ar0 * *reinterpret_cast<const double*>(pu) + ar1 * *reinterpret_cast<const double*>(pu + 24) +
                  ar2 * *reinterpret_cast<const double*>(pu + 48);
         }
 #pragma unroll
-        for (int j = 0; j < FC_BUNDLE; j++) {
+        for (int j = 0; j < FC_HB; j++) {
           const int u = u0 + j;
           if (row >= 0 && u < nup) {
             *reinterpret_cast<double*>(myring + (size_t)u * 16 * 72) = v[j];
@@ -516,7 +519,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_ilu_factor_strips(const FacAr
         }
       }
       // ---- the finished lower part L_ik
-      for (int b = 0; b < lomax; b++) {
+      for (int b = half; b < lomax; b += 2) {
         if (row >= 0 && b < nlo) crs[(size_t)(crs0 + b) * 9 + e9] = *reinterpret_cast<const double*>(sc + b * 768 + slot8);
       }
       // ---- all compute warps have finished the step: ring visible, stage reusable, progress published
