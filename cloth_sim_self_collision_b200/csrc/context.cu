@@ -246,6 +246,10 @@ static int build_topology(Ctx* c, const int* tri, const int* quad, const int* ro
     const char* mode = getenv("CLOTHGPU_TRISOLVE");
     c->use_strips = !(mode && strcmp(mode, "levels") == 0);
     c->use_strips_fac = c->use_strips;
+    {
+      const char* tw = getenv("CLOTHGPU_TRI_WARPS");
+      c->tri_two_warps = !(tw && atoi(tw) == 1);
+    }
     const char* fs = getenv("CLOTHGPU_STRIPS");
     const int force_ns = fs ? atoi(fs) : 0;
     for (int dir = 0; dir < 2 && c->use_strips; dir++) {

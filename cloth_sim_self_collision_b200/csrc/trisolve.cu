@@ -519,8 +519,8 @@ __global__ void __launch_bounds__(256) k_pack(long long nval, const int* __restr
 }
 
 // one CTA per (strip, scene): warp 0 computes, warp 1 streams matrix chunks, warp 2 publishes, warp 3 imports
-template <bool FWD, int ND, bool DBG>
-__global__ void __launch_bounds__(128, 1) k_trisolve(const TriArgs A) {
+template <bool FWD, int ND, bool DBG, int NCW>
+__global__ void __launch_bounds__((NCW + 3) * 32, 1) k_trisolve(const TriArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + TS_NST;
@@ -549,23 +549,7 @@ __global__ void __launch_bounds__(128, 1) k_trisolve(const TriArgs A) {
   double* out = A.vec + (size_t)scene * A.np * 3;
   const double* in = (FWD && A.src) ? A.src + (size_t)scene * A.np * 3 : out;
 
-  // the strip's slice of the vector: right-hand side now, solution as the sweep proceeds
-  for (int idx = tid; idx < nown * 3; idx += blockDim.x) {
-    const int p = p0 + idx / 3, comp = idx - (idx / 3) * 3;
-    const int row = FWD ? p : A.np - 1 - p;
-    xs[(idx / 3) * 4 + comp] = in[(size_t)row * 3 + comp];
-  }
   if (tid < 8) xs[(A.xs_rows - 2) * 4 + tid] = 0.0;  // zero row (padding operands) and dummy row (idle lanes)
-  // topology-only lists of this strip, staged once so that the publisher / import loops never wait on global memory
-  {
-    const int g0 = A.strip_gh[strip], ngh = A.strip_gh[strip + 1] - g0;
-    for (int i = tid; i < nsteps * TS_ROWS; i += blockDim.x) s_rows[i] = A.ms_rows[(size_t)ms0 * TS_ROWS + i];
-    for (int i = tid; i < ngh; i += blockDim.x) {
-      s_gh[i * 3 + 0] = A.gh_row[g0 + i];
-      s_gh[i * 3 + 1] = A.gh_src[g0 + i];
-      s_gh[i * 3 + 2] = A.gh_need[g0 + i];
-    }
-  }
   if (tid == 0) {
     for (int i = 0; i < TS_NST; i++) {
       mbar_init(&full[i], 1);
@@ -573,12 +557,189 @@ __global__ void __launch_bounds__(128, 1) k_trisolve(const TriArgs A) {
     }
     flags[0] = 0;
     flags[1] = 0;
+    flags[3] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
+  // Start-up, off the loader's path: the loader warp starts streaming matrix chunks at once; the other warps load
+  // the strip's slice of the vector (right-hand side now, solution as the sweep proceeds) with eight loads in flight
+  // per thread and meet at a named barrier; the publisher / import warps then stage their own topology lists.
+  if (warp != NCW) {
+    const int nth = (NCW + 2) * 32, t2 = warp < NCW ? tid : tid - 32;
+    const int n3 = nown * 3;
+    for (int i0 = t2; i0 < n3; i0 += nth * 8) {
+      double v[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int idx = i0 + j * nth;
+        const int p = p0 + idx / 3, comp = idx - (idx / 3) * 3;
+        const int row = FWD ? p : A.np - 1 - p;
+        v[j] = idx < n3 ? in[(size_t)row * 3 + comp] : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int idx = i0 + j * nth;
+        if (idx < n3) xs[(idx / 3) * 4 + (idx - (idx / 3) * 3)] = v[j];
+      }
+    }
+    asm volatile("bar.sync 3, %0;" ::"r"(nth) : "memory");
+  }
 
-  if (warp == 0) {
+  if (NCW == 2 && warp < 2) {
+    // ---------------------------------------------------------------- two compute warps, alternating micro-steps
+    // Warp (s & 1) owns micro-step s.  While the other warp runs the dependent tail of step s-1, this warp already
+    // fetches its coefficients, waits for its ghosts and computes the products of the operands that are at least two
+    // micro-steps old ("phase A"); after the hand-off (named barrier: arrive by the finisher of s-1, sync here) it
+    // only loads the NB operands that may come from step s-1, finishes the chain, applies D^-1 and stores
+    // ("phase B").  Forward sweeps have their near operands at the end of the chain (highest columns), backward
+    // sweeps at the beginning; a step whose near operands do not fit that shape runs entirely after the hand-off.
+    const int cw = warp;
+    constexpr int NB = FWD ? (ND < 3 ? ND : 3) : (ND < 2 ? ND : 2);
+    const int g = lane / 3, r = lane - g * 3;
+    const int gq = g < TS_ROWS ? g : TS_ROWS - 1;
+    const int l0 = (gq * 3) & 31;
+    uint32_t seen = 0;
+    constexpr int NE = 3 * (ND + LAY0);
+    int myoff = 0, off[ND], ndmax = 0, nearmask = 0, fmin = 0;
+    uint32_t gneed = 0;
+    double av[ND][3], dd0 = 0.0, dd1 = 0.0, dd2 = 0.0;
+#define TS_LOAD_STEP2(MP_, VP_)                                                                  \
+    {                                                                                            \
+      const int* Mp = (MP_);                                                                     \
+      const double2* Vp = reinterpret_cast<const double2*>(VP_) + lane;                          \
+      const int4 h0 = *reinterpret_cast<const int4*>(Mp);                                        \
+      ndmax = h0.x; gneed = (uint32_t)h0.y; nearmask = h0.z; fmin = h0.w;                        \
+      myoff = Mp[4 + g] + r * 8;                                                                 \
+      {                                                                                          \
+        const int4 s0 = *reinterpret_cast<const int4*>(Mp + TS_META_HDR + gq * TS_MAXD);         \
+        const int so[4] = {s0.x, s0.y, s0.z, s0.w};                                              \
+        _Pragma("unroll") for (int d = 0; d < 4 && d < ND; d++) off[d] = so[d];                  \
+        if (ND > 4) {                                                                            \
+          const int4 s1 = *reinterpret_cast<const int4*>(Mp + TS_META_HDR + gq * TS_MAXD + 4);   \
+          const int so1[4] = {s1.x, s1.y, s1.z, s1.w};                                           \
+          _Pragma("unroll") for (int d = 4; d < ND; d++) off[d] = so1[d - 4];                    \
+        }                                                                                        \
+      }                                                                                          \
+      double cv[NE + 1];                                                                         \
+      _Pragma("unroll") for (int u = 0; u < (NE + 1) / 2; u++) {                                 \
+        const double2 c2 = Vp[u * 32];                                                           \
+        cv[2 * u] = c2.x; cv[2 * u + 1] = c2.y;                                                  \
+      }                                                                                          \
+      _Pragma("unroll") for (int d = 0; d < ND; d++) {                                           \
+        av[d][0] = cv[(LAY0 + d) * 3 + 0]; av[d][1] = cv[(LAY0 + d) * 3 + 1]; av[d][2] = cv[(LAY0 + d) * 3 + 2]; \
+      }                                                                                          \
+      if (FWD) { dd0 = cv[0]; dd1 = cv[1]; dd2 = cv[2]; }                                        \
+    }
+#define TS_PRODUCT(D_)                                                                           \
+    {                                                                                            \
+      const double2 x01 = *reinterpret_cast<const double2*>(xsc + off[D_]);                      \
+      const double x2 = *reinterpret_cast<const double*>(xsc + off[D_] + 16);                    \
+      pr[D_] = av[D_][0] * x01.x + av[D_][1] * x01.y + av[D_][2] * x2;                           \
+    }
+    const bool dbg2 = DBG && cw == 0;
+    unsigned long long t_begin2 = 0, w_a = 0, w_wait = 0, w_b = 0, w_pre = 0;
+    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    if (dbg2) t_begin2 = gtime_ns();
+    if (cw < nsteps) {
+      mbar_wait(&full[0], 0);
+      TS_LOAD_STEP2(reinterpret_cast<const int*>(stages + cw * meta_bytes),
+                    reinterpret_cast<const double*>(stages + TS_K * meta_bytes + cw * val_bytes))
+    }
+    for (int s = cw; s < nsteps; s += 2) {
+      const int sg = s / TS_K, k = s - sg * TS_K, st = sg % TS_NST;
+      const unsigned char* sb = stages + (size_t)st * stage_bytes;
+      if (gneed > seen) {
+        do { seen = ld_acquire_cta(&flags[1]); } while (seen < gneed);
+      }
+      const bool conform = ndmax <= ND && (FWD ? fmin >= ND - NB : (nearmask >> NB) == 0);
+      if (dbg2) c0 = clock64();
+      double t = *reinterpret_cast<const double*>(xsc + myoff);
+      double pr[ND];
+      // ---- phase A: everything that cannot depend on micro-step s-1
+      if (conform) {
+        if (FWD) {
+#pragma unroll
+          for (int d = 0; d < ND - NB; d++) TS_PRODUCT(d)
+#pragma unroll
+          for (int d = 0; d < ND - NB; d++) t -= pr[d];
+        } else {
+#pragma unroll
+          for (int d = NB; d < ND; d++) TS_PRODUCT(d)
+        }
+      }
+      // ---- hand-off: micro-step s-1 (other warp) has stored its rows
+      if (dbg2) c1 = clock64();
+      if (s > 0) asm volatile("bar.sync %0, 64;" ::"r"(1 + ((s - 1) & 1)) : "memory");
+      if (dbg2) c2 = clock64();
+      // ---- phase B
+      if (conform) {
+        if (FWD) {
+#pragma unroll
+          for (int d = ND - NB; d < ND; d++) TS_PRODUCT(d)
+#pragma unroll
+          for (int d = ND - NB; d < ND; d++) t -= pr[d];
+        } else {
+#pragma unroll
+          for (int d = 0; d < NB; d++) TS_PRODUCT(d)
+#pragma unroll
+          for (int d = 0; d < ND; d++) t -= pr[d];
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < ND; d++) TS_PRODUCT(d)
+#pragma unroll
+        for (int d = 0; d < ND; d++) t -= pr[d];
+        if (ndmax > ND) {  // rows with more operands than the unrolled body holds (ND == TS_MAXD only)
+          const int* Mk = reinterpret_cast<const int*>(sb + k * meta_bytes);
+          const double* Vk = reinterpret_cast<const double*>(sb + TS_K * meta_bytes + k * val_bytes);
+          for (int d = ND; d < ndmax; d++) {
+            const int o = Mk[ts_slot_index(d, gq)];
+            const double a0 = Vk[ts_val_index((LAY0 + d) * 3 + 0, lane)], a1 = Vk[ts_val_index((LAY0 + d) * 3 + 1, lane)],
+                         a2 = Vk[ts_val_index((LAY0 + d) * 3 + 2, lane)];
+            const double x0 = *reinterpret_cast<const double*>(xsc + o), x1 = *reinterpret_cast<const double*>(xsc + o + 8),
+                         x2 = *reinterpret_cast<const double*>(xsc + o + 16);
+            t -= a0 * x0 + a1 * x1 + a2 * x2;
+          }
+        }
+      }
+      if (FWD) {  // v_i = D_i^-1 t
+        const double t0 = __shfl_sync(0xffffffffu, t, l0);
+        const double t1 = __shfl_sync(0xffffffffu, t, (l0 + 1) & 31);
+        const double t2 = __shfl_sync(0xffffffffu, t, (l0 + 2) & 31);
+        t = dd0 * t0 + dd1 * t1 + dd2 * t2;
+      }
+      *reinterpret_cast<double*>(xsc + myoff) = t;
+      __syncwarp();
+      if (s + 1 < nsteps) asm volatile("bar.arrive %0, 64;" ::"r"(1 + (s & 1)) : "memory");
+      if (lane == 0) {
+        // each compute warp has its own monotone "done" word (the publisher takes the maximum): a shared word could
+        // be overwritten with an older value by the slower of the two writers
+        st_release_cta(&flags[cw == 0 ? 0 : 3], (uint32_t)(s + 1));
+        if (k == TS_K - 1) mbar_arrive(&empty[st]);
+      }
+      if (dbg2) c3 = clock64();
+      // ---- fetch the image of this warp's next micro-step (s + 2), possibly from the next stage
+      if (s + 2 < nsteps) {
+        const int s2 = s + 2, sg2 = s2 / TS_K, k2 = s2 - sg2 * TS_K;
+        if (sg2 != sg) mbar_wait(&full[sg2 % TS_NST], (uint32_t)(sg2 / TS_NST) & 1u);
+        const unsigned char* nb2 = stages + (size_t)(sg2 % TS_NST) * stage_bytes;
+        TS_LOAD_STEP2(reinterpret_cast<const int*>(nb2 + k2 * meta_bytes),
+                      reinterpret_cast<const double*>(nb2 + TS_K * meta_bytes + k2 * val_bytes))
+      }
+      if (dbg2) {
+        w_a += (unsigned long long)(c1 - c0); w_wait += (unsigned long long)(c2 - c1);
+        w_b += (unsigned long long)(c3 - c2); w_pre += (unsigned long long)(clock64() - c3);
+      }
+    }
+    if (dbg2 && lane == 0) {  // per step of THIS warp (it owns every other micro-step): phase A, hand-off wait, phase B, prefetch
+      unsigned long long* o = A.dbg + (size_t)blockIdx.x * 8;
+      o[0] = t_begin2; o[1] = gtime_ns(); o[2] = w_a; o[3] = w_wait; o[4] = w_b; o[5] = w_pre;
+      o[6] = (unsigned long long)((nsteps + 1) / 2); o[7] = (unsigned long long)strip;
+    }
+#undef TS_PRODUCT
+#undef TS_LOAD_STEP2
+  } else if (NCW == 1 && warp == 0) {
     // ---------------------------------------------------------------- compute warp
     // A single warp retires ~0.25 dependent instructions per cycle, so a micro-step costs what its longest
     // dependent chain costs -- provided the independent work is in ONE basic block for the scheduler to overlap.
@@ -704,7 +865,7 @@ __global__ void __launch_bounds__(128, 1) k_trisolve(const TriArgs A) {
       o[0] = t_begin; o[1] = gtime_ns(); o[2] = w_mbar; o[3] = w_ghost; o[4] = w_comp; o[5] = w_sig;
       o[6] = (unsigned long long)nsteps; o[7] = (unsigned long long)strip;
     }
-  } else if (warp == 1) {
+  } else if (warp == NCW) {
     // ---------------------------------------------------------------- loader warp: TMA bulk copies, TS_NST stages ahead
     if (lane == 0) {
       const unsigned char* meta = reinterpret_cast<const unsigned char*>(A.meta) + (size_t)ms0 * meta_bytes;
@@ -719,13 +880,15 @@ __global__ void __launch_bounds__(128, 1) k_trisolve(const TriArgs A) {
         bulk_g2s(dst + TS_K * meta_bytes, packed + (size_t)sg * TS_K * val_bytes, (uint32_t)(TS_K * val_bytes), &full[st]);
       }
     }
-  } else if (warp == 2) {
+  } else if (warp == NCW + 1) {
     // ---------------------------------------------------------------- publisher warp
     // copies finished rows to the result vector and to the exchange vector (consumed by the import warps of later
     // strips); the row ids of the next four micro-steps are prefetched while it waits
     unsigned long long* xch = A.xch + (size_t)scene * A.np * 3;
     const int q3 = lane / 3, qc = lane - q3 * 3;
     const bool on = lane < 30;
+    for (int i = lane; i < nsteps * TS_ROWS; i += 32) s_rows[i] = A.ms_rows[(size_t)ms0 * TS_ROWS + i];
+    __syncwarp();
     uint32_t pub = 0;
     while (pub < (uint32_t)nsteps) {
       int rows[4];
@@ -733,7 +896,7 @@ __global__ void __launch_bounds__(128, 1) k_trisolve(const TriArgs A) {
       for (int j = 0; j < 4; j++)
         rows[j] = (on && pub + j < (uint32_t)nsteps) ? s_rows[(pub + j) * TS_ROWS + q3] : -1;
       uint32_t d;
-      while ((d = ld_acquire_cta(&flags[0])) <= pub) __nanosleep(20);
+      while ((d = max(ld_acquire_cta(&flags[0]), ld_acquire_cta(&flags[3]))) <= pub) __nanosleep(20);
       d = min(d, pub + 4u);
 #pragma unroll
       for (int j = 0; j < 4; j++) {
@@ -752,8 +915,10 @@ __global__ void __launch_bounds__(128, 1) k_trisolve(const TriArgs A) {
     // ---------------------------------------------------------------- import warp
     // sliding window over the strip's ghost list (ordered by first use): every poll reads the three components of
     // up to 32 ghosts from the exchange vector; all leading ghosts that have arrived are imported at once
-    const int ngh = A.strip_gh[strip + 1] - A.strip_gh[strip];
+    const int g0 = A.strip_gh[strip], ngh = A.strip_gh[strip + 1] - g0;
     const unsigned long long* xch = A.xch + (size_t)scene * A.np * 3;
+    for (int i = lane; i < ngh; i += 32) s_gh[i * 3] = A.gh_row[g0 + i];  // only the row ids are needed here
+    __syncwarp();
     int w0 = 0;
     while (w0 < ngh) {
       const int gi = w0 + lane;
@@ -791,12 +956,18 @@ static int pack_plan(Ctx* c, TriPlan& P) {
 
 template <bool FWD, int ND>
 static int launch_tri_nd(Ctx* c, const TriPlan& P, const TriArgs& A, int grid) {
-  if (A.dbg) {
-    CG_CUDA(cudaFuncSetAttribute(k_trisolve<FWD, ND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
-    k_trisolve<FWD, ND, true><<<grid, 128, P.smem_bytes, KS(c, FWD ? "k_trisolve_fwd" : "k_trisolve_bwd")>>>(A);
+  if (A.dbg && c->tri_two_warps) {
+    CG_CUDA(cudaFuncSetAttribute(k_trisolve<FWD, ND, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
+    k_trisolve<FWD, ND, true, 2><<<grid, 160, P.smem_bytes, KS(c, FWD ? "k_trisolve_fwd" : "k_trisolve_bwd")>>>(A);
+  } else if (A.dbg) {
+    CG_CUDA(cudaFuncSetAttribute(k_trisolve<FWD, ND, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
+    k_trisolve<FWD, ND, true, 1><<<grid, 128, P.smem_bytes, KS(c, FWD ? "k_trisolve_fwd" : "k_trisolve_bwd")>>>(A);
+  } else if (c->tri_two_warps) {
+    CG_CUDA(cudaFuncSetAttribute(k_trisolve<FWD, ND, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
+    k_trisolve<FWD, ND, false, 2><<<grid, 160, P.smem_bytes, KS(c, FWD ? "k_trisolve_fwd" : "k_trisolve_bwd")>>>(A);
   } else {
-    CG_CUDA(cudaFuncSetAttribute(k_trisolve<FWD, ND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
-    k_trisolve<FWD, ND, false><<<grid, 128, P.smem_bytes, KS(c, FWD ? "k_trisolve_fwd" : "k_trisolve_bwd")>>>(A);
+    CG_CUDA(cudaFuncSetAttribute(k_trisolve<FWD, ND, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
+    k_trisolve<FWD, ND, false, 1><<<grid, 128, P.smem_bytes, KS(c, FWD ? "k_trisolve_fwd" : "k_trisolve_bwd")>>>(A);
   }
   CG_LAUNCH_CHECK(c);
   return CLOTHGPU_OK;
