@@ -248,7 +248,7 @@ static int build_topology(Ctx* c, const int* tri, const int* quad, const int* ro
     c->use_strips_fac = c->use_strips;
     {
       const char* tw = getenv("CLOTHGPU_TRI_WARPS");
-      c->tri_two_warps = !(tw && atoi(tw) == 1);
+      c->tri_two_warps = tw && atoi(tw) == 2;
     }
     const char* fs = getenv("CLOTHGPU_STRIPS");
     const int force_ns = fs ? atoi(fs) : 0;

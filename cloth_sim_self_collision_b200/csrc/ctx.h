@@ -138,7 +138,7 @@ struct Ctx {
   TriPlan plan_f, plan_b;
   FacPlan plan_fac;
   unsigned long long* tri_xch = nullptr;  // exchange vector of the triangular sweeps (trisolve.cu)
-  bool tri_two_warps = true;  // two alternating compute warps per strip (CLOTHGPU_TRI_WARPS=1 selects one)
+  bool tri_two_warps = false;  // two alternating compute warps per strip (CLOTHGPU_TRI_WARPS=2; measured: no gain)
   int pcg_expect = 0;  // iterations the previous PCG solve needed (+1): when to start polling the convergence flag
   bool ilu_packed_valid = false;  // plan_*.packed mirrors iluDia / iluCrs
   bool tri_debug = false;         // clothgpu_debug_trisolve: per-CTA wait / compute cycle counters
