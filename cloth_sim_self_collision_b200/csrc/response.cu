@@ -18,6 +18,9 @@
 // reduced sequentially, so the sums are bit-identical too.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "ctx.h"
 #include "dev_math.cuh"
 
@@ -226,6 +229,48 @@ __global__ void __launch_bounds__(1024) k_imp_run(int ccd, int np, long long cap
   }
 }
 
+// Data-flow variant of the same schedule (the default): no levels, no barriers.  One CTA per scene; thread t owns the
+// elements t, t + T, ... in ascending order and starts an element as soon as the (at most four) predecessors on its
+// vertices have finished (one "done" byte per element in shared memory).  The smallest unfinished element is always
+// runnable and its owner is working on it, so the loop cannot dead-lock; independent dependency chains overlap
+// instead of meeting at a barrier per level, and geometry (positions, indices) is fetched before the wait.
+// Consecutive elements (which usually share their first vertex) are spread over different warps.
+__global__ void __launch_bounds__(512) k_imp_flow(int ccd, int np, long long cap_elem, const int* __restrict__ elems_all,
+                                                    const int* __restrict__ pred_all, const double* __restrict__ xyz_all,
+                                                    double* uvw_all, double delta, double stiffness, double dt,
+                                                    double mass, const int* __restrict__ cnt) {
+  extern __shared__ unsigned char done_sm[];
+  const int s = blockIdx.x;
+  const int* c = cnt + s * NCNT;
+  if (!c[CNT_ACTIVE]) return;
+  const int ne = c[CNT_ELEM];
+  if (ne == 0) return;
+  const int* elems = elems_all + (size_t)s * cap_elem * 5;
+  const int4* pred = reinterpret_cast<const int4*>(pred_all + (size_t)s * cap_elem * 4);
+  const double* xyz = xyz_all + (size_t)s * np * 3;
+  double* uvw = uvw_all + (size_t)s * np * 3;
+  volatile unsigned char* done = done_sm;
+  for (int k = threadIdx.x; k < ne; k += blockDim.x) done_sm[k] = 0;
+  __syncthreads();
+  // thread <-> element: element k of a round goes to warp (k % 16), lane (k / 16)
+  const int slot = (threadIdx.x & 31) * 16 + (threadIdx.x >> 5);
+  for (int k = slot; k < ne; k += 512) {
+    const int4 p = pred[k];
+    int n[5];
+#pragma unroll
+    for (int a = 0; a < 5; a++) n[a] = elems[(size_t)k * 5 + a];
+    if (p.x >= 0) while (!done[p.x]) { }
+    if (p.y >= 0) while (!done[p.y]) { }
+    if (p.z >= 0) while (!done[p.z]) { }
+    if (p.w >= 0) while (!done[p.w]) { }
+    __threadfence_block();
+    if (ccd) impulse_ccd_one(n, xyz, uvw, delta, dt, mass);
+    else impulse_prx_one(n, xyz, uvw, delta, stiffness, dt, mass);
+    __threadfence_block();
+    done[k] = 1;
+  }
+}
+
 int launch_impulse(Ctx* c, const double* xyz, double* uvw, double delta, double stiffness, double dt, double mass, int ccd) {
   // element counts are on the host already (the reference's loop control needs them)
   for (int s = 0; s < c->B; s++) {
@@ -249,8 +294,20 @@ int launch_impulse(Ctx* c, const double* xyz, double* uvw, double delta, double 
     k_imp_pred<<<div_up(n4, 256), 256, 0, KS(c, "k_imp_pred")>>>(n4, keys2, c->sort_vals2, c->imp_pred + (size_t)s * c->cap_elem * 4);
     CG_LAUNCH_CHECK(c);
   }
-  k_imp_run<<<c->B, 1024, 0, KS(c, "k_imp_run")>>>(ccd, c->np, c->cap_elem, c->elems, c->imp_pred, c->imp_level, c->imp_order,
-                                          c->imp_lptr, xyz, uvw, delta, stiffness, dt, mass, c->cnt);
+  int ne_max = 0;
+  for (int s = 0; s < c->B; s++)
+    if (c->h_cnt[s * NCNT + CNT_ACTIVE]) ne_max = std::max(ne_max, c->h_cnt[s * NCNT + CNT_ELEM]);
+  if (ne_max == 0) return CLOTHGPU_OK;
+  static const bool use_levels = getenv("CLOTHGPU_IMPULSE") && strcmp(getenv("CLOTHGPU_IMPULSE"), "levels") == 0;
+  if (!use_levels && ne_max <= 200 * 1024) {
+    const int smem = (ne_max + 127) / 128 * 128;
+    CG_CUDA(cudaFuncSetAttribute(k_imp_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(smem, 48 * 1024)));
+    k_imp_flow<<<c->B, 512, smem, KS(c, "k_imp_flow")>>>(ccd, c->np, c->cap_elem, c->elems, c->imp_pred, xyz, uvw, delta,
+                                                  stiffness, dt, mass, c->cnt);
+  } else {
+    k_imp_run<<<c->B, 1024, 0, KS(c, "k_imp_run")>>>(ccd, c->np, c->cap_elem, c->elems, c->imp_pred, c->imp_level, c->imp_order,
+                                            c->imp_lptr, xyz, uvw, delta, stiffness, dt, mass, c->cnt);
+  }
   CG_LAUNCH_CHECK(c);
   return CLOTHGPU_OK;
 }
