@@ -38,23 +38,52 @@ __device__ __forceinline__ void add3s(double* v, int i, V3 n, double a) {
   v[i * 3 + 2] += n.z * a;
 }
 
-// one element of SelfCollisionImpulse_Proximity, self_collision_cloth.cpp:31-110
-__device__ void impulse_prx_one(const int* n, const double* xyz, double* uvw, double delta, double stiffness, double dt,
-                                double mass) {
+// one element of SelfCollisionImpulse_Proximity, self_collision_cloth.cpp:31-110, in two parts: everything that only
+// depends on the positions (closest-point weights, normal, penetration depth) and the velocity update.  The data-flow
+// kernel evaluates the first part while it waits for the element's predecessors.
+struct PrxGeom {
+  bool ok, fv;
+  double wa, wb, wc;  // FV: w0, w1, w2 ; EE: w01, w23 (wc unused)
+  V3 norm;
+  double p_depth;
+};
+__device__ __forceinline__ void impulse_prx_geom(const int* n, const double* xyz, double delta, PrxGeom& G) {
   const V3 p0 = ld3(xyz, n[0]), p1 = ld3(xyz, n[1]), p2 = ld3(xyz, n[2]), p3 = ld3(xyz, n[3]);
-  const V3 v0 = ld3(uvw, n[0]), v1 = ld3(uvw, n[1]), v2 = ld3(uvw, n[2]), v3v = ld3(uvw, n[3]);
-  if (n[4]) {
+  G.ok = false;
+  G.fv = n[4] != 0;
+  if (G.fv) {
     double w0, w1;
-    {
-      const double dist = dist_face_vertex(p0, p1, p2, p3, w0, w1);
-      if (w0 < 0 || w0 > 1) return;
-      if (w1 < 0 || w1 > 1) return;
-      if (dist > delta) return;
-    }
+    const double dist = dist_face_vertex(p0, p1, p2, p3, w0, w1);
+    if (w0 < 0 || w0 > 1) return;
+    if (w1 < 0 || w1 > 1) return;
+    if (dist > delta) return;
     const double w2 = 1.0 - w0 - w1;
     const V3 pc = (w0 * p0 + w1 * p1) + w2 * p2;
-    const V3 norm = normalized(p3 - pc);
-    const double p_depth = delta - dot(p3 - pc, norm);
+    G.norm = normalized(p3 - pc);
+    G.p_depth = delta - dot(p3 - pc, G.norm);
+    G.wa = w0; G.wb = w1; G.wc = w2;
+  } else {
+    double w01, w23;
+    const double dist = dist_edge_edge(p0, p1, p2, p3, w01, w23);
+    if (w01 < 0 || w01 > 1) return;
+    if (w23 < 0 || w23 > 1) return;
+    if (dist > delta) return;
+    const V3 c01 = (1 - w01) * p0 + w01 * p1;
+    const V3 c23 = (1 - w23) * p2 + w23 * p3;
+    G.norm = normalized(c23 - c01);
+    G.p_depth = delta - length(c23 - c01);
+    G.wa = w01; G.wb = w23; G.wc = 0.0;
+  }
+  G.ok = true;
+}
+__device__ __forceinline__ void impulse_prx_apply(const int* n, const PrxGeom& G, double* uvw, double stiffness, double dt,
+                                                  double mass) {
+  if (!G.ok) return;
+  const V3 v0 = ld3(uvw, n[0]), v1 = ld3(uvw, n[1]), v2 = ld3(uvw, n[2]), v3v = ld3(uvw, n[3]);
+  const V3 norm = G.norm;
+  const double p_depth = G.p_depth;
+  if (G.fv) {
+    const double w0 = G.wa, w1 = G.wb, w2 = G.wc;
     const double rel_v = dot(((v3v - w0 * v0) - w1 * v1) - w2 * v2, norm);
     if (rel_v > 0.1 * p_depth / dt) return;
     const double imp_el = dt * stiffness * p_depth;
@@ -68,17 +97,7 @@ __device__ void impulse_prx_one(const int* n, const double* xyz, double* uvw, do
     add3(uvw, n[2], -norm, imp_mod, w2);
     add3s(uvw, n[3], norm, imp_mod);
   } else {
-    double w01, w23;
-    {
-      const double dist = dist_edge_edge(p0, p1, p2, p3, w01, w23);
-      if (w01 < 0 || w01 > 1) return;
-      if (w23 < 0 || w23 > 1) return;
-      if (dist > delta) return;
-    }
-    const V3 c01 = (1 - w01) * p0 + w01 * p1;
-    const V3 c23 = (1 - w23) * p2 + w23 * p3;
-    const V3 norm = normalized(c23 - c01);
-    const double p_depth = delta - length(c23 - c01);
+    const double w01 = G.wa, w23 = G.wb;
     const double rel_v = dot((((1 - w23) * v2 + w23 * v3v) - (1 - w01) * v0) - w01 * v1, norm);
     if (rel_v > 0.1 * p_depth / dt) return;
     const double imp_el = dt * stiffness * p_depth;
@@ -93,11 +112,23 @@ __device__ void impulse_prx_one(const int* n, const double* xyz, double* uvw, do
     add3(uvw, n[3], norm, imp_mod, w23);
   }
 }
+__device__ void impulse_prx_one(const int* n, const double* xyz, double* uvw, double delta, double stiffness, double dt,
+                                double mass) {
+  PrxGeom G;
+  impulse_prx_geom(n, xyz, delta, G);
+  impulse_prx_apply(n, G, uvw, stiffness, dt, mass);
+}
 
 // one element of SelfCollisionImpulse_CCD, self_collision_cloth.cpp:127-210.  Reference quirk (:141): the impact
 // time is re-solved with the UN-scaled velocity (end points p + v, not p + dt*v).
+__device__ void impulse_ccd_apply(const int* n, V3 p0, V3 p1, V3 p2, V3 p3, double* uvw, double delta, double dt,
+                                  double mass);
 __device__ void impulse_ccd_one(const int* n, const double* xyz, double* uvw, double delta, double dt, double mass) {
-  const V3 p0 = ld3(xyz, n[0]), p1 = ld3(xyz, n[1]), p2 = ld3(xyz, n[2]), p3 = ld3(xyz, n[3]);
+  impulse_ccd_apply(n, ld3(xyz, n[0]), ld3(xyz, n[1]), ld3(xyz, n[2]), ld3(xyz, n[3]), uvw, delta, dt, mass);
+}
+// positions are passed in: the data-flow kernel loads them while it waits for the element's predecessors
+__device__ void impulse_ccd_apply(const int* n, V3 p0, V3 p1, V3 p2, V3 p3, double* uvw, double delta, double dt,
+                                  double mass) {
   const V3 v0 = ld3(uvw, n[0]), v1 = ld3(uvw, n[1]), v2 = ld3(uvw, n[2]), v3v = ld3(uvw, n[3]);
   const double t = coplanar_time(p0, p1, p2, p3, p0 + v0, p1 + v1, p2 + v2, p3 + v3v);
   if (t < 0 || t > 1) return;
@@ -259,13 +290,17 @@ __global__ void __launch_bounds__(512) k_imp_flow(int ccd, int np, long long cap
     int n[5];
 #pragma unroll
     for (int a = 0; a < 5; a++) n[a] = elems[(size_t)k * 5 + a];
+    PrxGeom G;
+    V3 q0 = v3(0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
+    if (!ccd) impulse_prx_geom(n, xyz, delta, G);  // velocity independent: in the shadow of the wait
+    else { q0 = ld3(xyz, n[0]); q1 = ld3(xyz, n[1]); q2 = ld3(xyz, n[2]); q3 = ld3(xyz, n[3]); }
     if (p.x >= 0) while (!done[p.x]) { }
     if (p.y >= 0) while (!done[p.y]) { }
     if (p.z >= 0) while (!done[p.z]) { }
     if (p.w >= 0) while (!done[p.w]) { }
     __threadfence_block();
-    if (ccd) impulse_ccd_one(n, xyz, uvw, delta, dt, mass);
-    else impulse_prx_one(n, xyz, uvw, delta, stiffness, dt, mass);
+    if (ccd) impulse_ccd_apply(n, q0, q1, q2, q3, uvw, delta, dt, mass);
+    else impulse_prx_apply(n, G, uvw, stiffness, dt, mass);
     __threadfence_block();
     done[k] = 1;
   }
