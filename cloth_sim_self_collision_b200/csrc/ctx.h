@@ -57,7 +57,7 @@ enum { FC_H = 8, FC_NST = 3, FC_NIB = 3, FC_META_HDR = 48, FC_SMEM_HDR = 256, FC
        FC_THREADS = (8 + 3) * 32 };
 struct FacPlanHost {
   int ns = 0, R = 0, nms = 0, H = 0, gmaxB = 0, gmaxU = 0, gmaxOps = 0, max_imp = 0, meta_stride = 0, row_stride = 0;
-  int max_steps = 0, gmaxLo = 0, gT = 0, kg_stride = 0;
+  int max_steps = 0, gmaxLo = 0, gT = 0, kg_stride = 0, imp_bytes = 0;
   std::vector<int> strip_ms, ms_rows, meta, pk_src, imp_ptr, imp_row, imp_src, imp_need;
 };
 struct FacPlan {

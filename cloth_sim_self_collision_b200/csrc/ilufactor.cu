@@ -165,6 +165,25 @@ int build_facplan_host(int np, const int* rowptr, const int* colidx, const int* 
       F.max_imp = std::max(F.max_imp, nimp);
     }
   }
+  // operand offsets become absolute byte offsets into the CTA's shared memory (the layout is a function of the plan):
+  // ring operands sit at FC_SMEM_HDR + offset, imported ones in import buffer (local step % FC_NIB)
+  {
+    const int imp_bytes = round_up(std::max(F.max_imp, 1) * urow, 128);
+    F.imp_bytes = imp_bytes;
+    for (int k = 0; k < F.ns; k++)
+      for (int m = F.strip_ms[k]; m < F.strip_ms[k + 1]; m++) {
+        int* M = &F.meta[(size_t)m * F.meta_stride];
+        const int ibuf = (m - F.strip_ms[k]) % FC_NIB;
+        for (int kg = 0; kg < gLo; kg++) {
+          int* K = &M[FC_META_HDR + kg * F.kg_stride];
+          for (int t = 0; t < gT; t++)
+            for (int q = 0; q < TS_ROWS; q++) {
+              int& e = K[12 + (t * TS_ROWS + q) * 2];
+              e = e >= 0 ? FC_SMEM_HDR + e : FC_SMEM_HDR + ring_bytes + 128 + ibuf * imp_bytes + (-1 - e);
+            }
+        }
+      }
+  }
   F.max_steps = T.max_steps;
   if (F.pk_src.size() > (size_t)0x7fffffff) { set_error("factor plan exceeds 2^31 packed values"); return CLOTHGPU_ERR_CAPACITY; }
   return CLOTHGPU_OK;
@@ -203,7 +222,7 @@ int verify_facplan_host(int np, const int* rowptr, const int* colidx, const int*
             const int* K = &M[FC_META_HDR + kg * F.kg_stride];
             if (K[q] != gB * blk) PLAN_FAIL("padding k-group of an unused lane");
             for (int t = 0; t < F.gT; t++)
-              if (K[12 + (t * TS_ROWS + q) * 2] != ring_bytes || K[12 + (t * TS_ROWS + q) * 2 + 1] != K[q]) PLAN_FAIL("padding update of an unused lane");
+              if (K[12 + (t * TS_ROWS + q) * 2] != FC_SMEM_HDR + ring_bytes || K[12 + (t * TS_ROWS + q) * 2 + 1] != K[q]) PLAN_FAIL("padding update of an unused lane");
           }
           continue;
         }
@@ -235,18 +254,19 @@ int verify_facplan_host(int np, const int* rowptr, const int* colidx, const int*
             const int* E = &K[12 + (t * TS_ROWS + q) * 2];
             if (E[1] != (ij < 0 ? gB - 1 : ij - rowptr[row]) * blk) PLAN_FAIL("op ij");
             const int u = kj - dia[kr], mk = ms_of_row[kr];
-            if (E[0] >= 0) {
+            const int imp_base = FC_SMEM_HDR + ring_bytes + 128;
+            if (E[0] < imp_base) {
               if (kr / T.R != k || mk >= m || m - mk > FC_H - 1) PLAN_FAIL("ring operand out of reach");
-              if (E[0] != (((((mk - F.strip_ms[k]) % FC_H) * F.gmaxU + u) * 16 + q_of_row[kr]) * 9) * 8) PLAN_FAIL("ring operand offset");
+              if (E[0] - FC_SMEM_HDR != (((((mk - F.strip_ms[k]) % FC_H) * F.gmaxU + u) * 16 + q_of_row[kr]) * 9) * 8) PLAN_FAIL("ring operand offset");
             } else {
-              const int off = -1 - E[0], e = off / urow;
-              if (e >= nimp || F.imp_row[i0 + e] != kr || off % urow != u * 72) PLAN_FAIL("import operand");
+              const int off = E[0] - imp_base - ((m - F.strip_ms[k]) % FC_NIB) * F.imp_bytes, e = off / urow;
+              if (off < 0 || e >= nimp || F.imp_row[i0 + e] != kr || off % urow != u * 72) PLAN_FAIL("import operand");
             }
             t++;
           }
           for (; t < F.gT; t++) {
             const int* E = &K[12 + (t * TS_ROWS + q) * 2];
-            if (E[0] != ring_bytes || E[1] != gB * blk) PLAN_FAIL("padding update");
+            if (E[0] != FC_SMEM_HDR + ring_bytes || E[1] != gB * blk) PLAN_FAIL("padding update");
           }
         }
         for (int j = rowptr[row]; j < rowptr[row + 1]; j++) slot[colidx[j]] = -1;
@@ -429,7 +449,6 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_ilu_factor_strips(const FacAr
       if (dbg) c2 = clock64();
       const int* M = reinterpret_cast<const int*>(stages + (size_t)st * stage_bytes);
       unsigned char* sc = stages + (size_t)st * stage_bytes + meta_bytes;  // this step's row blocks
-      const unsigned char* ib = imp + (size_t)(m % FC_NIB) * imp_bytes;
       const int nops = M[0], nupmax = M[2], lomax = M[3];
       const int row = act ? M[4 + gm] : -1;
       // ---- updates A_ij -= A_ik U'_kj in the reference's order.  Lane (r, c) owns entry (r, c) of every block of
@@ -449,7 +468,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_ilu_factor_strips(const FacAr
 #pragma unroll
           for (int j = 0; j < FC_HB; j++) {
             const int2 e = *reinterpret_cast<const int2*>(K + 12 + ((t0 + j) * TS_ROWS + gm) * 2);
-            const unsigned char* pb = (e.x >= 0 ? ring + e.x : ib + (-1 - e.x)) + cc * 8;  // U'_kj[0..2][c]
+            const unsigned char* pb = smem + e.x + cc * 8;  // U'_kj[0..2][c]: absolute offset, ring or import buffer
             pt[j] = sc + e.y + slot8;
             b0[j] = *reinterpret_cast<const double*>(pb);
             b1[j] = *reinterpret_cast<const double*>(pb + 24);
