@@ -55,10 +55,12 @@ int run_resolve(Ctx* c, const clothgpu_params& p, int* applied, int* stats, bool
   // CCD impulse passes, :398-425
   int nactive = B;
   for (int itr = 0; itr < 5 && nactive > 0; itr++) {
+    // from the second pass on only the velocities of the vertices the impulses touched have changed: incremental
+    const bool inc = c->incremental_ccd && itr > 0;
     phase_begin(c);
-    CG_CHECK(launch_refit(c, x, v, dt, 1));
+    CG_CHECK(launch_refit(c, x, v, dt, 1, inc));
     phase_end(c, 3);
-    CG_CHECK(run_contacts(c, x, v, dt, delta, 1, n.data()));
+    CG_CHECK(run_contacts(c, x, v, dt, delta, 1, n.data(), false, inc));
     nactive = 0;
     for (int s = 0; s < B; s++) {
       if (!act[s]) continue;
@@ -78,9 +80,9 @@ int run_resolve(Ctx* c, const clothgpu_params& p, int* applied, int* stats, bool
     CG_CHECK(launch_riz_reset(c));
     for (int itr = 0; itr < 100 && nactive > 0; itr++) {
       phase_begin(c);
-      CG_CHECK(launch_refit(c, x, v, dt, 1));
+      CG_CHECK(launch_refit(c, x, v, dt, 1, c->incremental_ccd));
       phase_end(c, 3);
-      CG_CHECK(run_contacts(c, x, v, dt, delta, 1, n.data()));
+      CG_CHECK(run_contacts(c, x, v, dt, delta, 1, n.data(), false, c->incremental_ccd));
       nactive = 0;
       for (int s = 0; s < B; s++) {
         if (!act[s]) continue;

@@ -42,7 +42,8 @@ __device__ __forceinline__ Box ld_box_cg(const double* boxes, int i) {  // bypas
 __global__ void __launch_bounds__(256) k_refit(int nnode, int np, const int* __restrict__ nodes,
                                                 const int* __restrict__ tri, const double* __restrict__ xyz,
                                                 const double* __restrict__ uvw, double par, int mode, double* boxes,
-                                                int* flags, const int* __restrict__ cnt) {
+                                                int* flags, const int* __restrict__ cnt,
+                                                const int* __restrict__ vdirty, int* ndirty) {
   const int s = blockIdx.y;
   if (!cnt[s * NCNT + CNT_ACTIVE]) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -70,11 +71,18 @@ __global__ void __launch_bounds__(256) k_refit(int nnode, int np, const int* __r
     box_add(b, v3(x[n2 * 3] + par * v[n2 * 3], x[n2 * 3 + 1] + par * v[n2 * 3 + 1], x[n2 * 3 + 2] + par * v[n2 * 3 + 2]), eps);
   }
   st_box(bx, i, b);
+  // incremental detection: a node is dirty when a vertex of a triangle below it changed its velocity
+  int* nd = ndirty ? ndirty + (size_t)s * nnode : nullptr;
+  if (nd) {
+    const int* vd = vdirty + (size_t)s * np;
+    nd[i] = vd[n0] | vd[n1] | vd[n2];
+  }
   int cur = nodes[i * 3 + 0];
   while (cur >= 0) {
     __threadfence();
     if (atomicAdd(&fl[cur], 1) == 0) return;  // the sibling subtree is not finished: its last thread continues
     __threadfence();
+    if (nd) nd[cur] = __ldcg(nd + nodes[cur * 3 + 1]) | __ldcg(nd + nodes[cur * 3 + 2]);
     Box a = ld_box_cg(bx, nodes[cur * 3 + 1]);
     const Box o = ld_box_cg(bx, nodes[cur * 3 + 2]);
 #pragma unroll
@@ -91,12 +99,16 @@ __global__ void __launch_bounds__(256) k_refit(int nnode, int np, const int* __r
 __global__ void k_trav_reset(int* cnt) {
   int* c = cnt + blockIdx.x * NCNT;
   for (int k = threadIdx.x; k < NCNT - CNT_FRONT; k += blockDim.x) c[CNT_FRONT + k] = 0;
-  if (threadIdx.x == 0) { c[CNT_LEAF] = 0; c[CNT_RAW] = 0; c[CNT_ELEM] = 0; c[CNT_OVERFLOW] = 0; c[CNT_CAND] = 0; }
+  if (threadIdx.x == 0) {
+    c[CNT_RAWPREV] = c[CNT_RAW];  // raw elements of the previous detection (now in the other raw buffer)
+    c[CNT_LEAF] = 0; c[CNT_RAW] = 0; c[CNT_ELEM] = 0; c[CNT_OVERFLOW] = 0; c[CNT_CAND] = 0;
+  }
 }
 
 // the self() calls: every internal node starts one pair recursion on its two children
 __global__ void k_trav_init(int ninternal, const int* __restrict__ internal_list, const int* __restrict__ nodes,
-                            const uint32_t* __restrict__ pre, PairEnt* front, long long cap, int* cnt) {
+                            const uint32_t* __restrict__ pre, PairEnt* front, long long cap, int* cnt,
+                            int nnode, const int* __restrict__ ndirty) {
   const int s = blockIdx.y;
   if (!cnt[s * NCNT + CNT_ACTIVE]) return;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -106,6 +118,7 @@ __global__ void k_trav_init(int ninternal, const int* __restrict__ internal_list
   PairEnt e;
   e.i0 = nodes[n * 3 + 1];
   e.i1 = nodes[n * 3 + 2];
+  if (ndirty && !ndirty[(size_t)s * nnode + n]) e.i0 = -1;  // nothing below this node changed: a dead entry
   e.pre = pre[n];
   e.depth = 0;
   e.path_hi = 0;
@@ -140,10 +153,12 @@ __device__ __forceinline__ void path_push(PairEnt& e, unsigned code) {
 __global__ void __launch_bounds__(256) k_trav_step(int d, int nnode, const int* __restrict__ nodes,
                                                     const double* __restrict__ boxes, const PairEnt* __restrict__ fin,
                                                     PairEnt* __restrict__ fout, long long cap_front,
-                                                    PairEnt* __restrict__ leaf, long long cap_leaf, int* cnt) {
+                                                    PairEnt* __restrict__ leaf, long long cap_leaf, int* cnt,
+                                                    const int* __restrict__ ndirty) {
   const int s = blockIdx.y;
   int* c = cnt + s * NCNT;
   if (!c[CNT_ACTIVE]) return;
+  const int* nd = ndirty ? ndirty + (size_t)s * nnode : nullptr;
   const int nin = min(c[CNT_FRONT + d], (int)min(cap_front, (long long)INT_MAX));
   if (nin == 0) return;
   const double* bx = boxes + (size_t)s * nnode * 6;
@@ -160,8 +175,10 @@ __global__ void __launch_bounds__(256) k_trav_step(int d, int nnode, const int* 
     bool l0 = false, l1 = false;
     if (idx < nin) {
       e = in[idx];
-      const Box b0 = ld_box(bx, e.i0), b1 = ld_box(bx, e.i1);
-      if (box_intersect(b0, b1)) {
+      // incremental detection: only pairs with a changed triangle on either side can change the contact set
+      const bool live = e.i0 >= 0 && (!nd || nd[e.i0] || nd[e.i1]);
+      const Box b0 = ld_box(bx, live ? e.i0 : 0), b1 = ld_box(bx, live ? e.i1 : 0);
+      if (live && box_intersect(b0, b1)) {
         c00 = nodes[e.i0 * 3 + 1]; c01 = nodes[e.i0 * 3 + 2];
         c10 = nodes[e.i1 * 3 + 1]; c11 = nodes[e.i1 * 3 + 2];
         l0 = c01 == -1; l1 = c11 == -1;
@@ -391,6 +408,42 @@ __global__ void __launch_bounds__(128) k_narrow(int ccd, int nnode, int np, cons
   }
 }
 
+// Incremental detection (second and later CCD passes of a step: positions fixed, only velocities change): a contact
+// element depends on its four vertices only, so the elements of the previous pass whose vertices all kept their
+// velocity are carried over; everything else is re-tested by the dirty-restricted traversal.  Carried-over and
+// re-found elements may coincide (same key, same DFS rank): the canonical set removes the duplicates.
+__global__ void k_mark_dirty(int np, const double* __restrict__ uvw, double* __restrict__ snap, int* __restrict__ vdirty,
+                             const int* __restrict__ cnt) {
+  const int s = blockIdx.y;
+  if (!cnt[s * NCNT + CNT_ACTIVE]) return;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= np) return;
+  const size_t o = ((size_t)s * np + v) * 3;
+  int d = 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const double a = uvw[o + k];
+    d |= __double_as_longlong(a) != __double_as_longlong(snap[o + k]);
+    snap[o + k] = a;
+  }
+  vdirty[(size_t)s * np + v] = d;
+}
+__global__ void k_keep_clean(int np, const RawElem* __restrict__ prev, long long cap_raw, RawElem* __restrict__ raw,
+                             const int* __restrict__ vdirty, int* cnt) {
+  const int s = blockIdx.y;
+  int* c = cnt + s * NCNT;
+  if (!c[CNT_ACTIVE]) return;
+  const int n = min((long long)c[CNT_RAWPREV], cap_raw);
+  const int* vd = vdirty + (size_t)s * np;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const RawElem r = prev[(size_t)s * cap_raw + i];
+    if (vd[r.n[0]] | vd[r.n[1]] | vd[r.n[2]] | vd[r.n[3]]) continue;
+    const int k = atomicAdd(&c[CNT_RAW], 1);
+    if (k >= cap_raw) { atomicOr(&c[CNT_OVERFLOW], 4); continue; }
+    raw[(size_t)s * cap_raw + k] = r;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ canonical set
 struct RawLess {
   __device__ __forceinline__ bool operator()(const RawElem& a, const RawElem& b) const {
@@ -434,20 +487,39 @@ __global__ void k_compact_elems(int n, const RawElem* __restrict__ raw, const in
 
 __global__ void k_set_active(int* cnt, int v) { cnt[blockIdx.x * NCNT + CNT_ACTIVE] = v; }
 
-int launch_refit(Ctx* c, const double* xyz, const double* uvw, double par, int mode) {
+int launch_refit(Ctx* c, const double* xyz, const double* uvw, double par, int mode, bool incremental) {
+  // mode 1 keeps a snapshot of the velocities the boxes were built from; an incremental refit first marks the
+  // vertices whose velocity changed since then and propagates "dirty" up the tree together with the boxes
+  if (mode == 1 && incremental) {
+    dim3 gd(div_up(c->np, 256), c->B);
+    k_mark_dirty<<<gd, 256, 0, KS(c, "k_mark_dirty")>>>(c->np, uvw, c->uvw_snap, c->vdirty, c->cnt);
+    CG_LAUNCH_CHECK(c);
+  } else if (mode == 1) {
+    CG_CUDA(cudaMemcpyAsync(c->uvw_snap, uvw, sizeof(double) * (size_t)c->B * c->ndof, cudaMemcpyDeviceToDevice, c->stream));
+  }
   CG_CUDA(cudaMemsetAsync(c->refit_flag, 0, sizeof(int) * (size_t)c->B * c->nnode, c->stream));
   dim3 g(div_up(c->nnode, 256), c->B);
-  k_refit<<<g, 256, 0, KS(c, "k_refit")>>>(c->nnode, c->np, c->nodes, c->tri, xyz, uvw, par, mode, c->boxes, c->refit_flag, c->cnt);
+  const bool inc = mode == 1 && incremental;
+  k_refit<<<g, 256, 0, KS(c, "k_refit")>>>(c->nnode, c->np, c->nodes, c->tri, xyz, uvw, par, mode, c->boxes, c->refit_flag, c->cnt,
+                                   inc ? c->vdirty : nullptr, inc ? c->ndirty : nullptr);
   CG_LAUNCH_CHECK(c);
   return CLOTHGPU_OK;
 }
 
-static int traverse_and_test(Ctx* c, const double* xyz, const double* uvw, double dt, double delta, int ccd) {
+static int traverse_and_test(Ctx* c, const double* xyz, const double* uvw, double dt, double delta, int ccd,
+                             bool incremental = false) {
+  const int* nd = incremental ? c->ndirty : nullptr;
   k_trav_reset<<<c->B, 64, 0, KS(c, "k_trav_reset")>>>(c->cnt);
   CG_LAUNCH_CHECK(c);
+  if (incremental) {  // carry over the previous pass's elements whose vertices did not change
+    dim3 gk(148, c->B);
+    k_keep_clean<<<gk, 256, 0, KS(c, "k_keep_clean")>>>(c->np, c->raw_sorted, c->cap_raw, c->raw, c->vdirty, c->cnt);
+    CG_LAUNCH_CHECK(c);
+  }
   {
     dim3 g(div_up(c->ninternal, 256), c->B);
-    k_trav_init<<<g, 256, 0, KS(c, "k_trav_init")>>>(c->ninternal, c->internal_list, c->nodes, c->pre, c->frontA, c->cap_front, c->cnt);
+    k_trav_init<<<g, 256, 0, KS(c, "k_trav_init")>>>(c->ninternal, c->internal_list, c->nodes, c->pre, c->frontA, c->cap_front, c->cnt,
+                                             c->nnode, nd);
     CG_LAUNCH_CHECK(c);
   }
   // every descent moves at least one side of the pair one level down: bvh_height + 1 steps reach all leaf pairs
@@ -455,7 +527,7 @@ static int traverse_and_test(Ctx* c, const double* xyz, const double* uvw, doubl
     dim3 g(148 * 4, c->B);
     PairEnt* fin = (d & 1) ? c->frontB : c->frontA;
     PairEnt* fout = (d & 1) ? c->frontA : c->frontB;
-    k_trav_step<<<g, 256, 0, KS(c, "k_trav_step")>>>(d, c->nnode, c->nodes, c->boxes, fin, fout, c->cap_front, c->leaf, c->cap_leaf, c->cnt);
+    k_trav_step<<<g, 256, 0, KS(c, "k_trav_step")>>>(d, c->nnode, c->nodes, c->boxes, fin, fout, c->cap_front, c->leaf, c->cap_leaf, c->cnt, nd);
     CG_LAUNCH_CHECK(c);
   }
   {
@@ -507,11 +579,12 @@ int launch_contacts_async(Ctx* c, const double* xyz, const double* uvw, double d
 }
 
 int run_contacts(Ctx* c, const double* xyz, const double* uvw, double dt, double delta, int ccd, int* counts,
-                 bool prelaunched) {
+                 bool prelaunched, bool incremental) {
   if (c->nnode == 0) { set_error("context has no BVH"); return CLOTHGPU_ERR_STATE; }
   for (int attempt = 0;; attempt++) {
     phase_begin(c);
-    if (!(prelaunched && attempt == 0)) CG_CHECK(traverse_and_test(c, xyz, uvw, dt, delta, ccd));
+    // a retry after a queue overflow is always a full pass (the previous raw list does not survive the regrowth)
+    if (!(prelaunched && attempt == 0)) CG_CHECK(traverse_and_test(c, xyz, uvw, dt, delta, ccd, incremental && attempt == 0));
     CG_CHECK(fetch_counters(c));
     phase_end(c, 4);
     int bits = 0;
@@ -531,6 +604,8 @@ int run_contacts(Ctx* c, const double* xyz, const double* uvw, double dt, double
     if (c->h_cnt[s * NCNT + CNT_OVERFLOW] & 8) { set_error("contact element buffer overflow"); return CLOTHGPU_ERR_CAPACITY; }
     if (counts) counts[s] = c->h_cnt[s * NCNT + CNT_ACTIVE] ? c->h_cnt[s * NCNT + CNT_ELEM] : 0;
   }
+  // the (sorted, not yet de-duplicated) raw list of this pass is the "previous" list of the next incremental pass
+  std::swap(c->raw, c->raw_sorted);
   return CLOTHGPU_OK;
 }
 

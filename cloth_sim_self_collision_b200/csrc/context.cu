@@ -455,6 +455,13 @@ static int create_impl(Ctx* c, int nscene, int np, int ntri, int nquad, const in
     CG_CHECK(dev_upload(&c->edge_array, edge_array, edge_index[np]));
     CG_CHECK(dev_zeros(&c->boxes, B * nnode * 6));
     CG_CHECK(dev_zeros(&c->refit_flag, B * nnode));
+    CG_CHECK(dev_zeros(&c->uvw_snap, B * c->ndof));
+    CG_CHECK(dev_zeros(&c->vdirty, B * np));
+    CG_CHECK(dev_zeros(&c->ndirty, B * nnode));
+    {
+      const char* inc = getenv("CLOTHGPU_INCREMENTAL");
+      c->incremental_ccd = !(inc && atoi(inc) == 0);
+    }
     c->cap_front = std::max<long long>(16LL * ntri, 1 << 14);
     c->cap_leaf = std::max<long long>(16LL * ntri, 1 << 14);
     c->cap_raw = std::max<long long>(4LL * ntri, 1 << 14);
@@ -532,7 +539,7 @@ void clothgpu_destroy(clothgpu_ctx* c) {
                   c->lev_f_rows, c->lev_b_ptr, c->lev_b_rows, c->op_ptr, c->ops, c->nodes, c->pre, c->internal_list,
                   c->edge_index, c->edge_array, c->xyz, c->uvw, c->xyz_prev, c->uvw0, c->valDia, c->valCrs, c->iluDia,
                   c->iluCrs, c->vec_r, c->vec_x, c->vec_p, c->vec_z, c->tri_dW, c->tri_ddW, c->quad_dW, c->col_table,
-                  c->gravity, c->boxes, c->refit_flag, c->scal, c->partials, c->cnt, c->zone, c->zone_label,
+                  c->gravity, c->boxes, c->refit_flag, c->uvw_snap, c->vdirty, c->ndirty, c->scal, c->partials, c->cnt, c->zone, c->zone_label,
                   c->scratch, c->sort_keys, c->sort_keys2, c->sort_vals, c->sort_vals2};
   for (void* p : ptrs) cudaFree(p);
   cudaFree(c->tri_dbg_buf);

@@ -98,6 +98,7 @@ enum {
   CNT_NLEVEL = 9,    // impulse dependency levels
   CNT_TICKET = 10,   // arrival counter of the "last block reduces" pattern
   CNT_CAND = 11,     // narrow-phase candidates (leaf pair, test slot) that survived the cheap culls
+  CNT_RAWPREV = 12,  // raw contact elements of the previous detection pass (incremental CCD passes)
   CNT_FRONT = 16     // frontier sizes per traversal depth: CNT_FRONT + depth  (depth < 72)
 };
 // per-scene device scalars (doubles): layout of scal[]
@@ -167,6 +168,10 @@ struct Ctx {
   std::vector<double> gravity_override;  // B x 3 on the host, NaN = no override
   double* boxes = nullptr;
   int* refit_flag = nullptr;
+  // incremental CCD detection: velocities the last CCD boxes were built from, changed vertices / BVH nodes
+  double* uvw_snap = nullptr;
+  int *vdirty = nullptr, *ndirty = nullptr;
+  bool incremental_ccd = true;  // CLOTHGPU_INCREMENTAL=0 re-runs every pass in full
   double *scal = nullptr, *partials = nullptr;
   int* cnt = nullptr;
   int* zone = nullptr;    // union-find parent per vertex, -1 = not a member
@@ -256,9 +261,9 @@ int launch_ilu_factor_strips(Ctx* c);
 int run_pcg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out);
 int run_cg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out);
 int run_step_internal(Ctx* c, const clothgpu_params& p, bool use_ilu, double* conv_out, int* iter_out);
-int launch_refit(Ctx* c, const double* xyz, const double* uvw, double par, int mode);
+int launch_refit(Ctx* c, const double* xyz, const double* uvw, double par, int mode, bool incremental = false);
 int run_contacts(Ctx* c, const double* xyz, const double* uvw, double dt, double delta, int ccd, int* counts,
-                 bool prelaunched = false);
+                 bool prelaunched = false, bool incremental = false);
 int launch_contacts_async(Ctx* c, const double* xyz, const double* uvw, double dt, double delta, int ccd);
 int set_all_active(Ctx* c, int v);
 int launch_impulse(Ctx* c, const double* xyz, double* uvw, double delta, double stiffness, double dt, double mass,
