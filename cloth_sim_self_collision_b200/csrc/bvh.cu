@@ -524,7 +524,7 @@ static int traverse_and_test(Ctx* c, const double* xyz, const double* uvw, doubl
   }
   // every descent moves at least one side of the pair one level down: bvh_height + 1 steps reach all leaf pairs
   for (int d = 0; d <= c->bvh_height; d++) {
-    dim3 g(148 * 4, c->B);
+    dim3 g(incremental ? 74 : 148 * 4, c->B);  // incremental frontiers are small: a small grid launches faster
     PairEnt* fin = (d & 1) ? c->frontB : c->frontA;
     PairEnt* fout = (d & 1) ? c->frontA : c->frontB;
     k_trav_step<<<g, 256, 0, KS(c, "k_trav_step")>>>(d, c->nnode, c->nodes, c->boxes, fin, fout, c->cap_front, c->leaf, c->cap_leaf, c->cnt, nd);
