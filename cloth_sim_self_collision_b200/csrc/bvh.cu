@@ -101,7 +101,7 @@ __global__ void k_trav_reset(int* cnt) {
   for (int k = threadIdx.x; k < NCNT - CNT_FRONT; k += blockDim.x) c[CNT_FRONT + k] = 0;
   if (threadIdx.x == 0) {
     c[CNT_RAWPREV] = c[CNT_RAW];  // raw elements of the previous detection (now in the other raw buffer)
-    c[CNT_LEAF] = 0; c[CNT_RAW] = 0; c[CNT_ELEM] = 0; c[CNT_OVERFLOW] = 0; c[CNT_CAND] = 0;
+    c[CNT_LEAF] = 0; c[CNT_RAW] = 0; c[CNT_ELEM] = 0; c[CNT_OVERFLOW] = 0; c[CNT_CAND] = 0; c[CNT_GBAR] = 0;
   }
 }
 
@@ -150,11 +150,11 @@ __device__ __forceinline__ void path_push(PairEnt& e, unsigned code) {
 
 // one level of the pair recursion (bvh_aabb.cpp:441-475 / 797-833): prune on CAABB3D::IsIntersect, descend in the
 // child order (0,0),(1,0),(0,1),(1,1), collect leaf pairs
-__global__ void __launch_bounds__(256) k_trav_step(int d, int nnode, const int* __restrict__ nodes,
-                                                    const double* __restrict__ boxes, const PairEnt* __restrict__ fin,
-                                                    PairEnt* __restrict__ fout, long long cap_front,
-                                                    PairEnt* __restrict__ leaf, long long cap_leaf, int* cnt,
-                                                    const int* __restrict__ ndirty) {
+__device__ __forceinline__ void trav_step_body(int d, int nnode, const int* __restrict__ nodes,
+                                               const double* __restrict__ boxes, const PairEnt* __restrict__ fin,
+                                               PairEnt* __restrict__ fout, long long cap_front,
+                                               PairEnt* __restrict__ leaf, long long cap_leaf, int* cnt,
+                                               const int* __restrict__ ndirty) {
   const int s = blockIdx.y;
   int* c = cnt + s * NCNT;
   if (!c[CNT_ACTIVE]) return;
@@ -217,6 +217,40 @@ __global__ void __launch_bounds__(256) k_trav_step(int d, int nnode, const int* 
       if ((long long)lbase + 1 > cap_leaf) atomicOr(&c[CNT_OVERFLOW], 2);
       else lf[lbase] = e;
     }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_trav_step(int d, int nnode, const int* __restrict__ nodes,
+                                                    const double* __restrict__ boxes, const PairEnt* __restrict__ fin,
+                                                    PairEnt* __restrict__ fout, long long cap_front,
+                                                    PairEnt* __restrict__ leaf, long long cap_leaf, int* cnt,
+                                                    const int* __restrict__ ndirty) {
+  trav_step_body(d, nnode, nodes, boxes, fin, fout, cap_front, leaf, cap_leaf, cnt, ndirty);
+}
+
+// All levels of the pair recursion in ONE cooperative launch (co-residency guaranteed by the launch API): the CTAs
+// of a scene meet at a counter barrier between two levels instead of paying a kernel launch per BVH depth.
+__global__ void __launch_bounds__(256) k_trav_all(int ndepth, int nnode, const int* __restrict__ nodes,
+                                                   const double* __restrict__ boxes, PairEnt* frontA, PairEnt* frontB,
+                                                   long long cap_front, PairEnt* __restrict__ leaf, long long cap_leaf,
+                                                   int* cnt, const int* __restrict__ ndirty) {
+  const int s = blockIdx.y;
+  int* c = cnt + s * NCNT;
+  if (!c[CNT_ACTIVE]) return;
+  for (int d = 0; d < ndepth; d++) {
+    // level d is complete (barrier below / previous kernel): an empty frontier ends the recursion for every CTA
+    if (((volatile int*)c)[CNT_FRONT + d] == 0) break;
+    trav_step_body(d, nnode, nodes, boxes, (d & 1) ? frontB : frontA, (d & 1) ? frontA : frontB, cap_front, leaf,
+                   cap_leaf, cnt, ndirty);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(&c[CNT_GBAR], 1);
+      const int want = (d + 1) * (int)gridDim.x;
+      while (((volatile int*)c)[CNT_GBAR] < want) { }
+      __threadfence();
+    }
+    __syncthreads();
   }
 }
 
@@ -523,7 +557,26 @@ static int traverse_and_test(Ctx* c, const double* xyz, const double* uvw, doubl
     CG_LAUNCH_CHECK(c);
   }
   // every descent moves at least one side of the pair one level down: bvh_height + 1 steps reach all leaf pairs
-  for (int d = 0; d <= c->bvh_height; d++) {
+  bool fused = false;
+  // (used for the incremental passes only: their frontiers are tiny and nothing else runs beside them, while the
+  // full passes overlap the solve on the second stream, where a cooperative launch would have to wait for room)
+  if (incremental && c->trav_coop > 0 && c->B <= c->trav_coop && !c->ktiming) {
+    int ndepth = c->bvh_height + 1, nnode = c->nnode;
+    long long capf = c->cap_front, capl = c->cap_leaf;
+    const int* nodes = c->nodes; const double* boxes = c->boxes; PairEnt* fa = c->frontA; PairEnt* fb = c->frontB;
+    PairEnt* lf = c->leaf; int* cnt = c->cnt;
+    void* args[] = {&ndepth, &nnode, &nodes, &boxes, &fa, &fb, &capf, &lf, &capl, &cnt, &nd};
+    dim3 g(c->trav_sms, c->B);
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_trav_all, g, dim3(256), args, 0, c->stream);
+    if (e == cudaSuccess) {
+      c->launches++;
+      fused = true;
+    } else {
+      cudaGetLastError();  // e.g. too many CTAs for co-residency: fall back to one launch per level
+      c->trav_coop = 0;
+    }
+  }
+  for (int d = 0; d <= c->bvh_height && !fused; d++) {
     dim3 g(incremental ? 74 : 148 * 4, c->B);  // incremental frontiers are small: a small grid launches faster
     PairEnt* fin = (d & 1) ? c->frontB : c->frontA;
     PairEnt* fout = (d & 1) ? c->frontA : c->frontB;

@@ -462,6 +462,15 @@ static int create_impl(Ctx* c, int nscene, int np, int ntri, int nquad, const in
       const char* inc = getenv("CLOTHGPU_INCREMENTAL");
       c->incremental_ccd = !(inc && atoi(inc) == 0);
     }
+    {
+      // fused traversal: one CTA per SM and scene, all co-resident (cooperative launch); leave room for the strip
+      // kernels that run concurrently on the other stream
+      cudaDeviceProp pr;
+      CG_CUDA(cudaGetDeviceProperties(&pr, c->device));
+      c->trav_sms = pr.multiProcessorCount;
+      const char* tc = getenv("CLOTHGPU_FUSED_TRAVERSAL");
+      c->trav_coop = (pr.cooperativeLaunch && !(tc && atoi(tc) == 0)) ? 4 : 0;
+    }
     c->cap_front = std::max<long long>(16LL * ntri, 1 << 14);
     c->cap_leaf = std::max<long long>(16LL * ntri, 1 << 14);
     c->cap_raw = std::max<long long>(4LL * ntri, 1 << 14);

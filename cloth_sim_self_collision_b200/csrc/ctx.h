@@ -99,6 +99,7 @@ enum {
   CNT_TICKET = 10,   // arrival counter of the "last block reduces" pattern
   CNT_CAND = 11,     // narrow-phase candidates (leaf pair, test slot) that survived the cheap culls
   CNT_RAWPREV = 12,  // raw contact elements of the previous detection pass (incremental CCD passes)
+  CNT_GBAR = 13,     // arrival counter of the level barrier of the fused traversal kernel
   CNT_FRONT = 16     // frontier sizes per traversal depth: CNT_FRONT + depth  (depth < 72)
 };
 // per-scene device scalars (doubles): layout of scal[]
@@ -172,6 +173,8 @@ struct Ctx {
   double* uvw_snap = nullptr;
   int *vdirty = nullptr, *ndirty = nullptr;
   bool incremental_ccd = true;  // CLOTHGPU_INCREMENTAL=0 re-runs every pass in full
+  int trav_coop = 0;            // max scenes for which the fused (cooperative) traversal is co-resident; 0 = off
+  int trav_sms = 148;
   double *scal = nullptr, *partials = nullptr;
   int* cnt = nullptr;
   int* zone = nullptr;    // union-find parent per vertex, -1 = not a member
