@@ -73,7 +73,10 @@ __device__ void psd_clamp_sym22(const double* s2, double* s3) {
 
 // WdWddW_CST, cloth_internal_physics.h:70-176, one thread per (scene, triangle).
 // tri_dW: [scene][tri][3][3]; tri_ddW: [scene][tri][ino*3+jno][idim*3+jdim] (nullptr: gradient only)
-__global__ void __launch_bounds__(128) k_tri_elements(int ntri, int np, const int* __restrict__ tri,
+#ifndef TRI_B
+#define TRI_B 3
+#endif
+__global__ void __launch_bounds__(128, TRI_B) k_tri_elements(int ntri, int np, const int* __restrict__ tri,
                                                        const double* __restrict__ xyz0, const double* __restrict__ xyz,
                                                        double lambda, double myu, double* __restrict__ tri_dW,
                                                        double* __restrict__ tri_ddW) {
