@@ -86,6 +86,8 @@ def load():
     lib.clothgpu_buf_len.restype = C.c_longlong
     lib.clothgpu_launch_count.restype = C.c_longlong
     lib.clothgpu_buf_len.argtypes = [C.c_void_p, C.c_int]
+    lib.clothgpu_alloc_host.argtypes = [C.POINTER(C.c_void_p), C.c_longlong]
+    lib.clothgpu_free_host.argtypes = [C.c_void_p]
     lib.clothgpu_launch_count.argtypes = [C.c_void_p]
     lib.clothgpu_write.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_longlong]
     lib.clothgpu_read.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_longlong]
@@ -139,6 +141,7 @@ class ClothGPU:
                                       C.c_int(sc["ntri"]), C.c_int(sc["nquad"]), _ip(tri), _ip(quad), _ip(bc),
                                       _dp(xyz0), _ip(rowptr), _ip(colidx), C.c_int(self.nnode), *args)
         self.h = h
+        self._host_allocs = []
         self._check(rc)
 
     # ------------------------------------------------------------------ plumbing
@@ -148,6 +151,9 @@ class ClothGPU:
 
     def close(self):
         if getattr(self, "h", None):
+            for ptr in getattr(self, "_host_allocs", []):
+                self.lib.clothgpu_free_host(ptr)
+            self._host_allocs = []
             self.lib.clothgpu_destroy(self.h)
             self.h = None
 
@@ -175,11 +181,24 @@ class ClothGPU:
         assert xyz.size == self.ndof and uvw.size == self.ndof
         self._check(self.lib.clothgpu_upload_state(self.h, scene, _dp(xyz), _dp(uvw)))
 
-    def download_state(self, scene=0):
-        x = np.zeros(self.ndof)
-        v = np.zeros(self.ndof)
+    def download_state(self, scene=0, out=None):
+        """X, V of one scene; `out=(x, v)` fills caller-owned buffers (e.g. from `alloc_host`) instead of new ones."""
+        if out is None:
+            x = np.zeros(self.ndof)
+            v = np.zeros(self.ndof)
+        else:
+            x, v = out
+            assert x.size == self.ndof and v.size == self.ndof and x.dtype == np.float64 and v.dtype == np.float64
+            assert x.flags.c_contiguous and v.flags.c_contiguous
         self._check(self.lib.clothgpu_download_state(self.h, scene, _dp(x), _dp(v)))
         return x, v
+
+    def alloc_host(self, n):
+        """n doubles of page-locked host memory as a numpy array (freed with the context)."""
+        ptr = C.c_void_p()
+        self._check(self.lib.clothgpu_alloc_host(C.byref(ptr), int(n) * 8))
+        self._host_allocs.append(ptr)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(int(n),))
 
     def set_scene_gravity(self, scene, g):
         g = _cd(g)

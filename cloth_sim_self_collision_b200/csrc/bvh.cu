@@ -79,9 +79,10 @@ __global__ void __launch_bounds__(256) k_refit(int nnode, int np, const int* __r
   }
   int cur = nodes[i * 3 + 0];
   while (cur >= 0) {
-    __threadfence();
-    if (atomicAdd(&fl[cur], 1) == 0) return;  // the sibling subtree is not finished: its last thread continues
-    __threadfence();
+    // release our subtree's boxes / acquire the sibling's in one fenced atomic
+    int seen;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(seen) : "l"(fl + cur) : "memory");
+    if (seen == 0) return;  // the sibling subtree is not finished: its last thread continues
     if (nd) nd[cur] = __ldcg(nd + nodes[cur * 3 + 1]) | __ldcg(nd + nodes[cur * 3 + 2]);
     Box a = ld_box_cg(bx, nodes[cur * 3 + 1]);
     const Box o = ld_box_cg(bx, nodes[cur * 3 + 2]);

@@ -635,6 +635,17 @@ int clothgpu_download_state(clothgpu_ctx* c, int scene, double* xyz, double* uvw
   return CLOTHGPU_OK;
 }
 
+int clothgpu_alloc_host(void** ptr, long long bytes) {
+  if (!ptr || bytes <= 0) { set_error("bad argument"); return CLOTHGPU_ERR_ARG; }
+  *ptr = nullptr;
+  CG_CUDA(cudaMallocHost(ptr, (size_t)bytes));
+  return CLOTHGPU_OK;
+}
+int clothgpu_free_host(void* ptr) {
+  if (ptr) CG_CUDA(cudaFreeHost(ptr));
+  return CLOTHGPU_OK;
+}
+
 int clothgpu_set_scene_gravity(clothgpu_ctx* c, int scene, const double* g) {
   if (!c) { set_error("null context"); return CLOTHGPU_ERR_ARG; }
   if (scene < 0) {

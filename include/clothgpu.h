@@ -129,6 +129,10 @@ int clothgpu_read(clothgpu_ctx* ctx, int buf, int scene, void* host, long long c
 /* aXYZ / aUVW of one scene in one call (the state the reference keeps in two std::vector<double>) */
 int clothgpu_upload_state(clothgpu_ctx* ctx, int scene, const double* xyz, const double* uvw);
 int clothgpu_download_state(clothgpu_ctx* ctx, int scene, double* xyz, double* uvw);
+/* page-locked host memory for the buffers passed to the copies above (optional: pageable memory works, pinned memory
+ * lets the copies run as one DMA each -- the reference keeps aXYZ / aUVW in std::vector<double>, main.cpp:36-37) */
+int clothgpu_alloc_host(void** ptr, long long bytes);
+int clothgpu_free_host(void* ptr);
 /* per-scene gravity override (config 5: perturbed copies); scene < 0 clears all overrides */
 int clothgpu_set_scene_gravity(clothgpu_ctx* ctx, int scene, const double* gravity);
 int clothgpu_synchronize(clothgpu_ctx* ctx);

@@ -538,3 +538,25 @@ def test_contact_ops_need_a_bvh_and_zero_clearance_finds_nothing(oracle, sc_cont
     applied, stats = g.resolve_self_contact(p0)
     assert stats[0][1] == 0  # no proximity elements
     g.close()
+
+
+@pytest.mark.gpu
+def test_pinned_host_buffers_round_trip():
+    """clothgpu_alloc_host buffers (page-locked) through upload_state / download_state(out=...): same bytes as the
+    pageable path, and the step run from them gives the same state."""
+    sc = S.square_cloth_xz(9, 7, 0.1)
+    sc["bvh"] = S.median_split_bvh(sc)
+    rng = np.random.default_rng(3)
+    x0 = sc["xyz0"].reshape(-1) + 1e-3 * rng.standard_normal(sc["np"] * 3)
+    v0 = 1e-2 * rng.standard_normal(sc["np"] * 3)
+    g = G.ClothGPU(sc)
+    hx, hv = g.alloc_host(x0.size), g.alloc_host(v0.size)
+    hx[:] = x0
+    hv[:] = v0
+    g.upload_state(hx, hv)
+    x1, v1 = g.download_state()
+    assert np.array_equal(x1, x0) and np.array_equal(v1, v0)
+    ox, ov = g.alloc_host(x0.size), g.alloc_host(v0.size)
+    rx, rv = g.download_state(out=(ox, ov))
+    assert rx is ox and np.array_equal(ox, x0) and np.array_equal(ov, v0)
+    g.close()
