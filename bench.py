@@ -46,10 +46,12 @@ def parse_args():
     ap.add_argument("--scenes-per-gpu", type=int, default=1)
     ap.add_argument("--cpu-steps", type=int, default=3, help="steps of the bounded CPU baseline sample (0 = skip)")
     ap.add_argument("--ref-steps", type=int, default=5, help="cap on the timed steps of --impl reference")
-    ap.add_argument("--kernel-steps", type=int, default=3, help="steps of the per-kernel timing pass")
+    ap.add_argument("--kernel-steps", type=int, default=0, help="steps of the per-kernel timing pass (0 = the whole timed window)")
     ap.add_argument("--dense-steps", type=int, default=6,
                     help="extra report: steps of a second window in the dense self-contact regime (0 = skip)")
     ap.add_argument("--dense-start", type=int, default=64, help="first trajectory step of that window")
+    ap.add_argument("--profile-range", default="", choices=["", "timed", "dense"],
+                    help="bracket that region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -278,7 +280,9 @@ def run_ours(args):
     sampler.start()
     l0 = g.launch_count()
     g.timer_start()
+    _prof(args, "timed", True)
     stats = g.step_self_contact(p, K)
+    _prof(args, "timed", False)
     ms_dev = g.timer_stop()
     launches = g.launch_count() - l0
     barrier()
@@ -331,7 +335,7 @@ def run_ours(args):
             g.upload_state(start_state[s][0], start_state[s][1], scene=s)
         g.set_kernel_timing(True)
         g.set_profiling(True)
-        ks = max(1, min(args.kernel_steps, K))
+        ks = K if args.kernel_steps <= 0 else max(1, min(args.kernel_steps, K))
         g.step_self_contact(p, ks)
         kt = g.kernel_times()
         phases = g.phase_ms()
@@ -394,7 +398,9 @@ def run_ours(args):
                 g.upload_state(d0[s][0], d0[s][1], scene=s)
             g.synchronize()
             g.timer_start()
+            _prof(args, "dense", True)
             dst = g.step_self_contact(p, args.dense_steps)
+            _prof(args, "dense", False)
             dms = g.timer_stop() / (args.dense_steps * Sn)
             dense = {"trajectory_steps": "%d..%d" % (args.dense_start, args.dense_start + args.dense_steps - 1),
                      "ms_per_step": dms, "prox_elems_last": int(dst[0][1]), "ccd_passes_last": int(dst[0][2]),
@@ -431,6 +437,15 @@ def run_ours(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _prof(args, which, start):
+    if args.profile_range != which:
+        return
+    import torch
+    rt = torch.cuda.cudart()
+    torch.cuda.synchronize()
+    (rt.cudaProfilerStart if start else rt.cudaProfilerStop)()
 
 
 def main():
