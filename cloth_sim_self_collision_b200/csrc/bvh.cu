@@ -564,6 +564,16 @@ __global__ void k_compact_elems(int n, const RawElem* __restrict__ raw, const in
 
 __global__ void k_set_active(int* cnt, int v) { cnt[blockIdx.x * NCNT + CNT_ACTIVE] = v; }
 
+// scenes whose fused traversal (one CTA per SM and scene) is co-resident: resident CTAs of k_trav_all per SM
+int trav_all_max_scenes() {
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trav_all, 256, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return nb;
+}
+
 int launch_refit(Ctx* c, const double* xyz, const double* uvw, double par, int mode, bool incremental) {
   // mode 1 keeps a snapshot of the velocities the boxes were built from; an incremental refit first marks the
   // vertices whose velocity changed since then and propagates "dirty" up the tree together with the boxes

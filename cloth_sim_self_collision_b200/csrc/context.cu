@@ -469,7 +469,7 @@ static int create_impl(Ctx* c, int nscene, int np, int ntri, int nquad, const in
       CG_CUDA(cudaGetDeviceProperties(&pr, c->device));
       c->trav_sms = pr.multiProcessorCount;
       const char* tc = getenv("CLOTHGPU_FUSED_TRAVERSAL");
-      c->trav_coop = (pr.cooperativeLaunch && !(tc && atoi(tc) == 0)) ? 4 : 0;
+      c->trav_coop = (pr.cooperativeLaunch && !(tc && atoi(tc) == 0)) ? trav_all_max_scenes() : 0;
     }
     c->cap_front = std::max<long long>(16LL * ntri, 1 << 14);
     c->cap_leaf = std::max<long long>(16LL * ntri, 1 << 14);

@@ -265,6 +265,7 @@ int run_pcg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out);
 int run_cg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out);
 int run_step_internal(Ctx* c, const clothgpu_params& p, bool use_ilu, double* conv_out, int* iter_out);
 int launch_refit(Ctx* c, const double* xyz, const double* uvw, double par, int mode, bool incremental = false);
+int trav_all_max_scenes();
 int run_contacts(Ctx* c, const double* xyz, const double* uvw, double dt, double delta, int ccd, int* counts,
                  bool prelaunched = false, bool incremental = false);
 int launch_contacts_async(Ctx* c, const double* xyz, const double* uvw, double dt, double delta, int ccd);
