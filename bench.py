@@ -423,7 +423,8 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, sc, nscene_total),
             "clocks": clocks,
             "e2e": {"value": ms_e2e / (K * nscene_total), "unit": "ms/step",
-                    "h2d_bytes_per_step": 2 * 8 * sc["np"] * 3 * Sn, "d2h_bytes_per_step": 2 * 8 * sc["np"] * 3 * Sn},
+                    "h2d_bytes_per_step": 2 * 8 * sc["np"] * 3 * nscene_total,
+                    "d2h_bytes_per_step": 2 * 8 * sc["np"] * 3 * nscene_total},  # X and V of every scene of the job
             "gpu_launches": launches_total,
             "roofline": roof,
             "cpu_baseline": cpu,
