@@ -149,8 +149,8 @@ def algorithmic_bytes(sc, nleaf):
         "k_pack": 2 * 72 * (P + Cc),
         "k_pack_rows": 2 * 72 * (P + Cc),
         "k_matvec": 72 * (P + Cc) + 4 * Cc + 4 * P + 48 * P,
-        # leaf pair entry (32 B) + 2 triangles (24 B) + 6 vertices x (x, v) (288 B)
-        "k_narrow": nleaf * 344,
+        # (k_cull / k_narrow / k_trav_step: no bandwidth model -- their re-reads of vertices and boxes are served by
+        # L1/L2, ncu measures ~48 MB of DRAM traffic per full pass; they are latency / divergence bound)
         "k_tri_elements": T * (12 + 90 * 8) + 48 * P,
         "k_gather_slot": Cc * 72 + T * 6 * 72,
         "k_gather_vertex": P * (72 + 24 + 48) + T * 3 * (72 + 24),
