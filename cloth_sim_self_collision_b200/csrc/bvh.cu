@@ -327,20 +327,23 @@ struct SlotData {
   Box bb;       // box the FV tests cull against
 };
 
-__device__ __forceinline__ void load_slot(int ccd, int slot, const PairEnt& e, const int* __restrict__ nodes,
-                                          const int* __restrict__ tri, const double* __restrict__ bx,
-                                          const double* __restrict__ x, const double* __restrict__ v, double dt, SlotData& S) {
-  const int it = nodes[e.i0 * 3 + 1], jt = nodes[e.i1 * 3 + 1];
+__device__ __forceinline__ void load_slot(int ccd, int slot, int i0, int i1, const int4* __restrict__ node_tri,
+                                          const double* __restrict__ bx, const double* __restrict__ x,
+                                          const double* __restrict__ v, double dt, SlotData& S) {
+  const int4 ta = node_tri[i0], tb = node_tri[i1];  // {v0, v1, v2, triangle} of the two leaves
+  const int ia[3] = {ta.x, ta.y, ta.z}, ib[3] = {tb.x, tb.y, tb.z};
   if (slot < 6) {
     const bool first = slot < 3;
-    const int ft = first ? it : jt, vt = first ? jt : it, a = first ? slot : slot - 3;
-    S.n[0] = tri[ft * 3]; S.n[1] = tri[ft * 3 + 1]; S.n[2] = tri[ft * 3 + 2]; S.n[3] = tri[vt * 3 + a];
+    const int a = first ? slot : slot - 3;
+    const int* f = first ? ia : ib;
+    const int* o = first ? ib : ia;
+    S.n[0] = f[0]; S.n[1] = f[1]; S.n[2] = f[2]; S.n[3] = o[a];
     // reference quirk (bvh_aabb.cpp:490-505): the proximity FV test culls against the box of BVH node number
     // <triangle index>, not against the box of the face's own leaf; the CCD test uses the leaf (:855)
-    S.bb = ld_box(bx, ccd ? (first ? e.i0 : e.i1) : ft);
+    S.bb = ld_box(bx, ccd ? (first ? i0 : i1) : (first ? ta.w : tb.w));
   } else {
     const int k = slot - 6, a0 = k / 3, a1 = (a0 + 1) % 3, b0 = k - a0 * 3, b1 = (b0 + 1) % 3;
-    S.n[0] = tri[it * 3 + a0]; S.n[1] = tri[it * 3 + a1]; S.n[2] = tri[jt * 3 + b0]; S.n[3] = tri[jt * 3 + b1];
+    S.n[0] = ia[a0]; S.n[1] = ia[a1]; S.n[2] = ib[b0]; S.n[3] = ib[b1];
   }
 #pragma unroll
   for (int k = 0; k < 4; k++) {
@@ -361,11 +364,11 @@ __device__ __forceinline__ void load_slot(int ccd, int slot, const PairEnt& e, c
 #ifndef NARROW_B
 #define NARROW_B 4
 #endif
-__global__ void __launch_bounds__(CULL_T, CULL_B) k_cull(int ccd, int nnode, int np, const int* __restrict__ nodes,
-                                               const int* __restrict__ tri, const double* __restrict__ boxes,
+__global__ void __launch_bounds__(CULL_T, CULL_B) k_cull(int ccd, int nnode, int np, const int4* __restrict__ node_tri,
+                                               const double* __restrict__ boxes,
                                                const double* __restrict__ xyz, const double* __restrict__ uvw,
                                                double dt, double delta, const PairEnt* __restrict__ leaf,
-                                               long long cap_leaf, int2* __restrict__ cand, long long cap_cand, int* cnt) {
+                                               long long cap_leaf, int4* __restrict__ cand, long long cap_cand, int* cnt) {
   const int s = blockIdx.y;
   int* c = cnt + s * NCNT;
   if (!c[CNT_ACTIVE]) return;
@@ -374,21 +377,21 @@ __global__ void __launch_bounds__(CULL_T, CULL_B) k_cull(int ccd, int nnode, int
   const double* x = xyz + (size_t)s * np * 3;
   const double* v = ccd ? uvw + (size_t)s * np * 3 : nullptr;
   const PairEnt* lf = leaf + (size_t)s * cap_leaf;
-  int2* cd = cand + (size_t)s * cap_cand;
+  int4* cd = cand + (size_t)s * cap_cand;
   const int lane = threadIdx.x & 31;
   for (int i0 = blockIdx.x * blockDim.x; i0 < nleaf; i0 += gridDim.x * blockDim.x) {
     const int idx = i0 + threadIdx.x;
     unsigned mask = 0;
+    int ei0 = 0, ei1 = 0;
     if (idx < nleaf) {
       const PairEnt e = lf[idx];
-      const int it = nodes[e.i0 * 3 + 1], jt = nodes[e.i1 * 3 + 1];
-      int in[3], jn[3];
+      ei0 = e.i0; ei1 = e.i1;
+      const int4 ta = node_tri[e.i0], tb = node_tri[e.i1];  // {v0, v1, v2, triangle} of the two leaves
+      const int it = ta.w, jt = tb.w;
+      const int in[3] = {ta.x, ta.y, ta.z}, jn[3] = {tb.x, tb.y, tb.z};
       V3 p[3], q[3], pe[3], qe[3];
 #pragma unroll
-      for (int a = 0; a < 3; a++) {
-        in[a] = tri[it * 3 + a]; jn[a] = tri[jt * 3 + a];
-        p[a] = ld3(x, in[a]); q[a] = ld3(x, jn[a]);
-      }
+      for (int a = 0; a < 3; a++) { p[a] = ld3(x, in[a]); q[a] = ld3(x, jn[a]); }
       if (ccd) {
 #pragma unroll
         for (int a = 0; a < 3; a++) {
@@ -440,18 +443,18 @@ __global__ void __launch_bounds__(CULL_T, CULL_B) k_cull(int ccd, int nnode, int
     while (mask) {
       const int slot = __ffs(mask) - 1;
       mask &= mask - 1;
-      if (pos < cap_cand) cd[pos] = make_int2(idx, slot);
+      if (pos < cap_cand) cd[pos] = make_int4(ei0, ei1, slot, idx);
       else atomicOr(&c[CNT_OVERFLOW], 2);
       pos++;
     }
   }
 }
 
-__global__ void __launch_bounds__(128, NARROW_B) k_narrow(int ccd, int nnode, int np, const int* __restrict__ nodes,
-                                                 const int* __restrict__ tri, const double* __restrict__ boxes,
+__global__ void __launch_bounds__(128, NARROW_B) k_narrow(int ccd, int nnode, int np, const int4* __restrict__ node_tri,
+                                                 const double* __restrict__ boxes,
                                                  const double* __restrict__ xyz, const double* __restrict__ uvw,
                                                  double dt, double delta, const PairEnt* __restrict__ leaf,
-                                                 long long cap_leaf, const int2* __restrict__ cand, long long cap_cand,
+                                                 long long cap_leaf, const int4* __restrict__ cand, long long cap_cand,
                                                  RawElem* __restrict__ raw, long long cap_raw, int* cnt) {
   const int s = blockIdx.y;
   int* c = cnt + s * NCNT;
@@ -461,14 +464,13 @@ __global__ void __launch_bounds__(128, NARROW_B) k_narrow(int ccd, int nnode, in
   const double* x = xyz + (size_t)s * np * 3;
   const double* v = ccd ? uvw + (size_t)s * np * 3 : nullptr;
   const PairEnt* lf = leaf + (size_t)s * cap_leaf;
-  const int2* cd = cand + (size_t)s * cap_cand;
+  const int4* cd = cand + (size_t)s * cap_cand;
   RawElem* rw = raw + (size_t)s * cap_raw;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < ncand; k += gridDim.x * blockDim.x) {
-    const int2 cs = cd[k];
-    const int slot = cs.y;
-    const PairEnt e = lf[cs.x];
+    const int4 cs = cd[k];  // {leaf node i0, leaf node i1, slot, leaf pair index}
+    const int slot = cs.z;
     SlotData S;
-    load_slot(ccd, slot, e, nodes, tri, bx, x, v, dt, S);
+    load_slot(ccd, slot, cs.x, cs.y, node_tri, bx, x, v, dt, S);
     bool hit;
     if (ccd)
       hit = slot < 6 ? is_fv_ccd(S.n[0], S.n[1], S.n[2], S.n[3], S.p[0], S.p[1], S.p[2], S.p[3], S.q[0], S.q[1], S.q[2], S.q[3], S.bb)
@@ -480,7 +482,7 @@ __global__ void __launch_bounds__(128, NARROW_B) k_narrow(int ccd, int nnode, in
       int key[4];
       if (slot < 6) canon_fv(S.n[0], S.n[1], S.n[2], S.n[3], key);
       else canon_ee(S.n[0], S.n[1], S.n[2], S.n[3], key);
-      emit(e, slot, key, rw, cap_raw, c);
+      emit(lf[cs.w], slot, key, rw, cap_raw, c);  // the pair's DFS rank is only needed for the (rare) hits
     }
   }
 }
@@ -638,11 +640,11 @@ static int traverse_and_test(Ctx* c, const double* xyz, const double* uvw, doubl
   }
   {
     dim3 g(148 * 8 * (256 / CULL_T), c->B);
-    k_cull<<<g, CULL_T, 0, KS(c, "k_cull")>>>(ccd, c->nnode, c->np, c->nodes, c->tri, c->boxes, xyz, uvw, dt, delta, c->leaf,
+    k_cull<<<g, CULL_T, 0, KS(c, "k_cull")>>>(ccd, c->nnode, c->np, (const int4*)c->node_tri, c->boxes, xyz, uvw, dt, delta, c->leaf,
                                    c->cap_leaf, c->cand, c->cap_leaf * 2, c->cnt);
     CG_LAUNCH_CHECK(c);
     dim3 g2(148 * 4, c->B);
-    k_narrow<<<g2, 128, 0, KS(c, "k_narrow")>>>(ccd, c->nnode, c->np, c->nodes, c->tri, c->boxes, xyz, uvw, dt, delta, c->leaf,
+    k_narrow<<<g2, 128, 0, KS(c, "k_narrow")>>>(ccd, c->nnode, c->np, (const int4*)c->node_tri, c->boxes, xyz, uvw, dt, delta, c->leaf,
                                         c->cap_leaf, c->cand, c->cap_leaf * 2, c->raw, c->cap_raw, c->cnt);
     CG_LAUNCH_CHECK(c);
   }

@@ -64,7 +64,7 @@ static int alloc_queues(Ctx* c) {
   CG_CHECK(dev_alloc(&c->frontA, c->cap_front * c->B));
   CG_CHECK(dev_alloc(&c->frontB, c->cap_front * c->B));
   CG_CHECK(dev_alloc(&c->leaf, c->cap_leaf * c->B));
-  CG_CHECK(dev_alloc(&c->cand, c->cap_leaf * 2 * c->B));
+  CG_CHECK(dev_alloc(&c->cand, c->cap_leaf * 2 * c->B));  // int4 records
   CG_CHECK(dev_alloc(&c->raw, c->cap_raw * c->B));
   CG_CHECK(dev_alloc(&c->raw_sorted, c->cap_raw * c->B));
   CG_CHECK(dev_alloc(&c->elems, c->cap_elem * 5 * c->B));
@@ -359,7 +359,7 @@ static int build_topology(Ctx* c, const int* tri, const int* quad, const int* ro
   return CLOTHGPU_OK;
 }
 
-static int build_bvh(Ctx* c, const int* nodes) {
+static int build_bvh(Ctx* c, const int* nodes, const int* tri) {
   const int nn = c->nnode;
   // preorder rank in the order of the self traversal: self(n) visits n, then self(child0), self(child1)
   // (bvh_aabb.cpp:540-557); explicit stack, the trees are ~20 deep but the recursion is not needed
@@ -394,6 +394,18 @@ static int build_bvh(Ctx* c, const int* nodes) {
   c->bvh_height = height;
   c->ninternal = (int)internal.size();
   CG_CHECK(dev_upload(&c->nodes, nodes, (long long)nn * 3));
+  {
+    // leaf node -> {vertex 0, 1, 2, triangle}: one 16-byte load in the narrow phase instead of node -> triangle -> vertices
+    std::vector<int> nt((size_t)nn * 4, -1);
+    for (int i = 0; i < nn; i++) {
+      if (nodes[i * 3 + 2] != -1) continue;
+      const int t = nodes[i * 3 + 1];
+      if (t < 0 || t >= c->ntri) { set_error("BVH leaf refers to a triangle out of range"); return CLOTHGPU_ERR_ARG; }
+      nt[(size_t)i * 4 + 0] = tri[t * 3 + 0]; nt[(size_t)i * 4 + 1] = tri[t * 3 + 1]; nt[(size_t)i * 4 + 2] = tri[t * 3 + 2];
+      nt[(size_t)i * 4 + 3] = t;
+    }
+    CG_CHECK(dev_upload(&c->node_tri, nt));
+  }
   CG_CHECK(dev_upload(&c->pre, pre));
   CG_CHECK(dev_upload(&c->internal_list, internal));
   return CLOTHGPU_OK;
@@ -450,7 +462,7 @@ static int create_impl(Ctx* c, int nscene, int np, int ntri, int nquad, const in
   if (nnode > 0) {
     if (nnode != 2 * ntri - 1) { set_error("nnode must be 2*ntri-1"); return CLOTHGPU_ERR_ARG; }
     if (!bvh_nodes || !edge_index || !edge_array) { set_error("bvh_nodes / edge arrays missing"); return CLOTHGPU_ERR_ARG; }
-    CG_CHECK(build_bvh(c, bvh_nodes));
+    CG_CHECK(build_bvh(c, bvh_nodes, tri));
     CG_CHECK(dev_upload(&c->edge_index, edge_index, np + 1));
     CG_CHECK(dev_upload(&c->edge_array, edge_array, edge_index[np]));
     CG_CHECK(dev_zeros(&c->boxes, B * nnode * 6));
@@ -545,7 +557,7 @@ void clothgpu_destroy(clothgpu_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   void* ptrs[] = {c->tri, c->quad, c->bc, c->rowptr, c->colidx, c->diaind, c->xyz0, c->vt_ptr, c->vt_ent, c->vq_ptr,
                   c->vq_ent, c->slot_row, c->st_ptr, c->st_ent, c->sq_ptr, c->sq_ent, c->quadK, c->quadT, c->lev_f_ptr,
-                  c->lev_f_rows, c->lev_b_ptr, c->lev_b_rows, c->op_ptr, c->ops, c->nodes, c->pre, c->internal_list,
+                  c->lev_f_rows, c->lev_b_ptr, c->lev_b_rows, c->op_ptr, c->ops, c->nodes, c->node_tri, c->pre, c->internal_list,
                   c->edge_index, c->edge_array, c->xyz, c->uvw, c->xyz_prev, c->uvw0, c->valDia, c->valCrs, c->iluDia,
                   c->iluCrs, c->vec_r, c->vec_x, c->vec_p, c->vec_z, c->tri_dW, c->tri_ddW, c->quad_dW, c->col_table,
                   c->gravity, c->boxes, c->refit_flag, c->uvw_snap, c->vdirty, c->ndirty, c->scal, c->partials, c->cnt, c->zone, c->zone_label,

@@ -154,6 +154,7 @@ struct Ctx {
   long long nops = 0;
   // BVH
   int* nodes = nullptr;     // nnode x 3
+  int* node_tri = nullptr;  // nnode x 4: leaf -> {v0, v1, v2, triangle}
   uint32_t* pre = nullptr;  // preorder rank per node
   int bvh_height = 0, ninternal = 0;
   int* internal_list = nullptr;  // ids of the internal nodes
@@ -182,7 +183,7 @@ struct Ctx {
   // traversal queues (capacities are per scene)
   long long cap_front = 0, cap_leaf = 0, cap_raw = 0, cap_elem = 0;
   PairEnt *frontA = nullptr, *frontB = nullptr, *leaf = nullptr;
-  int2* cand = nullptr;  // 2 x cap_leaf candidates per scene
+  int4* cand = nullptr;  // 2 x cap_leaf candidates per scene: {leaf node i0, leaf node i1, test slot, leaf pair index}
   RawElem *raw = nullptr, *raw_sorted = nullptr;
   int* elems = nullptr;  // cap_elem x 5
   // impulse scheduling scratch
