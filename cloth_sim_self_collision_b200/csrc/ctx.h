@@ -174,6 +174,7 @@ struct Ctx {
   double* uvw_snap = nullptr;
   int *vdirty = nullptr, *ndirty = nullptr;
   bool incremental_ccd = true;  // CLOTHGPU_INCREMENTAL=0 re-runs every pass in full
+  int imp_threads = 256;        // CLOTHGPU_IMP_THREADS: threads of the data-flow impulse kernel
   int trav_coop = 0;            // max scenes for which the fused (cooperative) traversal is co-resident; 0 = off
   int trav_sms = 148;
   double *scal = nullptr, *partials = nullptr;

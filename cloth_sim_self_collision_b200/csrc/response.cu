@@ -339,7 +339,7 @@ int launch_impulse(Ctx* c, const double* xyz, double* uvw, double delta, double 
   if (!use_levels && ne_max <= 200 * 1024) {
     const int smem = (ne_max + 127) / 128 * 128;
     CG_CUDA(cudaFuncSetAttribute(k_imp_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(smem, 48 * 1024)));
-    static const int imp_threads = getenv("CLOTHGPU_IMP_THREADS") ? std::min(512, std::max(32, atoi(getenv("CLOTHGPU_IMP_THREADS")) / 32 * 32)) : 256;
+    const int imp_threads = c->imp_threads;
     k_imp_flow<<<c->B, imp_threads, smem, KS(c, "k_imp_flow")>>>(ccd, c->np, c->cap_elem, c->elems, c->imp_pred, xyz, uvw, delta,
                                                   stiffness, dt, mass, c->cnt);
   } else {
