@@ -481,7 +481,7 @@ static int create_impl(Ctx* c, int nscene, int np, int ntri, int nquad, const in
       CG_CUDA(cudaGetDeviceProperties(&pr, c->device));
       c->trav_sms = pr.multiProcessorCount;
       const char* it = getenv("CLOTHGPU_IMP_THREADS");
-      if (it) c->imp_threads = std::min(512, std::max(32, atoi(it) / 32 * 32));
+      if (it) c->imp_threads = std::min(256, std::max(32, atoi(it) / 32 * 32));
       const char* tc = getenv("CLOTHGPU_FUSED_TRAVERSAL");
       c->trav_coop = (pr.cooperativeLaunch && !(tc && atoi(tc) == 0)) ? trav_all_max_scenes() : 0;
     }

@@ -192,7 +192,8 @@ __device__ __forceinline__ double cubic_root(double r0, double r1, double v0, do
   return 0.5 * (r0 + r1);
 }
 // FindCoplanerInterp, bvh_aabb.cpp:598-662
-static __device__ __noinline__ double coplanar_time(V3 s0, V3 s1, V3 s2, V3 s3, V3 e0, V3 e1, V3 e2, V3 e3) {
+// (body inlined where latency counts -- the Gauss-Seidel impulse chain --, a call in the throughput-bound narrow phase)
+static __device__ __forceinline__ double coplanar_time_inl(V3 s0, V3 s1, V3 s2, V3 s3, V3 e0, V3 e1, V3 e2, V3 e3) {
   const V3 x1 = s1 - s0, x2 = s2 - s0, x3 = s3 - s0;
   const V3 v1 = (e1 - e0) - x1, v2 = (e2 - e0) - x2, v3v = (e3 - e0) - x3;
   const double k0 = triple(x3, x1, x2);
@@ -229,6 +230,10 @@ static __device__ __noinline__ double coplanar_time(V3 s0, V3 s1, V3 s2, V3 s3, 
   }
   if (f0 * f1 > 0) return -1;
   return cubic_root(r0, r1, f0, k0, k1, k2, k3);
+}
+
+static __device__ __noinline__ double coplanar_time(V3 s0, V3 s1, V3 s2, V3 s3, V3 e0, V3 e1, V3 e2, V3 e3) {
+  return coplanar_time_inl(s0, s1, s2, s3, e0, e1, e2, e3);
 }
 
 // GetMinDist_LineSegPoint, vector3d.h:282-295

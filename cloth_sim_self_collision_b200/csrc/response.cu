@@ -121,16 +121,16 @@ __device__ void impulse_prx_one(const int* n, const double* xyz, double* uvw, do
 
 // one element of SelfCollisionImpulse_CCD, self_collision_cloth.cpp:127-210.  Reference quirk (:141): the impact
 // time is re-solved with the UN-scaled velocity (end points p + v, not p + dt*v).
-__device__ void impulse_ccd_apply(const int* n, V3 p0, V3 p1, V3 p2, V3 p3, double* uvw, double delta, double dt,
+__device__ __forceinline__ void impulse_ccd_apply(const int* n, V3 p0, V3 p1, V3 p2, V3 p3, double* uvw, double delta, double dt,
                                   double mass);
 __device__ void impulse_ccd_one(const int* n, const double* xyz, double* uvw, double delta, double dt, double mass) {
   impulse_ccd_apply(n, ld3(xyz, n[0]), ld3(xyz, n[1]), ld3(xyz, n[2]), ld3(xyz, n[3]), uvw, delta, dt, mass);
 }
 // positions are passed in: the data-flow kernel loads them while it waits for the element's predecessors
-__device__ void impulse_ccd_apply(const int* n, V3 p0, V3 p1, V3 p2, V3 p3, double* uvw, double delta, double dt,
+__device__ __forceinline__ void impulse_ccd_apply(const int* n, V3 p0, V3 p1, V3 p2, V3 p3, double* uvw, double delta, double dt,
                                   double mass) {
   const V3 v0 = ld3(uvw, n[0]), v1 = ld3(uvw, n[1]), v2 = ld3(uvw, n[2]), v3v = ld3(uvw, n[3]);
-  const double t = coplanar_time(p0, p1, p2, p3, p0 + v0, p1 + v1, p2 + v2, p3 + v3v);
+  const double t = coplanar_time_inl(p0, p1, p2, p3, p0 + v0, p1 + v1, p2 + v2, p3 + v3v);
   if (t < 0 || t > 1) return;
   const V3 p0m = p0 + t * v0, p1m = p1 + t * v1, p2m = p2 + t * v2, p3m = p3 + t * v3v;
   if (n[4]) {
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(1024) k_imp_run(int ccd, int np, long long cap
 // runnable and its owner is working on it, so the loop cannot dead-lock; independent dependency chains overlap
 // instead of meeting at a barrier per level, and geometry (positions, indices) is fetched before the wait.
 // Consecutive elements (which usually share their first vertex) are spread over different warps.
-__global__ void __launch_bounds__(512) k_imp_flow(int ccd, int np, long long cap_elem, const int* __restrict__ elems_all,
+__global__ void __launch_bounds__(256) k_imp_flow(int ccd, int np, long long cap_elem, const int* __restrict__ elems_all,
                                                     const int* __restrict__ pred_all, const double* __restrict__ xyz_all,
                                                     double* uvw_all, double delta, double stiffness, double dt,
                                                     double mass, const int* __restrict__ cnt) {
