@@ -191,9 +191,29 @@ __device__ __forceinline__ double cubic_root(double r0, double r1, double v0, do
   }
   return 0.5 * (r0 + r1);
 }
+// The same bisection with the next level evaluated speculatively: both candidate midpoints of halving n+1 (and their
+// cubic values) are computed while the sign test of halving n resolves, so two halvings cost one dependent
+// evaluation plus a select.  Identical arithmetic on the path taken, hence identical result; used where the chain
+// latency counts (Gauss-Seidel impulses), not in the throughput-bound narrow phase (twice the flops).
+__device__ __forceinline__ double cubic_root_spec(double r0, double r1, double v0, double k0, double k1, double k2, double k3) {
+#pragma unroll
+  for (int n = 0; n < 14; n += 2) {
+    const double r2 = 0.5 * (r0 + r1);
+    const double ra = 0.5 * (r0 + r2), rb = 0.5 * (r2 + r1);  // next midpoint if the root is left / right of r2
+    const double v2 = cubic(r2, k0, k1, k2, k3);
+    const double va = cubic(ra, k0, k1, k2, k3), vb = cubic(rb, k0, k1, k2, k3);
+    const bool left = v0 * v2 < 0;
+    if (left) r1 = r2; else r0 = r2;
+    const double r3 = left ? ra : rb, v3 = left ? va : vb;
+    if (v0 * v3 < 0) r1 = r3; else r0 = r3;
+  }
+  return 0.5 * (r0 + r1);
+}
 // FindCoplanerInterp, bvh_aabb.cpp:598-662
 // (body inlined where latency counts -- the Gauss-Seidel impulse chain --, a call in the throughput-bound narrow phase)
+template <bool SPEC>
 static __device__ __forceinline__ double coplanar_time_inl(V3 s0, V3 s1, V3 s2, V3 s3, V3 e0, V3 e1, V3 e2, V3 e3) {
+#define cubic_root(A_, B_, C_, D_, E_, F_, G_) (SPEC ? cubic_root_spec(A_, B_, C_, D_, E_, F_, G_) : cubic_root(A_, B_, C_, D_, E_, F_, G_))
   const V3 x1 = s1 - s0, x2 = s2 - s0, x3 = s3 - s0;
   const V3 v1 = (e1 - e0) - x1, v2 = (e2 - e0) - x2, v3v = (e3 - e0) - x3;
   const double k0 = triple(x3, x1, x2);
@@ -232,8 +252,9 @@ static __device__ __forceinline__ double coplanar_time_inl(V3 s0, V3 s1, V3 s2, 
   return cubic_root(r0, r1, f0, k0, k1, k2, k3);
 }
 
+#undef cubic_root
 static __device__ __noinline__ double coplanar_time(V3 s0, V3 s1, V3 s2, V3 s3, V3 e0, V3 e1, V3 e2, V3 e3) {
-  return coplanar_time_inl(s0, s1, s2, s3, e0, e1, e2, e3);
+  return coplanar_time_inl<false>(s0, s1, s2, s3, e0, e1, e2, e3);
 }
 
 // GetMinDist_LineSegPoint, vector3d.h:282-295

@@ -130,7 +130,7 @@ __device__ void impulse_ccd_one(const int* n, const double* xyz, double* uvw, do
 __device__ __forceinline__ void impulse_ccd_apply(const int* n, V3 p0, V3 p1, V3 p2, V3 p3, double* uvw, double delta, double dt,
                                   double mass) {
   const V3 v0 = ld3(uvw, n[0]), v1 = ld3(uvw, n[1]), v2 = ld3(uvw, n[2]), v3v = ld3(uvw, n[3]);
-  const double t = coplanar_time_inl(p0, p1, p2, p3, p0 + v0, p1 + v1, p2 + v2, p3 + v3v);
+  const double t = coplanar_time_inl<true>(p0, p1, p2, p3, p0 + v0, p1 + v1, p2 + v2, p3 + v3v);
   if (t < 0 || t > 1) return;
   const V3 p0m = p0 + t * v0, p1m = p1 + t * v1, p2m = p2 + t * v2, p3m = p3 + t * v3v;
   if (n[4]) {
