@@ -20,7 +20,7 @@ def shard_scenes(nscene_total, world, rank):
 def scene_gravity(base_gravity, scene):
     """Per-scene gravity of config 5: gravity-y perturbed by 0.001 per scene so that trajectories differ
     (SURVEY.md section 8d); scene 0 is config 3 itself."""
-    return (float(base_gravity[0]), 0.05 + 0.001 * scene, float(base_gravity[2]))
+    return (float(base_gravity[0]), float(base_gravity[1]) + 0.001 * scene, float(base_gravity[2]))
 
 
 def gather_scene_values(dist, local_values, nscene_total, device="cpu"):

@@ -99,6 +99,23 @@ def device_count():
     return load().clothgpu_device_count()
 
 
+def bvh_build_topdown(tri, xyz, return_fallbacks=False):
+    """MakeBVHTopology_TopDown (bvh_aabb.cpp:294-313) through the C ABI (host code, no GPU needed): the reference's
+    own CNodeBVH array, (2*ntri-1) x {iroot, ichild0, ichild1}."""
+    lib = load()
+    tri = _ci(tri).ravel()
+    xyz = _cd(xyz).ravel()
+    ntri = tri.size // 3
+    nodes = np.empty((max(2 * ntri - 1, 1), 3), dtype=np.int32)
+    nfb = C.c_int(0)
+    n = lib.clothgpu_bvh_build_topdown(C.c_int(ntri), _ip(tri), C.c_int(xyz.size // 3), _dp(xyz), _ip(nodes),
+                                       C.c_int(nodes.shape[0]), C.byref(nfb))
+    if n < 0:
+        raise ClothGPUError("clothgpu error %d: %s" % (-n, lib.clothgpu_last_error().decode()))
+    nodes = np.ascontiguousarray(nodes[:n])
+    return (nodes, int(nfb.value)) if return_fallbacks else nodes
+
+
 def _ci(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 

@@ -277,53 +277,24 @@ bool CContactElement::operator<(const CContactElement& p) const {
 }
 
 // ------------------------------------------------------------------------------------------------ BVH
-namespace {
-int build_median(std::vector<CNodeBVH>& nodes, std::vector<int>& tris, int lo, int hi, int parent,
-                 const std::vector<double>& cen) {
-  const int id = (int)nodes.size();
-  nodes.push_back(CNodeBVH());
-  nodes[id].iroot = parent;
-  if (hi - lo == 1) {
-    nodes[id].ichild[0] = tris[lo];
-    nodes[id].ichild[1] = -1;
-    return id;
-  }
-  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
-  for (int k = lo; k < hi; k++)
-    for (int d = 0; d < 3; d++) {
-      mn[d] = std::min(mn[d], cen[(size_t)tris[k] * 3 + d]);
-      mx[d] = std::max(mx[d], cen[(size_t)tris[k] * 3 + d]);
-    }
-  int ax = 0;
-  for (int d = 1; d < 3; d++)
-    if (mx[d] - mn[d] > mx[ax] - mn[ax]) ax = d;
-  const int mid = (lo + hi) / 2;
-  std::nth_element(tris.begin() + lo, tris.begin() + mid, tris.begin() + hi, [&](int a, int b) {
-    const double ca = cen[(size_t)a * 3 + ax], cb = cen[(size_t)b * 3 + ax];
-    return ca < cb || (ca == cb && a < b);
-  });
-  const int c0 = build_median(nodes, tris, lo, mid, id, cen);
-  const int c1 = build_median(nodes, tris, mid, hi, id, cen);
-  nodes[id].ichild[0] = c0;
-  nodes[id].ichild[1] = c1;
-  return id;
-}
-}  // namespace
-
+// MakeBVHTopology_TopDown (bvh_aabb.cpp:294-313): the reference's own node array (libclothgpu's host builder,
+// csrc/bvhbuild.cu); where the reference crashes on exactly square grids it falls back to a longest-axis split
 int MakeBVHTopology_TopDown(const std::vector<int>& aTri, const std::vector<double>& aXYZ,
                             std::vector<CNodeBVH>& aNodeBVH) {
   const int ntri = (int)aTri.size() / 3;
   aNodeBVH.clear();
   if (ntri == 0) return -1;
-  std::vector<double> cen((size_t)ntri * 3);
-  for (int t = 0; t < ntri; t++)
-    for (int d = 0; d < 3; d++)
-      cen[(size_t)t * 3 + d] = (aXYZ[(size_t)aTri[t * 3] * 3 + d] + aXYZ[(size_t)aTri[t * 3 + 1] * 3 + d] +
-                                aXYZ[(size_t)aTri[t * 3 + 2] * 3 + d]) / 3.0;
-  std::vector<int> tris(ntri);
-  for (int t = 0; t < ntri; t++) tris[t] = t;
-  aNodeBVH.reserve(2 * (size_t)ntri);
-  return build_median(aNodeBVH, tris, 0, ntri, -1, cen);
+  std::vector<int> nodes((size_t)(2 * ntri - 1) * 3);
+  const int n = clothgpu_bvh_build_topdown(ntri, aTri.data(), (int)aXYZ.size() / 3, aXYZ.data(), nodes.data(),
+                                           2 * ntri - 1, nullptr);
+  if (n < 0) check(-n, "clothgpu_bvh_build_topdown");
+  aNodeBVH.resize(n);
+  for (int i = 0; i < n; i++) {
+    aNodeBVH[i].iroot = nodes[(size_t)i * 3];
+    aNodeBVH[i].ichild[0] = nodes[(size_t)i * 3 + 1];
+    aNodeBVH[i].ichild[1] = nodes[(size_t)i * 3 + 2];
+  }
+  return 0;
 }
 
 void BuildBoundingBoxChild_Prx(int, double delta, const std::vector<double>& aXYZ, const std::vector<int>& aTri,

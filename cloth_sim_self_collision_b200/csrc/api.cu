@@ -49,9 +49,13 @@ int run_resolve(Ctx* c, const clothgpu_params& p, int* applied, int* stats, bool
     app[s] = n[s] > 0;
     if (stats) stats[s * CLOTHGPU_NSTATS + 1] = n[s];
   }
-  phase_begin(c);
-  CG_CHECK(launch_impulse(c, x, v, delta, p.stiff_contact, dt, p.mass_point, 0));
-  phase_end(c, 6);
+  // (with a skipped detection the reference applies the proximity impulse to an empty set: the element list of an
+  // earlier pass must not be picked up)
+  if (delta * 0.5 > 0) {
+    phase_begin(c);
+    CG_CHECK(launch_impulse(c, x, v, delta, p.stiff_contact, dt, p.mass_point, 0));
+    phase_end(c, 6);
+  }
   // CCD impulse passes, :398-425
   int nactive = B;
   for (int itr = 0; itr < 5 && nactive > 0; itr++) {
@@ -355,8 +359,12 @@ int clothgpu_step_self_contact(clothgpu_ctx* c, const clothgpu_params* p, int ns
       CG_CHECK(rc);
       CG_CUDA(cudaEventRecord(c->ev_join, c->stream2));
     }
-    CG_CHECK(run_step_internal(c, *p, true, nullptr, iters.data()));
-    if (overlap) CG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    {
+      const int rc = run_step_internal(c, *p, true, nullptr, iters.data());
+      // join the second stream on every path: its work must not outlive a failed step
+      if (overlap) CG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+      CG_CHECK(rc);
+    }
     CG_CHECK(run_resolve(c, *p, applied.data(), stats, overlap));
     if (stats)
       for (int s = 0; s < c->B; s++) stats[s * CLOTHGPU_NSTATS + 0] = iters[s];

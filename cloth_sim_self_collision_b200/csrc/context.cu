@@ -543,7 +543,10 @@ int clothgpu_create(clothgpu_ctx** out, int device, int nscene, int np, int ntri
   }
   if (device >= 0) CG_CUDA(cudaSetDevice(device));
   clothgpu_ctx* c = new clothgpu_ctx();
-  CG_CUDA(cudaGetDevice(&c->device));
+  {
+    const cudaError_t e = cudaGetDevice(&c->device);
+    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__); }
+  }
   const int r = create_impl(c, nscene, np, ntri, nquad, tri, quad, bcflag, xyz0, crs_rowptr, crs_colidx, nnode,
                             bvh_nodes, edge_index, edge_array);
   if (r != CLOTHGPU_OK) {
@@ -596,6 +599,7 @@ long long clothgpu_buf_len(const clothgpu_ctx* c, int buf) {
 
 int clothgpu_write(clothgpu_ctx* c, int buf, int scene, const void* host, long long count) {
   if (!c || !host) { set_error("null argument"); return CLOTHGPU_ERR_ARG; }
+  cudaSetDevice(c->device);
   BufInfo bi;
   CG_CHECK(buf_info(c, buf, scene, &bi));
   if (buf == CLOTHGPU_BUF_LEAF_PAIRS) { set_error("LEAF_PAIRS is read-only"); return CLOTHGPU_ERR_ARG; }
@@ -616,6 +620,7 @@ int clothgpu_write(clothgpu_ctx* c, int buf, int scene, const void* host, long l
 
 int clothgpu_read(clothgpu_ctx* c, int buf, int scene, void* host, long long count) {
   if (!c || !host) { set_error("null argument"); return CLOTHGPU_ERR_ARG; }
+  cudaSetDevice(c->device);
   BufInfo bi;
   CG_CHECK(buf_info(c, buf, scene, &bi));
   if (count < 0 || count > bi.count) { set_error("count exceeds buffer length"); return CLOTHGPU_ERR_ARG; }
@@ -636,6 +641,7 @@ int clothgpu_read(clothgpu_ctx* c, int buf, int scene, void* host, long long cou
 
 int clothgpu_upload_state(clothgpu_ctx* c, int scene, const double* xyz, const double* uvw) {
   if (!c || !xyz || !uvw || scene < 0 || scene >= c->B) { set_error("bad argument"); return CLOTHGPU_ERR_ARG; }
+  cudaSetDevice(c->device);
   CG_CUDA(cudaMemcpyAsync(c->xyz + (long long)scene * c->ndof, xyz, sizeof(double) * c->ndof, cudaMemcpyHostToDevice, c->stream));
   CG_CUDA(cudaMemcpyAsync(c->uvw + (long long)scene * c->ndof, uvw, sizeof(double) * c->ndof, cudaMemcpyHostToDevice, c->stream));
   CG_CUDA(cudaStreamSynchronize(c->stream));
@@ -643,6 +649,7 @@ int clothgpu_upload_state(clothgpu_ctx* c, int scene, const double* xyz, const d
 }
 int clothgpu_download_state(clothgpu_ctx* c, int scene, double* xyz, double* uvw) {
   if (!c || !xyz || !uvw || scene < 0 || scene >= c->B) { set_error("bad argument"); return CLOTHGPU_ERR_ARG; }
+  cudaSetDevice(c->device);
   CG_CUDA(cudaMemcpyAsync(xyz, c->xyz + (long long)scene * c->ndof, sizeof(double) * c->ndof, cudaMemcpyDeviceToHost, c->stream));
   CG_CUDA(cudaMemcpyAsync(uvw, c->uvw + (long long)scene * c->ndof, sizeof(double) * c->ndof, cudaMemcpyDeviceToHost, c->stream));
   CG_CUDA(cudaStreamSynchronize(c->stream));
@@ -673,18 +680,21 @@ int clothgpu_set_scene_gravity(clothgpu_ctx* c, int scene, const double* g) {
 
 int clothgpu_synchronize(clothgpu_ctx* c) {
   if (!c) { set_error("null context"); return CLOTHGPU_ERR_ARG; }
+  cudaSetDevice(c->device);
   CG_CUDA(cudaStreamSynchronize(c->stream));
   return CLOTHGPU_OK;
 }
 
 int clothgpu_timer_start(clothgpu_ctx* c) {
   if (!c) { set_error("null context"); return CLOTHGPU_ERR_ARG; }
+  cudaSetDevice(c->device);
   CG_CUDA(cudaStreamSynchronize(c->stream));
   CG_CUDA(cudaEventRecord(c->ev0, c->stream));
   return CLOTHGPU_OK;
 }
 int clothgpu_timer_stop(clothgpu_ctx* c, float* ms) {
   if (!c || !ms) { set_error("null argument"); return CLOTHGPU_ERR_ARG; }
+  cudaSetDevice(c->device);
   CG_CUDA(cudaEventRecord(c->ev1, c->stream));
   CG_CUDA(cudaEventSynchronize(c->ev1));
   CG_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
@@ -700,6 +710,7 @@ int clothgpu_set_profiling(clothgpu_ctx* c, int on) {
 }
 int clothgpu_set_kernel_timing(clothgpu_ctx* c, int on) {
   if (!c) { set_error("null context"); return CLOTHGPU_ERR_ARG; }
+  cudaSetDevice(c->device);
   CG_CUDA(cudaStreamSynchronize(c->stream));
   c->ktiming = on != 0;
   c->ktimes.clear();

@@ -282,7 +282,8 @@ int fetch_counters(Ctx* c);  // cnt -> h_cnt, synchronous
 int ensure_scratch(Ctx* c, size_t bytes);
 int ensure_sort_capacity(Ctx* c, long long n);
 int grow_queues(Ctx* c, int overflow_bits);
-int set_active(Ctx* c, const int* active);  // per-scene participation flags (null: all scenes)
+int set_active(Ctx* c, const int* active);
+int bvh_build_topdown_host(int ntri, const int* tri, int np, const double* xyz, std::vector<int>& nodes, int* nfallback);  // per-scene participation flags (null: all scenes)
 
 }  // namespace cg
 

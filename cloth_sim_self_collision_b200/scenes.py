@@ -120,6 +120,15 @@ def jittered_rest(sc, amplitude_frac=0.2, seed=88172645463325252):
     return x.ravel()
 
 
+def reference_bvh(sc, jitter=True):
+    """The BVH topology the reference's own builder (MakeBVHTopology_TopDown, bvh_aabb.cpp:294-313) produces, from
+    libclothgpu's host builder (csrc/bvhbuild.cu; node-for-node identical, tests/test_bvh_builder.py).  jitter=True
+    feeds it the seeded-jitter copy of the rest positions: on that input the
+    reference's builder itself survives square grids, so the tree is exactly the one the reference would use."""
+    from . import clothgpu as G
+    return G.bvh_build_topdown(sc["tri"], jittered_rest(sc) if jitter else sc["xyz0"])
+
+
 def median_split_bvh(sc, xyz=None):
     """A balanced BVH *topology* over the triangles (median split of the centroids along the longest axis).
 

@@ -120,6 +120,15 @@ int clothgpu_create(clothgpu_ctx** out, int device, int nscene, int np, int ntri
                     const int* edge_array);
 void clothgpu_destroy(clothgpu_ctx* ctx);
 
+/* MakeBVHTopology_TopDown, bvh_aabb.cpp:294-313 (MakeTriSurTri :109-138, DevideTriAryConnex :156-290): BVH topology
+ * over the triangles, node for node the array the reference builds (same splits, same list orders, same numbering)
+ * wherever the reference survives; where it crashes (bvh_aabb.cpp:238, exactly square sub-grids) the split falls back
+ * to the longest axis with ties resolved x,y,z and *nfallback (may be NULL) counts those nodes.  Host code, no GPU
+ * needed.  nodes: cap_nodes x {iroot, ichild0, ichild1}, cap_nodes >= 2*ntri-1.  Returns the node count, or
+ * -CLOTHGPU_ERR_* on failure. */
+int clothgpu_bvh_build_topdown(int ntri, const int* tri, int np, const double* xyz, int* nodes, int cap_nodes,
+                               int* nfallback);
+
 int clothgpu_nscene(const clothgpu_ctx* ctx);
 /* element count of a buffer for one scene, in units of its type (doubles or ints) */
 long long clothgpu_buf_len(const clothgpu_ctx* ctx, int buf);

@@ -1602,6 +1602,27 @@ void orc_sim_step_internal(void* h, double dt, double lambda, double myu, double
   free(b); free(x);
 }
 
+/* StepTime_InternalDynamics, solve_internal_sparse.h:185-253: the same assembly, solved by Solve_CG (1e-4 / 1000) */
+void orc_sim_step_internal_cg(void* h, double dt, double lambda, double myu, double stiff_bend, const double* gravity,
+                              double mass_point, double stiff_contact, double clearance, int col_kind,
+                              const double* col_par, double* conv_ratio, int* iteration) {
+  sim_state* s = (sim_state*)h;
+  const int ndof = s->np * 3;
+  double* b = (double*)malloc(sizeof(double) * (size_t)ndof);
+  double* x = (double*)malloc(sizeof(double) * (size_t)ndof);
+  double cr = 1.0e-4;
+  int it = 1000, i;
+  orc_assemble(s->np, s->ntri, s->nquad, s->tri, s->quad, s->bc, s->xyz0, s->xyz, s->uvw, s->rowptr, s->colidx, dt,
+               lambda, myu, stiff_bend, gravity, mass_point, stiff_contact, clearance, col_kind, col_par, s->valDia,
+               s->valCrs, b);
+  orc_cg(s->np, s->rowptr, s->colidx, s->valDia, s->valCrs, b, x, &cr, &it);
+  for (i = 0; i < ndof; i++) s->xyz[i] += x[i];
+  for (i = 0; i < ndof; i++) s->uvw[i] = x[i] / dt;
+  if (conv_ratio) *conv_ratio = cr;
+  if (iteration) *iteration = it;
+  free(b); free(x);
+}
+
 /* GetIntermidiateVelocityContactResolved, self_collision_cloth.cpp:355-456.  stats as in oracle/ref_shim.cpp */
 int orc_sim_resolve_contacts(void* h, double* uvw, const double* xyz_prev, double dt, double clearance,
                              double mass_point, double stiffness, int* stats) {

@@ -80,6 +80,9 @@ void orc_sim_get_state(void* h, double* xyz, double* uvw);
 void orc_sim_step_internal(void* h, double dt, double lambda, double myu, double stiff_bend, const double* gravity,
                            double mass_point, double stiff_contact, double clearance, int col_kind,
                            const double* col_par, double* conv_ratio, int* iteration);
+void orc_sim_step_internal_cg(void* h, double dt, double lambda, double myu, double stiff_bend, const double* gravity,
+                           double mass_point, double stiff_contact, double clearance, int col_kind,
+                           const double* col_par, double* conv_ratio, int* iteration);
 int orc_sim_resolve_contacts(void* h, double* uvw, const double* xyz_prev, double dt, double clearance,
                              double mass_point, double stiffness, int* stats);
 void orc_sim_step_self_contact(void* h, double dt, double lambda, double myu, double stiff_bend, const double* gravity,

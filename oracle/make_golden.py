@@ -100,6 +100,20 @@ def internal(ref):
     print("traj_internal17: iters", its[:10])
 
 
+def bvh_hashes(ref):
+    """sha256 of the CNodeBVH arrays MakeBVHTopology_TopDown builds (tests/test_bvh_builder.py::GOLDEN_CASES)."""
+    import hashlib
+    import json
+    from tests.test_bvh_builder import GOLDEN_CASES, _mesh
+    out = {}
+    for case in GOLDEN_CASES:
+        tri, xyz = _mesh(case)
+        nodes = ref.bvh_build(tri, xyz)
+        out["%d_%d_%s" % case] = hashlib.sha256(np.ascontiguousarray(nodes, dtype=np.int32).tobytes()).hexdigest()
+    json.dump(out, open(os.path.join(OUT, "bvh_hashes.json"), "w"), indent=1, sort_keys=True)
+    print("bvh_hashes:", len(out), "trees")
+
+
 if __name__ == "__main__":
     ref = O.load_ref()
     assert ref is not None, "build oracle/_ref first (make -C oracle ref)"
@@ -107,3 +121,4 @@ if __name__ == "__main__":
     phases(ref)
     trajectory(ref)
     internal(ref)
+    bvh_hashes(ref)

@@ -325,6 +325,14 @@ class Sim:
                                          _dp(p.col_par), C.byref(cr), C.byref(it))
         return cr.value, it.value
 
+    def step_internal_cg(self, p):
+        """StepTime_InternalDynamics (solve_internal_sparse.h:185-253)"""
+        cr = _d(0); it = _i(0)
+        self.lib._f("sim_step_internal_cg")(self.h, _d(p.dt), _d(p.lam), _d(p.myu), _d(p.stiff_bend), _dp(p.gravity),
+                                            _d(p.mass_point), _d(p.stiff_contact), _d(p.clearance), _i(p.col_kind),
+                                            _dp(p.col_par), C.byref(cr), C.byref(it))
+        return cr.value, it.value
+
     def resolve_contacts(self, uvw, xyz_prev, p):
         uvw = _cd(uvw).copy()
         stats = np.zeros(NSTATS, dtype=np.int32)

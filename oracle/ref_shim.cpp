@@ -572,6 +572,24 @@ void ref_sim_step_internal(void* h, double dt, double lambda, double myu, double
   }
 }
 
+// StepTime_InternalDynamics (solve_internal_sparse.h:185-253): the unpreconditioned CG variant
+void ref_sim_step_internal_cg(void* h, double dt, double lambda, double myu, double stiff_bend, const double* gravity,
+                              double mass_point, double stiff_contact, double clearance, int col_kind,
+                              const double* col_par, double* conv_ratio, int* iteration) {
+  RefSim* s = (RefSim*)h;
+  CoutCapture cap;
+  StepTime_InternalDynamics(s->aXYZ, s->aUVW, s->mat_A, s->aXYZ0, s->aBC, s->aTri, s->aQuad, dt, lambda, myu, stiff_bend,
+                            gravity, mass_point, stiff_contact, clearance, pick_collider(col_kind, col_par));
+  std::string out = cap.ss.str();
+  std::vector<int> it;
+  parse_ints(out, "iteration:", it);
+  if (iteration) *iteration = it.empty() ? -1 : it[0];
+  if (conv_ratio) {
+    size_t p = out.find("conv_ratio:");
+    *conv_ratio = p == std::string::npos ? -1.0 : std::atof(out.c_str() + p + 11);
+  }
+}
+
 // stats layout (ints): [0]=PCG iteration, [1]=#proximity elems, [2]=#CCD impulse passes run, [3]=#RIZ rounds run,
 // [4]=is_impulse_applied, [5]=last "NNode In RIZ", [8..8+5)=CCD elems per impulse pass, [16..16+100)=CCD elems per RIZ round
 enum { REF_NSTATS = 128 };

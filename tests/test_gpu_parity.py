@@ -254,10 +254,10 @@ def test_contact_pipeline_small_folded(oracle, sc_contact):
 
 
 def _scene_with_bvh(oracle, nx, nz):
-    """BVH topology: any valid binary tree over the triangles is an input shared by both sides; build a balanced
-    median-split tree here so that the test does not need the reference builder."""
+    """BVH topology: the reference builder's tree (MakeBVHTopology_TopDown on the seeded-jitter rest copy) from the
+    product's host builder, which tests/test_bvh_builder.py pins node for node to the reference."""
     sc = S.square_cloth_xz(nx, nz, 0.1, S.SELF_CONTACT["areal_density"])
-    sc["bvh"] = S.median_split_bvh(sc)
+    sc["bvh"] = S.reference_bvh(sc)
     return sc
 
 
@@ -371,7 +371,7 @@ def test_large_scene_properties(oracle):
     assembles is symmetric block-wise, A x matches a float128-free re-evaluation on sampled rows via the oracle's
     SpMV on the GPU's own matrix, ILU solve inverts the factors, and contact sets are sorted and unique."""
     sc = S.config3_256()
-    sc["bvh"] = S.median_split_bvh(sc)
+    sc["bvh"] = S.reference_bvh(sc)
     p = T.params_for(sc, S.SELF_CONTACT)
     x, v = T.folded_state(sc, gap=0.006, vel=3.0)
     g = G.ClothGPU(sc)
@@ -487,7 +487,7 @@ def test_config4_crumpled_512(oracle):
     """BASELINE.json configs[3]: 512 x 512 crumpled cloth.  Factor and triangular solves bit-exact on the GPU's own
     matrix (72 / 64 strips instead of 26), and one full self-contact step against the oracle."""
     sc = S.config4_512()
-    sc["bvh"] = S.median_split_bvh(sc)
+    sc["bvh"] = S.reference_bvh(sc)
     p = T.params_for(sc, S.SELF_CONTACT)
     x, v = S.crumpled_state(sc)
     _linear_chain_vs_oracle(oracle, sc, p, x, v)
@@ -509,6 +509,8 @@ def test_tiny_and_ragged_scenes(oracle):
     single strip, rows without any dependency) and a 3 x 9 strip, three self-contact steps each."""
     for nx, nz in ((1, 1), (1, 2), (2, 8)):
         sc = S.square_cloth_xz(nx, nz, 0.1, S.SELF_CONTACT["areal_density"])
+        # any valid binary tree is a legal input of the per-step path: a median-split tree here, the reference
+        # builder's tree (S.reference_bvh) everywhere else
         sc["bvh"] = S.median_split_bvh(sc)
         p = T.params_for(sc, S.SELF_CONTACT)
         g = G.ClothGPU(sc)
@@ -545,7 +547,7 @@ def test_pinned_host_buffers_round_trip():
     """clothgpu_alloc_host buffers (page-locked) through upload_state / download_state(out=...): same bytes as the
     pageable path, and the step run from them gives the same state."""
     sc = S.square_cloth_xz(9, 7, 0.1)
-    sc["bvh"] = S.median_split_bvh(sc)
+    sc["bvh"] = S.reference_bvh(sc)
     rng = np.random.default_rng(3)
     x0 = sc["xyz0"].reshape(-1) + 1e-3 * rng.standard_normal(sc["np"] * 3)
     v0 = 1e-2 * rng.standard_normal(sc["np"] * 3)
@@ -589,3 +591,90 @@ def test_measurement_switches_do_not_change_results(oracle, monkeypatch):
     for env, ((x, v), st) in zip(variants[1:], results[1:]):
         assert np.array_equal(st, bst), env
         assert np.array_equal(x, bx) and np.array_equal(v, bv), env
+
+
+def test_step_internal_cg_vs_oracle(oracle):
+    """clothgpu_step_internal_cg = StepTime_InternalDynamics (solve_internal_sparse.h:185-253, Solve_CG 1e-4 / 1000),
+    teacher forced: same iteration counts, positions to rounding, velocities to the amplification of the dot-product
+    rounding by the unpreconditioned iteration (the reference stops at a 1e-4 residual itself)."""
+    sc = S.square_cloth_xy(12, 1.0)
+    p = T.params_for(sc, S.INTERNAL_CLOTH, col_kind=2, col_par=(0.1, 0.5, -0.8, 0.3))
+    g = G.ClothGPU(sc, with_bvh=False)
+    sim = oracle.sim(sc)
+    x, v = sim.get_state()
+    for step in range(6):
+        g.upload_state(x, v)
+        cr, it = g.step_internal_cg(p)
+        ocr, oit = sim.step_internal_cg(p)
+        gx, gv = g.download_state()
+        x, v = sim.get_state()
+        assert int(it[0]) == oit, (step, it, oit)
+        assert abs(cr[0] - ocr) <= 1.0e-2 * ocr
+        assert rel_err(gx, x) < 1.0e-8 and rel_err(gv, v) < 1.0e-5, (step, rel_err(gx, x), rel_err(gv, v))
+    assert oit > 3
+    g.close()
+
+
+def test_collider_sphere_inside(oracle):
+    """CLOTHGPU_COLLIDER_SPHERE_INSIDE (the container sphere of self_contact_sparse/main.cpp:117-133): assembled
+    matrix / right-hand side bit-exact on a state that touches the wall, then free-running implicit steps."""
+    sc = S.square_cloth_xy(12, 1.0)
+    p = T.params_for(sc, S.INTERNAL_CLOTH, col_kind=3, col_par=(0.5, 0.5, -0.2, 0.9))
+    x, v = T.wavy_state(sc)
+    g = G.ClothGPU(sc, with_bvh=False)
+    g.upload_state(x, v)
+    g.assemble(p)
+    dia, crs, b = oracle.assemble(sc, x, v, p)
+    # the wall must be active for some vertices, or the test says nothing about the collider
+    p_none = T.params_for(sc, S.INTERNAL_CLOTH, col_kind=0)
+    assert not np.array_equal(oracle.assemble(sc, x, v, p_none)[0], dia)
+    assert np.array_equal(g.read(G.BUF_VAL_DIA), dia)
+    assert np.array_equal(g.read(G.BUF_VAL_CRS), crs)
+    assert np.array_equal(g.read(G.BUF_VEC_R), b)
+    sim = oracle.sim(sc)
+    sim.set_state(x, v)
+    g.upload_state(x, v)
+    for step in range(5):
+        it = int(g.step_internal(p)[0])
+        assert it == int(sim.step_internal(p)[1])
+    gx, gv = g.download_state()
+    ox, ov = sim.get_state()
+    assert rel_err(gx, ox) < 1.0e-9 and rel_err(gv, ov) < 1.0e-7
+    g.close()
+
+
+def test_config3_contact_regime_vs_oracle(oracle):
+    """The benchmarked workload itself (BASELINE.json configs[2]: 256 x 256, reference BVH tree, from rest): the GPU
+    trajectory is taken into the self-contact regime and single steps there (58: first CCD passes; 66: thousands of
+    contact elements, five CCD passes, impact zones) are teacher forced on the C restatement AND on the compiled
+    reference (oracle/_ref, when it travelled): statistics and per-pass element counts exact, X / V to 1e-9."""
+    from oracle import oracle_py as O
+    sc = S.config3_256()
+    sc["bvh"] = S.reference_bvh(sc)
+    p = T.params_for(sc, S.SELF_CONTACT)
+    g = G.ClothGPU(sc)
+    libs = [("oracle", oracle)]
+    ref = O.load_ref()
+    if ref is not None:
+        libs.append(("reference", ref))
+    done = 0
+    seen = []
+    for target in (58, 66):
+        g.step_self_contact(p, target - 1 - done)
+        done = target - 1
+        x, v = g.download_state()
+        st = g.step_self_contact(p)[0]
+        done += 1
+        gx, gv = g.download_state()
+        seen.append(st[:5].copy())
+        for name, lib in libs:
+            sim = lib.sim(sc)
+            sim.set_state(x, v)
+            ost = sim.step_self_contact(p)
+            ox, ov = sim.get_state()
+            assert np.array_equal(st[:5], ost[:5]), (name, target, st[:5], ost[:5])
+            assert np.array_equal(st[8:116], ost[8:116]), (name, target)
+            assert rel_err(gx, ox) < RTOL and rel_err(gv, ov) < RTOL, (name, target, rel_err(gx, ox), rel_err(gv, ov))
+    print("config 3 contact regime stats (pcg, prox, ccd passes, riz rounds, applied):", seen)
+    assert seen[1][1] > 1000 and seen[1][2] >= 3, "step 66 must be deep in the contact regime"
+    g.close()

@@ -238,3 +238,20 @@ def test_internal_cloth_trajectory_bit_exact(ref, oracle):
     xb, vb = so.get_state()
     assert np.array_equal(xa, xb) and np.array_equal(va, vb)
     assert np.abs(xa - sc["xyz0"]).max() > 0.1
+
+
+def test_internal_cloth_cg_trajectory_bit_exact(ref, oracle):
+    """StepTime_InternalDynamics (solve_internal_sparse.h:185-253, the unpreconditioned Solve_CG variant) and the
+    SPHERE_INSIDE collider of self_contact_sparse/main.cpp:117-133 inside a step."""
+    sc = S.square_cloth_xy(12, 1.0)
+    for kind, par in ((2, (0.1, 0.5, -0.8, 0.3)), (3, (0.5, 0.5, -0.2, 0.9))):
+        p = T.params_for(sc, S.INTERNAL_CLOTH, col_kind=kind, col_par=par)
+        sa, so = ref.sim(sc), oracle.sim(sc)
+        for step in range(6):
+            ra = sa.step_internal_cg(p)
+            rb = so.step_internal_cg(p)
+            assert ra[1] == rb[1] and abs(ra[0] - rb[0]) <= 1e-5 * rb[0]
+        xa, va = sa.get_state()
+        xb, vb = so.get_state()
+        assert np.array_equal(xa, xb) and np.array_equal(va, vb)
+        assert ra[1] > 3

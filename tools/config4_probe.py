@@ -10,7 +10,7 @@ sys.path.insert(0, ROOT)
 from cloth_sim_self_collision_b200 import clothgpu as G, scenes as S  # noqa: E402
 
 sc = S.config4_512()
-sc["bvh"] = S.median_split_bvh(sc)
+sc["bvh"] = S.reference_bvh(sc)
 c = dict(S.SELF_CONTACT)
 p = G.make_params(c["dt"], c["lam"], c["myu"], c["stiff_bend"], c["gravity"], sc["mass_point"], c["stiff_contact"],
                   c["clearance"], c["col_kind"], c["col_par"])

@@ -12,7 +12,7 @@ from cloth_sim_self_collision_b200 import clothgpu as G, scenes as S  # noqa: E4
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 70
 sc = S.square_cloth_xz(n - 1, n - 1, 0.1, S.SELF_CONTACT["areal_density"])
-sc["bvh"] = S.median_split_bvh(sc)
+sc["bvh"] = S.reference_bvh(sc)
 c = dict(S.SELF_CONTACT)
 p = G.make_params(c["dt"], c["lam"], c["myu"], c["stiff_bend"], c["gravity"], sc["mass_point"], c["stiff_contact"],
                   c["clearance"], c["col_kind"], c["col_par"])
