@@ -326,8 +326,9 @@ def _parity(g, G, sc, c, p, x0, v0, gravity):
     rx = float(np.abs(gx - ox).max() / max(np.abs(ox).max(), 1e-300))
     rv = float(np.abs(gv - ov).max() / max(np.abs(ov).max(), 1e-300))
     eq = bool(np.array_equal(st[:5], ost[:5]) and np.array_equal(st[8:116], ost[8:116]))
-    rep = {"checker": kind, "stats_equal": eq, "rel_x": rx, "rel_v": rv, "tol": 1.0e-9,
-           "stats": [int(k) for k in st[:5]], "ok": bool(eq and rx < 1.0e-9 and rv < 1.0e-9)}
+    bit = bool(np.array_equal(gx, ox) and np.array_equal(gv, ov))
+    rep = {"checker": kind, "stats_equal": eq, "bit_identical": bit, "rel_x": rx, "rel_v": rv, "tol": 0.0,
+           "stats": [int(k) for k in st[:5]], "ok": bool(eq and bit)}
     return rep, cms, sim, cp
 
 

@@ -451,6 +451,15 @@ static int create_impl(Ctx* c, int nscene, int np, int ntri, int nquad, const in
   c->gravity_override.assign((size_t)B * 3, std::numeric_limits<double>::quiet_NaN());
   c->npartial = 296;
   CG_CHECK(dev_zeros(&c->scal, B * NSCAL)); CG_CHECK(dev_zeros(&c->partials, B * c->npartial * 4));
+  c->xd_nch = div_up(c->ndof, 256);
+  CG_CHECK(dev_zeros(&c->xd_tsum, (long long)B * c->xd_nch));
+  {
+    unsigned char* st = nullptr;
+    CG_CHECK(dev_zeros(&st, (long long)B * c->xd_nch * 32));
+    c->xd_stat = st;
+    const char* dm = getenv("CLOTHGPU_DOT");
+    c->exact_dot = !(dm && strcmp(dm, "tree") == 0);
+  }
   CG_CHECK(dev_zeros(&c->cnt, B * NCNT));
   CG_CUDA(cudaMallocHost((void**)&c->h_cnt, sizeof(int) * NCNT * B));
   CG_CUDA(cudaMallocHost((void**)&c->h_scal, sizeof(double) * NSCAL * B));
@@ -565,7 +574,7 @@ void clothgpu_destroy(clothgpu_ctx* c) {
                   c->lev_f_rows, c->lev_b_ptr, c->lev_b_rows, c->op_ptr, c->ops, c->nodes, c->node_tri, c->pre, c->internal_list,
                   c->edge_index, c->edge_array, c->xyz, c->uvw, c->xyz_prev, c->uvw0, c->valDia, c->valCrs, c->iluDia,
                   c->iluCrs, c->vec_r, c->vec_x, c->vec_p, c->vec_z, c->tri_dW, c->tri_ddW, c->quad_dW, c->col_table,
-                  c->gravity, c->boxes, c->refit_flag, c->uvw_snap, c->vdirty, c->ndirty, c->scal, c->partials, c->cnt, c->zone, c->zone_label,
+                  c->gravity, c->boxes, c->refit_flag, c->uvw_snap, c->vdirty, c->ndirty, c->scal, c->partials, c->xd_tsum, c->xd_stat, c->cnt, c->zone, c->zone_label,
                   c->scratch, c->sort_keys, c->sort_keys2, c->sort_vals, c->sort_vals2};
   for (void* p : ptrs) cudaFree(p);
   cudaFree(c->tri_dbg_buf);

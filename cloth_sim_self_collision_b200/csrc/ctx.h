@@ -178,6 +178,11 @@ struct Ctx {
   int trav_coop = 0;            // max scenes for which the fused (cooperative) traversal is co-resident; 0 = off
   int trav_sms = 148;
   double *scal = nullptr, *partials = nullptr;
+  // exact (serial-order) dot products, linsolve.cu k_xdot_*: chunk sums and per-chunk integer statistics
+  bool exact_dot = true;  // CLOTHGPU_DOT=tree selects the tree reduction (deterministic, not the reference's order)
+  int xd_nch = 0;
+  double* xd_tsum = nullptr;
+  void* xd_stat = nullptr;
   int* cnt = nullptr;
   int* zone = nullptr;    // union-find parent per vertex, -1 = not a member
   int* zone_label = nullptr;

@@ -68,7 +68,8 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
 }
 
 // what the last block does with the finished sum (Solve_PCG / Solve_CG scalar bookkeeping, ilu_sparse.cpp:640-705)
-enum { POST_STORE = 0, POST_PCG_INIT = 1, POST_PCG_CHECK = 2, POST_FINAL_CONV = 3, POST_CG_CHECK = 4 };
+enum { POST_STORE = 0, POST_PCG_INIT = 1, POST_PCG_CHECK = 2, POST_FINAL_CONV = 3, POST_CG_CHECK = 4,
+       POST_SKIP = 5 };  // POST_SKIP: k_update_xr without its fused reduction (the exact dot follows)
 
 struct DotArgs {
   int n;
@@ -145,6 +146,222 @@ __global__ void __launch_bounds__(256) k_dot(DotArgs A, const double* __restrict
   reduce_finish(v, A, partials + (size_t)s * npartial, scal + s * NSCAL, c, sm);
 }
 
+// ------------------------------------------------------------------------------------------------ exact serial dot
+// InnerProduct (matrix_square_sparse.cpp:313-324) is a serial loop, r += a[i]*b[i], and every PCG scalar derives from
+// it; the self-collision response downstream is chaotic (a 1e-16 relative change of the velocities entering
+// GetIntermidiateVelocityContactResolved moves its output by 1e-2, measured on the reference itself), so whole steps
+// only match the reference if the dot products do, bit for bit.  The three kernels below return exactly the value of
+// that serial loop, in parallel:
+//   while the running sum s stays inside one binade [2^e, 2^(e+1)) with ulp u, fl(s + p) = s + u*rint(p/u) (unless p/u
+//   is an exact tie), i.e. the rounded additions are EXACT integer additions in units of u and therefore associative.
+//   k_xdot_partial : approximate (tree) sums per chunk of 256 products -> predicted binade of s at each chunk start
+//   k_xdot_stats   : per chunk, in units of the predicted u: integer total K, min / max of the integer prefix sums,
+//                    a "bad" flag (tie, overflow)
+//   k_xdot_walk    : one warp per scene walks the chunks 32 at a time (integer scan); a chunk is accepted when the
+//                    exact s at its start is in the predicted binade and S + prefix stays strictly inside
+//                    (2^52, 2^53) throughout; any other chunk (a binade crossing, a tie, the first chunk: ~15 of 768
+//                    at 256^2) is redone 32 elements at a time with the true s, element by element where needed.
+// No approximation anywhere: a chunk is either provably exact or recomputed.
+struct XChunk {
+  long long K, pmin, pmax;
+  int e, bad;
+};
+static_assert(sizeof(XChunk) == 32, "XChunk layout");
+enum { XD_CHUNK = 256 };
+
+__device__ __forceinline__ bool xd_binade(double s, int& e) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(s) & 0x7fffffffffffffffULL;
+  const int be = (int)(bits >> 52);
+  if (be == 0 || be == 0x7ff) return false;  // zero, subnormal, inf, nan: no binade arithmetic
+  e = be - 1023;
+  return e >= -960;  // 2^(e-52) and its inverse are normal powers of two
+}
+__device__ __forceinline__ double xd_pow2(int k) { return __longlong_as_double((long long)(1023 + k) << 52); }
+__device__ __forceinline__ long long xd_scan_incl(long long v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+// S + [lo, hi] strictly inside the binade of sign(s)
+__device__ __forceinline__ bool xd_inside(bool positive, long long S, long long lo, long long hi) {
+  const long long L = (1LL << 52) + 1, H = (1LL << 53) - 1;
+  return positive ? (S + lo >= L && S + hi <= H) : (S + lo >= -H && S + hi <= -L);
+}
+
+__global__ void __launch_bounds__(256) k_xdot_partial(int n, int nch, const double* __restrict__ a,
+                                                       const double* __restrict__ b, double* __restrict__ tsum,
+                                                       const int* __restrict__ cnt, int skip_done) {
+  const int s = blockIdx.y;
+  if (skip_done && cnt[s * NCNT + CNT_PCG_DONE]) return;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= nch) return;
+  const double* as = a + (size_t)s * n;
+  const double* bs = b + (size_t)s * n;
+  double v = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int i = c * XD_CHUNK + j * 32 + lane;
+    if (i < n) v += as[i] * bs[i];
+  }
+  v = warp_sum(v);
+  if (lane == 0) tsum[(size_t)s * nch + c] = v;
+}
+
+__global__ void __launch_bounds__(256) k_xdot_stats(int n, int nch, const double* __restrict__ a,
+                                                     const double* __restrict__ b, const double* __restrict__ tsum,
+                                                     XChunk* __restrict__ st, const int* __restrict__ cnt, int skip_done) {
+  __shared__ double sm[8];
+  __shared__ double base;
+  const int s = blockIdx.y;
+  if (skip_done && cnt[s * NCNT + CNT_PCG_DONE]) return;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 8, c = c0 + w;
+  const double* ts = tsum + (size_t)s * nch;
+  // approximate value of the running sum at the start of this CTA's first chunk
+  double acc = 0;
+  for (int k = threadIdx.x; k < c0; k += 256) acc += ts[k];
+  const double tot = block_sum(acc, sm);
+  if (threadIdx.x == 0) base = tot;
+  __syncthreads();
+  if (c >= nch) return;
+  double start = base;
+  for (int k = c0; k < c; k++) start += ts[k];
+  XChunk out;
+  out.K = 0; out.pmin = 0; out.pmax = 0; out.e = 0; out.bad = 1;
+  int e;
+  if (xd_binade(start, e)) {
+    out.e = e;
+    const double scale = xd_pow2(-(e - 52));
+    const double* as = a + (size_t)s * n;
+    const double* bs = b + (size_t)s * n;
+    // lane l owns the 8 consecutive elements c*256 + l*8 .. +7: local integer prefix, then a scan over the lanes
+    long long run = 0, lmin = 0, lmax = 0;
+    bool bad = false;
+    const int i0 = c * XD_CHUNK + lane * 8;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int i = i0 + j;
+      const double p = i < n ? as[i] * bs[i] : 0.0;
+      const double q = p * scale;
+      const double kf = rint(q);
+      if (!(fabs(q) < 9007199254740992.0) || fabs(q - kf) == 0.5) bad = true;
+      else run += (long long)kf;
+      lmin = min(lmin, run);
+      lmax = max(lmax, run);
+    }
+    const long long inc = xd_scan_incl(run, lane);
+    const long long exc = inc - run;
+    long long mn = exc + lmin, mx = exc + lmax;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    const bool anybad = __any_sync(0xffffffffu, bad);
+    out.K = __shfl_sync(0xffffffffu, inc, 31);
+    out.pmin = mn;
+    out.pmax = mx;
+    out.bad = (anybad || mx - mn >= (1LL << 53)) ? 1 : 0;
+    if (out.bad) out.K = 0;
+  }
+  if (lane == 0) st[(size_t)s * nch + c] = out;
+}
+
+__global__ void __launch_bounds__(32) k_xdot_walk(DotArgs A, int nch, const double* __restrict__ a,
+                                                   const double* __restrict__ b, const XChunk* __restrict__ st,
+                                                   double* __restrict__ scal, int* __restrict__ cnt, int skip_done) {
+  const int s = blockIdx.x, lane = threadIdx.x;
+  int* cn = cnt + s * NCNT;
+  if (skip_done && cn[CNT_PCG_DONE]) return;
+  const int n = A.n;
+  const double* as = a + (size_t)s * n;
+  const double* bs = b + (size_t)s * n;
+  const XChunk* cs = st + (size_t)s * nch;
+  double sum = 0.0;
+  int pos = 0;
+  XChunk nx;
+  int nx_pos = -1;
+  while (pos < nch) {
+    const int c = pos + lane;
+    XChunk ch;
+    if (nx_pos == pos) ch = nx;
+    else if (c < nch) ch = cs[c];
+    else { ch.K = 0; ch.pmin = 0; ch.pmax = 0; ch.e = 0; ch.bad = 1; }
+    if (c >= nch) ch.bad = 1;
+    // speculative prefetch of the next group (used when all 32 chunks of this one are accepted)
+    nx_pos = pos + 32;
+    if (nx_pos + lane < nch) nx = cs[nx_pos + lane];
+    int e = 0;
+    const bool okbin = xd_binade(sum, e);
+    const long long Kl = ch.bad ? 0 : ch.K;
+    const long long inc = xd_scan_incl(Kl, lane);
+    bool ok = false;
+    long long S0 = 0;
+    if (okbin) {
+      S0 = (long long)(sum * xd_pow2(-(e - 52)));
+      if (!ch.bad && ch.e == e) ok = xd_inside(sum > 0, S0 + (inc - Kl), ch.pmin, ch.pmax);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    const int f = (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);
+    if (f > 0) {
+      const long long tot = __shfl_sync(0xffffffffu, inc, f - 1);
+      sum = (double)(S0 + tot) * xd_pow2(e - 52);
+    }
+    pos += f;
+    if (f < 32 && pos < nch) {
+      // ---- the chunk at pos is redone with the true running sum, 32 elements at a time
+      const int i0 = pos * XD_CHUNK;
+      double pr[8];
+#pragma unroll
+      for (int g = 0; g < 8; g++) {
+        const int i = i0 + g * 32 + lane;
+        pr[g] = i < n ? as[i] * bs[i] : 0.0;
+      }
+#pragma unroll 1
+      for (int g = 0; g < 8; g++) {
+        const int cntg = min(32, n - (i0 + g * 32));
+        if (cntg <= 0) break;
+        const double p = pr[g];
+        int j = 0;
+        while (j < cntg) {
+          int e2 = 0;
+          const bool okb = xd_binade(sum, e2);
+          int f2 = j;
+          if (okb) {
+            const double q = p * xd_pow2(-(e2 - 52));
+            const double kf = rint(q);
+            const bool mine = lane >= j && lane < cntg;
+            const bool valid = mine && fabs(q) < 9007199254740992.0 && fabs(q - kf) != 0.5;
+            const long long k = valid ? (long long)kf : 0;
+            const long long inc2 = xd_scan_incl(k, lane);
+            const long long S2 = (long long)(sum * xd_pow2(-(e2 - 52)));
+            const bool okl = lane < j || (valid && xd_inside(sum > 0, S2 + inc2, 0, 0));
+            const unsigned m2 = __ballot_sync(0xffffffffu, okl);
+            f2 = (m2 == 0xffffffffu) ? 32 : (__ffs(~m2) - 1);
+            if (f2 > cntg) f2 = cntg;
+            if (f2 > j) {
+              const long long tot2 = __shfl_sync(0xffffffffu, inc2, f2 - 1);
+              sum = (double)(S2 + tot2) * xd_pow2(e2 - 52);
+            }
+          }
+          j = f2;
+          if (j < cntg) {  // one true floating-point addition, exactly what the serial loop does
+            const double pj = __shfl_sync(0xffffffffu, p, j);
+            sum = sum + pj;
+            j++;
+          }
+        }
+      }
+      pos++;
+    }
+  }
+  if (lane == 0) dot_post(A, sum, scal + s * NSCAL, cn);
+}
+
 // PCG update (ilu_sparse.cpp:674-682): alpha = rPr / pAp; r += (-alpha) Ap; x += alpha p; then r.r
 // CG update (matrix_square_sparse.cpp:378-386): alpha = sq / pAp; x += alpha p; r += (-alpha) Ap
 __global__ void __launch_bounds__(256) k_update_xr(DotArgs A, int rpr_slot, const double* __restrict__ Ap,
@@ -165,6 +382,7 @@ __global__ void __launch_bounds__(256) k_update_xr(DotArgs A, int rpr_slot, cons
     x[off + i] += alpha * p[off + i];
     v += ri * ri;
   }
+  if (A.post == POST_SKIP) return;
   reduce_finish(v, A, partials + (size_t)s * npartial, sc, c, sm);
 }
 
@@ -370,6 +588,18 @@ int launch_matvec(Ctx* c, double alpha, const double* x, double beta, double* y)
 static int dot_launch(Ctx* c, const double* a, const double* b, int slot, int post, int iter, double tol2, int skip_done) {
   DotArgs A;
   A.n = c->ndof; A.post = post; A.slot = slot; A.iter = iter; A.tol2 = tol2;
+  if (c->exact_dot) {  // the reference's serial sum, bit for bit (three kernels, see k_xdot_*)
+    const int nch = c->xd_nch;
+    dim3 g(div_up(nch, 8), c->B);
+    XChunk* st = reinterpret_cast<XChunk*>(c->xd_stat);
+    k_xdot_partial<<<g, 256, 0, KS(c, "k_xdot_partial")>>>(c->ndof, nch, a, b, c->xd_tsum, c->cnt, skip_done);
+    CG_LAUNCH_CHECK(c);
+    k_xdot_stats<<<g, 256, 0, KS(c, "k_xdot_stats")>>>(c->ndof, nch, a, b, c->xd_tsum, st, c->cnt, skip_done);
+    CG_LAUNCH_CHECK(c);
+    k_xdot_walk<<<c->B, 32, 0, KS(c, "k_xdot_walk")>>>(A, nch, a, b, st, c->scal, c->cnt, skip_done);
+    CG_LAUNCH_CHECK(c);
+    return CLOTHGPU_OK;
+  }
   dim3 g(std::min(div_up(c->ndof, 256), c->npartial), c->B);
   k_dot<<<g, 256, 0, KS(c, "k_dot")>>>(A, a, b, c->partials, c->scal, c->cnt, c->npartial, skip_done);
   CG_LAUNCH_CHECK(c);
@@ -448,10 +678,11 @@ int run_pcg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out) {
     CG_CHECK(dot_launch(c, c->vec_p, c->vec_z, SC_PAP, POST_STORE, 0, tol2, 1));
     {
       DotArgs A;
-      A.n = n; A.post = POST_PCG_CHECK; A.slot = SC_SQ; A.iter = it; A.tol2 = tol2;
+      A.n = n; A.post = c->exact_dot ? POST_SKIP : POST_PCG_CHECK; A.slot = SC_SQ; A.iter = it; A.tol2 = tol2;
       k_update_xr<<<vec_grid(c, n), 256, 0, KS(c, "k_update_xr")>>>(A, cur, c->vec_z, c->vec_p, c->vec_r, c->vec_x, c->partials,
                                                          c->scal, c->cnt, c->npartial);
       CG_LAUNCH_CHECK(c);
+      if (c->exact_dot) CG_CHECK(dot_launch(c, c->vec_r, c->vec_r, SC_SQ, POST_PCG_CHECK, it, tol2, 1));
     }
     // every kernel of the loop skips scenes whose convergence flag is set, so the host only has to look at the flags
     // when the solve is likely over: not before the iteration count of the previous solve minus one
@@ -493,10 +724,11 @@ int run_cg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out) {
     CG_CHECK(dot_launch(c, c->vec_p, c->vec_z, SC_PAP, POST_STORE, 0, tol2, 1));
     {
       DotArgs A;
-      A.n = n; A.post = POST_CG_CHECK; A.slot = SC_DOT; A.iter = it; A.tol2 = tol2;
+      A.n = n; A.post = c->exact_dot ? POST_SKIP : POST_CG_CHECK; A.slot = SC_DOT; A.iter = it; A.tol2 = tol2;
       k_update_xr<<<vec_grid(c, n), 256, 0, KS(c, "k_update_xr")>>>(A, SC_SQ, c->vec_z, c->vec_p, c->vec_r, c->vec_x, c->partials,
                                                          c->scal, c->cnt, c->npartial);
       CG_LAUNCH_CHECK(c);
+      if (c->exact_dot) CG_CHECK(dot_launch(c, c->vec_r, c->vec_r, SC_DOT, POST_CG_CHECK, it, tol2, 1));
     }
     if ((it & 7) == 0 || it == max_iter - 1) {  // unpreconditioned CG runs hundreds of cheap iterations: poll sparsely
       CG_CHECK(all_done(c, &done));

@@ -2,10 +2,13 @@
 
 Bars:
   * integer / index work (leaf-pair sets, contact elements incl. is_fv, impact-zone partitions): exact
-  * assembly, SpMV, ILU factor, triangular solves, boxes, impulses, impact-zone velocities: bit-exact (same
-    per-entry operation order, compiled without FMA contraction)
-  * anything downstream of a dot product (PCG / CG iterates, whole steps): relative 1e-9 here, the north star asks
-    for 1e-5 (the dot products are tree sums, the reference's are serial sums)
+  * every floating-point result -- assembly, SpMV, dot products, ILU factor, triangular solves, PCG / CG iterates,
+    boxes, impulses, impact-zone velocities, whole steps and whole trajectories: BIT-EXACT (np.array_equal).  The
+    kernels keep the reference's per-entry operation order, are compiled without FMA contraction, and the dot products
+    reproduce the reference's serial sum exactly (csrc/linsolve.cu k_xdot_*).  The north star asks for 1e-5; bit
+    equality is needed in practice because the reference's contact response amplifies a 1e-16 perturbation of its
+    input velocities to 1e-2 (tools/reference_sensitivity.py, profiles/r02_reference_sensitivity.txt).
+  * CLOTHGPU_DOT=tree (the non-parity fast mode: tree reductions) is held to 1e-9 relative on contact-free steps
 """
 import os
 
@@ -71,7 +74,7 @@ def test_linear_system_pipeline(oracle, sc_contact, sc_internal):
             assert np.array_equal(g.read(G.BUF_VEC_Z), oracle.matvec(sc, dia, crs, alpha, xx, beta, yy))
         g.write(G.BUF_VEC_Z, yy)
         d = g.dot(G.BUF_VEC_P, G.BUF_VEC_Z)[0]
-        assert abs(d - oracle.dot(xx, yy)) <= 1.0e-13 * np.abs(xx * yy).sum()
+        assert d == oracle.dot(xx, yy)
         g.axpy(0.37, G.BUF_VEC_P, G.BUF_VEC_Z)
         assert np.array_equal(g.read(G.BUF_VEC_Z), yy + 0.37 * xx)
         # ILU(0)
@@ -87,16 +90,16 @@ def test_linear_system_pipeline(oracle, sc_contact, sc_internal):
         ox, orr, ocr, oit = oracle.pcg(sc, dia, crs, idia, icrs, b)
         cr, it = g.pcg()
         assert it[0] == oit
-        assert rel_err(g.read(G.BUF_VEC_X), ox) < RTOL
-        assert abs(cr[0] - ocr) <= 1.0e-6 * ocr
+        assert np.array_equal(g.read(G.BUF_VEC_X), ox)
+        assert np.array_equal(g.read(G.BUF_VEC_R), orr)
+        assert cr[0] == ocr
         g.write(G.BUF_VEC_R, b)
         ox, orr, ocr, oit = oracle.cg(sc, dia, crs, b, 1.0e-4, 1000)
         cr, it = g.cg(1.0e-4, 1000)
         assert it[0] == oit
-        # unpreconditioned CG runs hundreds of iterations here and amplifies the rounding of the dot products: the
-        # iterates agree to the solver tolerance (1e-4), not to rounding
-        assert rel_err(g.read(G.BUF_VEC_X), ox) < 1.0e-4
-        assert abs(cr[0] - ocr) <= 1.0e-2 * ocr
+        # hundreds of unpreconditioned iterations, every dot product the reference's serial sum: still bit for bit
+        assert np.array_equal(g.read(G.BUF_VEC_X), ox)
+        assert cr[0] == ocr
         # zero right-hand side: early out (ilu_sparse.cpp:651)
         g.write(G.BUF_VEC_R, np.zeros(sc["np"] * 3))
         cr, it = g.pcg()
@@ -134,7 +137,7 @@ def test_golden_linear_phases(gold, sc_contact):
     assert np.array_equal(g.read(G.BUF_VEC_P), gold["ilu_solve"])
     cr, it = g.pcg()
     assert it[0] == int(gold["pcg_iter"])
-    assert rel_err(g.read(G.BUF_VEC_X), gold["pcg_x"]) < RTOL
+    assert np.array_equal(g.read(G.BUF_VEC_X), gold["pcg_x"])
     g.upload_state(gold["x"], gold["v"])
     g.update_intermediate_velocity(p)
     assert np.array_equal(g.download_state()[1], gold["upd_v"])
@@ -295,7 +298,7 @@ def test_resolve_and_step_vs_oracle(oracle):
         x, v = sim.get_state()
         assert st[0] == ost[0], "PCG iterations"
         assert np.array_equal(st[1:5], ost[1:5])
-        assert rel_err(gx, x) < RTOL and rel_err(gv, v) < RTOL
+        assert np.array_equal(gx, x) and np.array_equal(gv, v)
     g.close()
 
 
@@ -311,16 +314,15 @@ def test_internal_trajectory_golden():
         its.append(int(g.step_internal(p)[0]))
         if step == int(gold["steps"][k]):
             x, v = g.download_state()
-            assert rel_err(x, gold["x"][k]) < 1.0e-8 and rel_err(v, gold["v"][k]) < 1.0e-7
+            assert np.array_equal(x, gold["x"][k]) and np.array_equal(v, gold["v"][k])
             k += 1
     assert its == list(gold["iters"])
     g.close()
 
 
 def test_config1_trajectory_golden():
-    """Config 1: the default self_contact_sparse scene, free running.  Contact decisions are threshold tests, so a
-    free run can fork from the reference after many steps; the bar here is the pre-fork stretch plus teacher-forced
-    agreement, the drift is reported."""
+    """Config 1: the default self_contact_sparse scene, 100 FREE-RUNNING steps (proximity + CCD impulses and impact
+    zones from step ~36 on): statistics and states bit-identical to the reference's own trajectory throughout."""
     gold = np.load(os.path.join(GOLD, "traj_config1.npz"))
     sc = S.config1_default()
     sc["bvh"] = np.ascontiguousarray(gold["bvh"])
@@ -330,15 +332,14 @@ def test_config1_trajectory_golden():
     errs = {}
     for step in range(1, 101):
         st = g.step_self_contact(p)[0]
-        if step <= 40:
+        if step <= len(gold["stats"]):
             assert np.array_equal(st[:5], gold["stats"][step - 1][:5]), step
         if step in keep:
             k = keep.index(step)
             x, v = g.download_state()
             errs[step] = (rel_err(x, gold["x"][k]), rel_err(v, gold["v"][k]))
-    print("free-run drift vs reference:", errs)
-    for step in (10, 35, 36, 40):
-        assert errs[step][0] < 1.0e-8 and errs[step][1] < 1.0e-6, errs
+            assert np.array_equal(x, gold["x"][k]) and np.array_equal(v, gold["v"][k]), (step, errs[step])
+    assert len(errs) == len(keep)
     g.close()
 
 
@@ -473,13 +474,8 @@ def test_config2_internal_128(oracle):
         gx, gv = g.download_state()
         ox, ov = sim.get_state()
         if size == 1.0:
-            # 2a never converges (100-iteration cap, residual stalls): the iterate is dominated by the rounding of the
-            # dot products, whose summation order differs (tree vs the reference's serial loop),
-            # so only the iteration counts and a loose position bound are meaningful here
-            assert it == 100
-            assert rel_err(gx, ox) < 1.0e-3, rel_err(gx, ox)
-        else:
-            assert rel_err(gx, ox) < 1.0e-9 and rel_err(gv, ov) < 1.0e-7, (size, rel_err(gx, ox), rel_err(gv, ov))
+            assert it == 100  # 2a never converges: 100 iterations of rounding-dominated iterates, still bit for bit
+        assert np.array_equal(gx, ox) and np.array_equal(gv, ov), (size, rel_err(gx, ox), rel_err(gv, ov))
         g.close()
 
 
@@ -500,7 +496,7 @@ def test_config4_crumpled_512(oracle):
     ost = sim.step_self_contact(p)
     ox, ov = sim.get_state()
     assert np.array_equal(st[:5], ost[:5]), (st[:5], ost[:5])
-    assert rel_err(gx, ox) < 1.0e-9 and rel_err(gv, ov) < 1.0e-7
+    assert np.array_equal(gx, ox) and np.array_equal(gv, ov)
     g.close()
 
 
@@ -521,7 +517,7 @@ def test_tiny_and_ragged_scenes(oracle):
             assert np.array_equal(st[:5], ost[:5]), (nx, nz, st[:5], ost[:5])
         gx, gv = g.download_state()
         ox, ov = sim.get_state()
-        assert rel_err(gx, ox) < 1.0e-9 and rel_err(gv, ov) < 1.0e-7, (nx, nz)
+        assert np.array_equal(gx, ox) and np.array_equal(gv, ov), (nx, nz)
         g.close()
 
 
@@ -595,22 +591,23 @@ def test_measurement_switches_do_not_change_results(oracle, monkeypatch):
 
 def test_step_internal_cg_vs_oracle(oracle):
     """clothgpu_step_internal_cg = StepTime_InternalDynamics (solve_internal_sparse.h:185-253, Solve_CG 1e-4 / 1000),
-    teacher forced: same iteration counts, positions to rounding, velocities to the amplification of the dot-product
-    rounding by the unpreconditioned iteration (the reference stops at a 1e-4 residual itself)."""
+    teacher forced AND free running (the GPU state is never corrected): bit-identical states, iteration counts and
+    convergence ratios."""
     sc = S.square_cloth_xy(12, 1.0)
     p = T.params_for(sc, S.INTERNAL_CLOTH, col_kind=2, col_par=(0.1, 0.5, -0.8, 0.3))
     g = G.ClothGPU(sc, with_bvh=False)
     sim = oracle.sim(sc)
     x, v = sim.get_state()
     for step in range(6):
-        g.upload_state(x, v)
+        if step < 3:
+            g.upload_state(x, v)
         cr, it = g.step_internal_cg(p)
         ocr, oit = sim.step_internal_cg(p)
         gx, gv = g.download_state()
         x, v = sim.get_state()
         assert int(it[0]) == oit, (step, it, oit)
-        assert abs(cr[0] - ocr) <= 1.0e-2 * ocr
-        assert rel_err(gx, x) < 1.0e-8 and rel_err(gv, v) < 1.0e-5, (step, rel_err(gx, x), rel_err(gv, v))
+        assert cr[0] == ocr
+        assert np.array_equal(gx, x) and np.array_equal(gv, v), (step, rel_err(gx, x), rel_err(gv, v))
     assert oit > 3
     g.close()
 
@@ -619,7 +616,7 @@ def test_collider_sphere_inside(oracle):
     """CLOTHGPU_COLLIDER_SPHERE_INSIDE (the container sphere of self_contact_sparse/main.cpp:117-133): assembled
     matrix / right-hand side bit-exact on a state that touches the wall, then free-running implicit steps."""
     sc = S.square_cloth_xy(12, 1.0)
-    p = T.params_for(sc, S.INTERNAL_CLOTH, col_kind=3, col_par=(0.5, 0.5, -0.2, 0.9))
+    p = T.params_for(sc, S.INTERNAL_CLOTH, col_kind=3, col_par=(0.5, 0.5, -0.2, 0.62))
     x, v = T.wavy_state(sc)
     g = G.ClothGPU(sc, with_bvh=False)
     g.upload_state(x, v)
@@ -639,7 +636,7 @@ def test_collider_sphere_inside(oracle):
         assert it == int(sim.step_internal(p)[1])
     gx, gv = g.download_state()
     ox, ov = sim.get_state()
-    assert rel_err(gx, ox) < 1.0e-9 and rel_err(gv, ov) < 1.0e-7
+    assert np.array_equal(gx, ox) and np.array_equal(gv, ov)
     g.close()
 
 
@@ -647,7 +644,7 @@ def test_config3_contact_regime_vs_oracle(oracle):
     """The benchmarked workload itself (BASELINE.json configs[2]: 256 x 256, reference BVH tree, from rest): the GPU
     trajectory is taken into the self-contact regime and single steps there (58: first CCD passes; 66: thousands of
     contact elements, five CCD passes, impact zones) are teacher forced on the C restatement AND on the compiled
-    reference (oracle/_ref, when it travelled): statistics and per-pass element counts exact, X / V to 1e-9."""
+    reference (oracle/_ref, when it travelled): statistics, per-pass element counts, X and V bit-identical."""
     from oracle import oracle_py as O
     sc = S.config3_256()
     sc["bvh"] = S.reference_bvh(sc)
@@ -674,7 +671,79 @@ def test_config3_contact_regime_vs_oracle(oracle):
             ox, ov = sim.get_state()
             assert np.array_equal(st[:5], ost[:5]), (name, target, st[:5], ost[:5])
             assert np.array_equal(st[8:116], ost[8:116]), (name, target)
-            assert rel_err(gx, ox) < RTOL and rel_err(gv, ov) < RTOL, (name, target, rel_err(gx, ox), rel_err(gv, ov))
+            assert np.array_equal(gx, ox) and np.array_equal(gv, ov), (name, target, rel_err(gx, ox), rel_err(gv, ov))
     print("config 3 contact regime stats (pcg, prox, ccd passes, riz rounds, applied):", seen)
     assert seen[1][1] > 1000 and seen[1][2] >= 3, "step 66 must be deep in the contact regime"
     g.close()
+
+
+def _serial_dot_cases(n, rng):
+    """Vectors that stress every path of the exact dot: binade crossings up and down, cancellation, exact ties,
+    zeros, huge dynamic range, subnormal products, a sum that returns to zero."""
+    one = np.ones(n)
+    cases = {
+        "normal": (rng.standard_normal(n), rng.standard_normal(n)),
+        "squares": ((lambda a: (a, a))(rng.standard_normal(n))),
+        "wide_range": (rng.standard_normal(n) * 10.0 ** rng.uniform(-12, 12, n), rng.standard_normal(n)),
+        "growing": (np.exp(np.linspace(-30, 30, n)), one),
+        "shrinking": (np.exp(np.linspace(30, -30, n)), one),
+        "alternating_cancel": (np.where(np.arange(n) % 2 == 0, 1.0, -1.0) * (1.0 + 1e-9 * rng.standard_normal(n)), 1e6 * one),
+        "ties": (np.where(rng.random(n) < 0.3, 0.5, 1.0) * 2.0 ** rng.integers(-3, 3, n), one),
+        "integers": (rng.integers(-1000, 1000, n).astype(np.float64), rng.integers(-1000, 1000, n).astype(np.float64)),
+        "mostly_zero": (np.where(rng.random(n) < 0.01, rng.standard_normal(n), 0.0), one),
+        "all_zero": (np.zeros(n), one),
+        "tiny": (1e-160 * rng.standard_normal(n), 1e-160 * rng.standard_normal(n)),
+        "huge": (1e150 * rng.standard_normal(n), 1e150 * rng.random(n)),
+    }
+    big_then_small = rng.standard_normal(n)
+    big_then_small[: n // 3] *= 1e15
+    big_then_small[n // 3: 2 * n // 3] *= -1e15
+    cases["return_to_small"] = (big_then_small, one)
+    sym = rng.standard_normal(n)
+    sym[n // 2:] = -sym[: n - n // 2][::-1]
+    cases["sum_to_zero"] = (sym, one)
+    return cases
+
+
+def test_exact_dot_is_the_serial_sum(oracle):
+    """clothgpu_dot == InnerProduct (matrix_square_sparse.cpp:313-324), the serial left-to-right sum, bit for bit:
+    lengths that are / are not multiples of the 256-element chunks, one chunk, 256 x 256 scale."""
+    rng = np.random.default_rng(17)
+    for nx, nz in ((3, 5), (12, 12), (40, 40), (255, 255)):
+        sc = S.square_cloth_xz(nx, nz, 0.1)
+        g = G.ClothGPU(sc, with_bvh=False)
+        n = sc["np"] * 3
+        for name, (a, b) in _serial_dot_cases(n, rng).items():
+            g.write(G.BUF_VEC_P, a)
+            g.write(G.BUF_VEC_Z, b)
+            d = g.dot(G.BUF_VEC_P, G.BUF_VEC_Z)[0]
+            assert d == oracle.dot(a, b), (n, name, d, oracle.dot(a, b))
+        # non-finite input: whatever the serial loop gives (inf / nan), compared as bit patterns
+        a = rng.standard_normal(n)
+        a[n // 2] = np.inf
+        g.write(G.BUF_VEC_P, a)
+        g.write(G.BUF_VEC_Z, np.ones(n))
+        d = g.dot(G.BUF_VEC_P, G.BUF_VEC_Z)[0]
+        assert np.array([d]).tobytes() == np.array([oracle.dot(a, np.ones(n))]).tobytes()
+        g.close()
+
+
+def test_tree_dot_fast_mode(oracle, monkeypatch):
+    """CLOTHGPU_DOT=tree (non-parity fast mode): fixed-shape tree reductions instead of the serial
+    sums.  Deterministic run to run; PCG iterates agree with the reference to rounding (1e-9), not bit for bit."""
+    monkeypatch.setenv("CLOTHGPU_DOT", "tree")
+    sc = S.square_cloth_xy(24, 24 * 0.04)
+    p = T.params_for(sc, S.INTERNAL_CLOTH, col_kind=2, col_par=(0.4, 0.5, -0.6, 0.3))
+    runs = []
+    for rep in range(2):
+        g = G.ClothGPU(sc, with_bvh=False)
+        its = [int(g.step_internal(p)[0]) for _ in range(5)]
+        runs.append((g.download_state(), its))
+        g.close()
+    assert np.array_equal(runs[0][0][0], runs[1][0][0]) and runs[0][1] == runs[1][1]
+    sim = oracle.sim(sc)
+    oits = [int(sim.step_internal(p)[1]) for _ in range(5)]
+    ox, ov = sim.get_state()
+    assert runs[0][1] == oits
+    assert rel_err(runs[0][0][0], ox) < RTOL and rel_err(runs[0][0][1], ov) < 1.0e-7
+    assert not np.array_equal(runs[0][0][1], ov), "the tree mode is not expected to be bit-identical"
