@@ -321,8 +321,9 @@ def test_internal_trajectory_golden():
 
 
 def test_config1_trajectory_golden():
-    """Config 1: the default self_contact_sparse scene, 100 FREE-RUNNING steps (proximity + CCD impulses and impact
-    zones from step ~36 on): statistics and states bit-identical to the reference's own trajectory throughout."""
+    """Config 1: the default self_contact_sparse scene, 200 FREE-RUNNING steps (proximity + CCD impulses and impact
+    zones from step ~36 on): statistics and states bit-identical to the reference's own trajectory throughout, and the
+    survey's known-answer checksum of the final positions."""
     gold = np.load(os.path.join(GOLD, "traj_config1.npz"))
     sc = S.config1_default()
     sc["bvh"] = np.ascontiguousarray(gold["bvh"])
@@ -330,7 +331,7 @@ def test_config1_trajectory_golden():
     g = G.ClothGPU(sc)
     keep = list(gold["steps"])
     errs = {}
-    for step in range(1, 101):
+    for step in range(1, 201):
         st = g.step_self_contact(p)[0]
         if step <= len(gold["stats"]):
             assert np.array_equal(st[:5], gold["stats"][step - 1][:5]), step
@@ -340,6 +341,8 @@ def test_config1_trajectory_golden():
             errs[step] = (rel_err(x, gold["x"][k]), rel_err(v, gold["v"][k]))
             assert np.array_equal(x, gold["x"][k]) and np.array_equal(v, gold["v"][k]), (step, errs[step])
     assert len(errs) == len(keep)
+    x, _ = g.download_state()
+    assert float(np.dot(x, 1.0 + (np.arange(x.size) % 7))) == -89.699184471192837
     g.close()
 
 
