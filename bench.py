@@ -487,7 +487,12 @@ def run_ours(args):
         g.set_kernel_timing(True)
         g.set_profiling(True)
         ks = K if args.kernel_steps <= 0 else max(1, min(args.kernel_steps, K))
-        g.step_self_contact(p, ks)
+        imp_elems = 0
+        det_passes = 0
+        for _ in range(ks):
+            st1 = g.step_self_contact(p, 1)[0]
+            imp_elems += int(st1[1]) + int(sum(st1[8:8 + 5]))   # elements run through the Gauss-Seidel impulse sweeps
+            det_passes += 1 + int(st1[2]) + int(st1[3])
         kt = g.kernel_times()
         phases = g.phase_ms()
         nleaf = int(len(g.leaf_pairs(0)))
@@ -516,6 +521,10 @@ def run_ours(args):
                 e["frac_of_peak"] = e["achieved_GBps"] / peak
             roof["per_kernel"][name] = e
         roof["phase_ms_per_step"] = {k: v / ks for k, v in phases.items()}
+        roof["impulse_elements_per_step"] = imp_elems / ks
+        roof["detection_passes_per_step"] = det_passes / ks
+        if "k_imp_flow" in kt and imp_elems > 0:
+            roof["impulse_ns_per_element"] = kt["k_imp_flow"][1] * 1.0e6 / imp_elems
 
         # ---- parity of the benchmarked trajectory + CPU baseline: the reference (or its C port) on this box's host,
         # a bounded sample of the same workload from the state at the start of the timed region

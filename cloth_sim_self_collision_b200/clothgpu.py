@@ -132,6 +132,67 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+def _elem_call(fn, n, ins, outs, scalars=()):
+    lib = load()
+    rc = getattr(lib, fn)(C.c_int(n), *[_dp(a) for a in ins], *[C.c_double(v) for v in scalars], *[_dp(a) for a in outs])
+    if rc != 0:
+        raise ClothGPUError("clothgpu error %d: %s" % (rc, lib.clothgpu_last_error().decode()))
+    return outs
+
+
+def elem_psd_sym22(s2):
+    """MakePositiveDefinite_Sim22 (cloth_internal_physics.h:15-67) for n stresses {s00, s11, s01}."""
+    s2 = _cd(s2).reshape(-1, 3)
+    return _elem_call("clothgpu_elem_psd_sym22", len(s2), [s2], [np.zeros_like(s2)])[0]
+
+
+def elem_cst(C0, c, lam, myu):
+    """WdWddW_CST (cloth_internal_physics.h:70-176) for n triangles: (W[n], dW[n,3,3], ddW[n,3,3,3,3])."""
+    C0 = _cd(C0).reshape(-1, 9)
+    c = _cd(c).reshape(-1, 9)
+    n = len(C0)
+    return _elem_call("clothgpu_elem_cst", n, [C0, c], [np.zeros(n), np.zeros((n, 3, 3)), np.zeros((n, 3, 3, 3, 3))],
+                      (lam, myu))
+
+
+def elem_bend(C0, c, stiff):
+    """WdWddW_Bend (cloth_internal_physics.h:180-238) for n hinges: (W[n], dW[n,4,3], ddW[n,4,4,3,3])."""
+    C0 = _cd(C0).reshape(-1, 12)
+    c = _cd(c).reshape(-1, 12)
+    n = len(C0)
+    return _elem_call("clothgpu_elem_bend", n, [C0, c], [np.zeros(n), np.zeros((n, 4, 3)), np.zeros((n, 4, 4, 3, 3))],
+                      (stiff,))
+
+
+def elem_contact(pd_normal, stiff, clearance):
+    """WdWddW_Contact (cloth_internal_physics.h:243-280) for n vertices given the callback's {pd, n}."""
+    pdn = _cd(pd_normal).reshape(-1, 4)
+    n = len(pdn)
+    return _elem_call("clothgpu_elem_contact", n, [pdn], [np.zeros(n), np.zeros((n, 3)), np.zeros((n, 3, 3))],
+                      (stiff, clearance))
+
+
+def dist_face_vertex(p):
+    """DistanceFaceVertex (bvh_aabb.cpp:321-340): p[n,4,3] -> (dist, w0, w1)."""
+    p = _cd(p).reshape(-1, 12)
+    n = len(p)
+    return _elem_call("clothgpu_dist_face_vertex", n, [p], [np.zeros(n), np.zeros(n), np.zeros(n)])
+
+
+def dist_edge_edge(p):
+    """DistanceEdgeEdge (bvh_aabb.cpp:343-384): p[n,4,3] = {p0,p1,q0,q1} -> (dist, ratio_p, ratio_q)."""
+    p = _cd(p).reshape(-1, 12)
+    n = len(p)
+    return _elem_call("clothgpu_dist_edge_edge", n, [p], [np.zeros(n), np.zeros(n), np.zeros(n)])
+
+
+def coplanar_interp(s, e):
+    """FindCoplanerInterp (bvh_aabb.cpp:598-662): s, e [n,4,3] -> t[n]."""
+    s = _cd(s).reshape(-1, 12)
+    e = _cd(e).reshape(-1, 12)
+    return _elem_call("clothgpu_coplanar_interp", len(s), [s, e], [np.zeros(len(s))])[0]
+
+
 class ClothGPU:
     """A batch of `nscene` cloth scenes sharing one topology, resident on one GPU."""
 
@@ -361,6 +422,12 @@ class ClothGPU:
         return applied, stats
 
     # ------------------------------------------------------------------ whole steps
+    def make_normal(self, buf_xyz=0, scene=0):
+        """MakeNormal (self_contact_sparse/main.cpp:183-211): unit vertex normals, np x 3."""
+        out = np.zeros(self.ndof)
+        self._check(self.lib.clothgpu_make_normal(self.h, C.c_int(buf_xyz), C.c_int(scene), _dp(out)))
+        return out
+
     def step_self_contact(self, p, nsteps=1):
         p = params_from(p)
         stats = np.zeros((self.nscene, NSTATS), dtype=np.int32)

@@ -276,6 +276,56 @@ bool CContactElement::operator<(const CContactElement& p) const {
   return ino3 < p.ino3;
 }
 
+// ------------------------------------------------------------------------------------------------ element level
+void MakePositiveDefinite_Sim22(const double s2[3], double s3[3]) {
+  check(clothgpu_elem_psd_sym22(1, s2, s3), "clothgpu_elem_psd_sym22");
+}
+void WdWddW_CST(double& W, double dW[3][3], double ddW[3][3][3][3], const double C[3][3], const double c[3][3],
+                const double lambda, const double myu) {
+  check(clothgpu_elem_cst(1, &C[0][0], &c[0][0], lambda, myu, &W, &dW[0][0], &ddW[0][0][0][0]), "clothgpu_elem_cst");
+}
+void WdWddW_Bend(double& W, double dW[4][3], double ddW[4][4][3][3], const double C[4][3], const double c[4][3],
+                 double stiff) {
+  double w = 0;
+  check(clothgpu_elem_bend(1, &C[0][0], &c[0][0], stiff, &w, &dW[0][0], &ddW[0][0][0][0]), "clothgpu_elem_bend");
+  W += w;  // cloth_internal_physics.h:235 accumulates
+}
+void WdWddW_Contact(double& W, double dW[3], double ddW[3][3], const double c[3], double stiff_contact,
+                    double contact_clearance, void (*penetrationDepth)(double&, double*, const double*)) {
+  double pdn[4] = {0, 0, 0, 0};
+  penetrationDepth(pdn[0], pdn + 1, c);  // the caller's callback is host code
+  check(clothgpu_elem_contact(1, pdn, stiff_contact, contact_clearance, &W, dW, &ddW[0][0]), "clothgpu_elem_contact");
+}
+
+namespace {
+void pack4(double* p, const CVector3D& a, const CVector3D& b, const CVector3D& c, const CVector3D& d) {
+  const CVector3D* v[4] = {&a, &b, &c, &d};
+  for (int i = 0; i < 4; i++) { p[i * 3] = v[i]->x; p[i * 3 + 1] = v[i]->y; p[i * 3 + 2] = v[i]->z; }
+}
+}  // namespace
+double DistanceFaceVertex(const CVector3D& p0, const CVector3D& p1, const CVector3D& p2, const CVector3D& p3,
+                          double& w0, double& w1) {
+  double p[12], d = 0;
+  pack4(p, p0, p1, p2, p3);
+  check(clothgpu_dist_face_vertex(1, p, &d, &w0, &w1), "clothgpu_dist_face_vertex");
+  return d;
+}
+double DistanceEdgeEdge(const CVector3D& p0, const CVector3D& p1, const CVector3D& q0, const CVector3D& q1,
+                        double& ratio_p, double& ratio_q) {
+  double p[12], d = 0;
+  pack4(p, p0, p1, q0, q1);
+  check(clothgpu_dist_edge_edge(1, p, &d, &ratio_p, &ratio_q), "clothgpu_dist_edge_edge");
+  return d;
+}
+double FindCoplanerInterp(const CVector3D& s0, const CVector3D& s1, const CVector3D& s2, const CVector3D& s3,
+                          const CVector3D& e0, const CVector3D& e1, const CVector3D& e2, const CVector3D& e3) {
+  double s[12], e[12], t = 0;
+  pack4(s, s0, s1, s2, s3);
+  pack4(e, e0, e1, e2, e3);
+  check(clothgpu_coplanar_interp(1, s, e, &t), "clothgpu_coplanar_interp");
+  return t;
+}
+
 // ------------------------------------------------------------------------------------------------ BVH
 // MakeBVHTopology_TopDown (bvh_aabb.cpp:294-313): the reference's own node array (libclothgpu's host builder,
 // csrc/bvhbuild.cu); where the reference crashes on exactly square grids it falls back to a longest-axis split

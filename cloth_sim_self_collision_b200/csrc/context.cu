@@ -578,6 +578,7 @@ void clothgpu_destroy(clothgpu_ctx* c) {
                   c->scratch, c->sort_keys, c->sort_keys2, c->sort_vals, c->sort_vals2};
   for (void* p : ptrs) cudaFree(p);
   cudaFree(c->tri_dbg_buf);
+  cudaFree(c->normals);
   cudaFree(c->tri_xch);
   free_facplan(c->plan_fac);
   free_triplan(c->plan_f);

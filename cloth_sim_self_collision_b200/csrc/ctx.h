@@ -166,6 +166,7 @@ struct Ctx {
   double *vec_r = nullptr, *vec_x = nullptr, *vec_p = nullptr, *vec_z = nullptr;
   double *tri_dW = nullptr, *tri_ddW = nullptr, *quad_dW = nullptr;
   double* col_table = nullptr;
+  double* normals = nullptr;  // vertex normals of clothgpu_make_normal (allocated on first use)
   double* gravity = nullptr;  // B x 3
   std::vector<double> gravity_override;  // B x 3 on the host, NaN = no override
   double* boxes = nullptr;
@@ -181,6 +182,7 @@ struct Ctx {
   // exact (serial-order) dot products, linsolve.cu k_xdot_*: chunk sums and per-chunk integer statistics
   bool exact_dot = true;  // CLOTHGPU_DOT=tree selects the tree reduction (deterministic, not the reference's order)
   int xd_nch = 0;
+  bool xd_attr_set = false;
   double* xd_tsum = nullptr;
   void* xd_stat = nullptr;
   int* cnt = nullptr;

@@ -162,8 +162,11 @@ __global__ void __launch_bounds__(256) k_dot(DotArgs A, const double* __restrict
 //                    (2^52, 2^53) throughout; any other chunk (a binade crossing, a tie, the first chunk: ~15 of 768
 //                    at 256^2) is redone 32 elements at a time with the true s, element by element where needed.
 // No approximation anywhere: a chunk is either provably exact or recomputed.
+// (integers are carried as doubles: every quantity that decides about or enters an ACCEPTED chunk is an integer of
+// magnitude < 2^53 and therefore exact; a sum that got rounded has passed 2^53 on the way, which the min / max of the
+// prefix sums record, so such a chunk can only be rejected)
 struct XChunk {
-  long long K, pmin, pmax;
+  double K, pmin, pmax;
   int e, bad;
 };
 static_assert(sizeof(XChunk) == 32, "XChunk layout");
@@ -177,18 +180,34 @@ __device__ __forceinline__ bool xd_binade(double s, int& e) {
   return e >= -960;  // 2^(e-52) and its inverse are normal powers of two
 }
 __device__ __forceinline__ double xd_pow2(int k) { return __longlong_as_double((long long)(1023 + k) << 52); }
-__device__ __forceinline__ long long xd_scan_incl(long long v, int lane) {
+__device__ __forceinline__ double xd_scan_incl(double v, int lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const long long t = __shfl_up_sync(0xffffffffu, v, o);
+    const double t = __shfl_up_sync(0xffffffffu, v, o);
     if (lane >= o) v += t;
   }
   return v;
 }
 // S + [lo, hi] strictly inside the binade of sign(s)
-__device__ __forceinline__ bool xd_inside(bool positive, long long S, long long lo, long long hi) {
-  const long long L = (1LL << 52) + 1, H = (1LL << 53) - 1;
+__device__ __forceinline__ bool xd_inside(bool positive, double S, double lo, double hi) {
+  const double L = 4503599627370497.0, H = 9007199254740991.0;  // 2^52 + 1, 2^53 - 1
   return positive ? (S + lo >= L && S + hi <= H) : (S + lo >= -H && S + hi <= -L);
+}
+
+// lane-local statistics of 8 consecutive products in units of u = 2^(e-52): integer total, min / max of the prefix
+// sums, and whether any element is not exactly representable (tie or too large)
+__device__ __forceinline__ void xd_lane_stats(const double (&p)[8], double scale, double& run, double& lmin,
+                                              double& lmax, bool& bad) {
+  run = 0; lmin = 0; lmax = 0; bad = false;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const double q = p[j] * scale;
+    const double kf = rint(q);
+    if (!(fabs(q) < 9007199254740992.0) || fabs(q - kf) == 0.5) bad = true;
+    else run += kf;
+    lmin = fmin(lmin, run);
+    lmax = fmax(lmax, run);
+  }
 }
 
 __global__ void __launch_bounds__(256) k_xdot_partial(int n, int nch, const double* __restrict__ a,
@@ -229,7 +248,10 @@ __global__ void __launch_bounds__(256) k_xdot_stats(int n, int nch, const double
   __syncthreads();
   if (c >= nch) return;
   double start = base;
-  for (int k = c0; k < c; k++) start += ts[k];
+  {
+    const double mine = (lane < 8 && c0 + lane < nch) ? ts[c0 + lane] : 0.0;
+    for (int k = 0; k < w; k++) start += __shfl_sync(0xffffffffu, mine, k);
+  }
   XChunk out;
   out.K = 0; out.pmin = 0; out.pmax = 0; out.e = 0; out.bad = 1;
   int e;
@@ -239,121 +261,146 @@ __global__ void __launch_bounds__(256) k_xdot_stats(int n, int nch, const double
     const double* as = a + (size_t)s * n;
     const double* bs = b + (size_t)s * n;
     // lane l owns the 8 consecutive elements c*256 + l*8 .. +7: local integer prefix, then a scan over the lanes
-    long long run = 0, lmin = 0, lmax = 0;
-    bool bad = false;
+    double pr[8];
     const int i0 = c * XD_CHUNK + lane * 8;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       const int i = i0 + j;
-      const double p = i < n ? as[i] * bs[i] : 0.0;
-      const double q = p * scale;
-      const double kf = rint(q);
-      if (!(fabs(q) < 9007199254740992.0) || fabs(q - kf) == 0.5) bad = true;
-      else run += (long long)kf;
-      lmin = min(lmin, run);
-      lmax = max(lmax, run);
+      pr[j] = i < n ? as[i] * bs[i] : 0.0;
     }
-    const long long inc = xd_scan_incl(run, lane);
-    const long long exc = inc - run;
-    long long mn = exc + lmin, mx = exc + lmax;
+    double run, lmin, lmax;
+    bool bad;
+    xd_lane_stats(pr, scale, run, lmin, lmax, bad);
+    const double inc = xd_scan_incl(run, lane);
+    const double exc = inc - run;
+    double mn = exc + lmin, mx = exc + lmax;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
     const bool anybad = __any_sync(0xffffffffu, bad);
     out.K = __shfl_sync(0xffffffffu, inc, 31);
     out.pmin = mn;
     out.pmax = mx;
-    out.bad = (anybad || mx - mn >= (1LL << 53)) ? 1 : 0;
+    out.bad = (anybad || !(mx - mn < 9007199254740992.0)) ? 1 : 0;
     if (out.bad) out.K = 0;
   }
   if (lane == 0) st[(size_t)s * nch + c] = out;
 }
 
-__global__ void __launch_bounds__(32) k_xdot_walk(DotArgs A, int nch, const double* __restrict__ a,
-                                                   const double* __restrict__ b, const XChunk* __restrict__ st,
-                                                   double* __restrict__ scal, int* __restrict__ cnt, int skip_done) {
-  const int s = blockIdx.x, lane = threadIdx.x;
+enum { XD_WALK_THREADS = 256, XD_CACHE = 24 };  // product cache: chunks whose slow path is foreseeable
+
+// one CTA per scene: all threads stage the chunk statistics (and the products of the chunks that will foreseeably
+// need the slow path: flagged ones, and those where the predicted binade changes) in shared memory, then warp 0 walks
+template <bool SMEM_STATS>
+__global__ void __launch_bounds__(XD_WALK_THREADS) k_xdot_walk(DotArgs A, int nch, const double* __restrict__ a,
+                                                                const double* __restrict__ b,
+                                                                const XChunk* __restrict__ st, double* __restrict__ scal,
+                                                                int* __restrict__ cnt, int skip_done) {
+  extern __shared__ __align__(16) unsigned char xsm[];
+  __shared__ int ncached;
+  __shared__ int cached_chunk[XD_CACHE];
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   int* cn = cnt + s * NCNT;
   if (skip_done && cn[CNT_PCG_DONE]) return;
   const int n = A.n;
   const double* as = a + (size_t)s * n;
   const double* bs = b + (size_t)s * n;
   const XChunk* cs = st + (size_t)s * nch;
+  double* pcache = reinterpret_cast<double*>(xsm);                          // XD_CACHE x 256 products
+  XChunk* sst = reinterpret_cast<XChunk*>(xsm + XD_CACHE * XD_CHUNK * 8);   // nch chunk statistics (SMEM_STATS)
+  if (tid == 0) ncached = 0;
+  if (SMEM_STATS) {
+    const int4* src = reinterpret_cast<const int4*>(cs);
+    int4* dst = reinterpret_cast<int4*>(sst);
+    for (int k = tid; k < nch * 2; k += XD_WALK_THREADS) dst[k] = src[k];
+  }
+  __syncthreads();
+  const XChunk* S = SMEM_STATS ? sst : cs;
+  for (int c = tid; c < nch; c += XD_WALK_THREADS) {
+    const bool suspect = c == 0 || S[c].bad || (c + 1 < nch && S[c + 1].e != S[c].e);
+    if (suspect) {
+      const int k = atomicAdd(&ncached, 1);
+      if (k < XD_CACHE) cached_chunk[k] = c;
+    }
+  }
+  __syncthreads();
+  const int nc = min(ncached, XD_CACHE);
+  for (int k = tid; k < nc * XD_CHUNK; k += XD_WALK_THREADS) {
+    const int i = cached_chunk[k >> 8] * XD_CHUNK + (k & 255);
+    pcache[k] = i < n ? as[i] * bs[i] : 0.0;
+  }
+  __syncthreads();
+  if (tid >= 32) return;
+
   double sum = 0.0;
   int pos = 0;
-  XChunk nx;
-  int nx_pos = -1;
   while (pos < nch) {
     const int c = pos + lane;
     XChunk ch;
-    if (nx_pos == pos) ch = nx;
-    else if (c < nch) ch = cs[c];
+    if (c < nch) ch = S[c];
     else { ch.K = 0; ch.pmin = 0; ch.pmax = 0; ch.e = 0; ch.bad = 1; }
-    if (c >= nch) ch.bad = 1;
-    // speculative prefetch of the next group (used when all 32 chunks of this one are accepted)
-    nx_pos = pos + 32;
-    if (nx_pos + lane < nch) nx = cs[nx_pos + lane];
     int e = 0;
     const bool okbin = xd_binade(sum, e);
-    const long long Kl = ch.bad ? 0 : ch.K;
-    const long long inc = xd_scan_incl(Kl, lane);
+    const double Kl = ch.bad ? 0.0 : ch.K;
+    const double inc = xd_scan_incl(Kl, lane);
     bool ok = false;
-    long long S0 = 0;
+    double S0 = 0;
     if (okbin) {
-      S0 = (long long)(sum * xd_pow2(-(e - 52)));
+      S0 = sum * xd_pow2(-(e - 52));
       if (!ch.bad && ch.e == e) ok = xd_inside(sum > 0, S0 + (inc - Kl), ch.pmin, ch.pmax);
     }
     const unsigned m = __ballot_sync(0xffffffffu, ok);
     const int f = (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);
     if (f > 0) {
-      const long long tot = __shfl_sync(0xffffffffu, inc, f - 1);
-      sum = (double)(S0 + tot) * xd_pow2(e - 52);
+      const double tot = __shfl_sync(0xffffffffu, inc, f - 1);
+      sum = (S0 + tot) * xd_pow2(e - 52);
     }
     pos += f;
     if (f < 32 && pos < nch) {
-      // ---- the chunk at pos is redone with the true running sum, 32 elements at a time
-      const int i0 = pos * XD_CHUNK;
+      // ---- the chunk at pos is redone with the true running sum: lane l owns its elements l*8 .. l*8+7
       double pr[8];
+      int slot = -1;
+      for (int k = 0; k < nc; k++)
+        if (cached_chunk[k] == pos) slot = k;
+      if (slot >= 0) {
 #pragma unroll
-      for (int g = 0; g < 8; g++) {
-        const int i = i0 + g * 32 + lane;
-        pr[g] = i < n ? as[i] * bs[i] : 0.0;
+        for (int j = 0; j < 8; j++) pr[j] = pcache[slot * XD_CHUNK + lane * 8 + j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int i = pos * XD_CHUNK + lane * 8 + j;
+          pr[j] = i < n ? as[i] * bs[i] : 0.0;
+        }
       }
-#pragma unroll 1
-      for (int g = 0; g < 8; g++) {
-        const int cntg = min(32, n - (i0 + g * 32));
-        if (cntg <= 0) break;
-        const double p = pr[g];
-        int j = 0;
-        while (j < cntg) {
-          int e2 = 0;
-          const bool okb = xd_binade(sum, e2);
-          int f2 = j;
-          if (okb) {
-            const double q = p * xd_pow2(-(e2 - 52));
-            const double kf = rint(q);
-            const bool mine = lane >= j && lane < cntg;
-            const bool valid = mine && fabs(q) < 9007199254740992.0 && fabs(q - kf) != 0.5;
-            const long long k = valid ? (long long)kf : 0;
-            const long long inc2 = xd_scan_incl(k, lane);
-            const long long S2 = (long long)(sum * xd_pow2(-(e2 - 52)));
-            const bool okl = lane < j || (valid && xd_inside(sum > 0, S2 + inc2, 0, 0));
-            const unsigned m2 = __ballot_sync(0xffffffffu, okl);
-            f2 = (m2 == 0xffffffffu) ? 32 : (__ffs(~m2) - 1);
-            if (f2 > cntg) f2 = cntg;
-            if (f2 > j) {
-              const long long tot2 = __shfl_sync(0xffffffffu, inc2, f2 - 1);
-              sum = (double)(S2 + tot2) * xd_pow2(e2 - 52);
-            }
+      // (products beyond n are exact zeros: adding them changes nothing, in either path)
+      int L0 = 0;
+      while (L0 < 32) {
+        int e2 = 0;
+        int f2 = L0;
+        if (xd_binade(sum, e2)) {
+          double run, lmin, lmax;
+          bool bad;
+          xd_lane_stats(pr, xd_pow2(-(e2 - 52)), run, lmin, lmax, bad);
+          if (lane < L0) { run = 0; lmin = 0; lmax = 0; bad = false; }
+          const double inc2 = xd_scan_incl(run, lane);
+          const double S2 = sum * xd_pow2(-(e2 - 52));
+          const bool okl = lane < L0 || (!bad && xd_inside(sum > 0, S2 + (inc2 - run), lmin, lmax));
+          const unsigned m2 = __ballot_sync(0xffffffffu, okl);
+          f2 = (m2 == 0xffffffffu) ? 32 : (__ffs(~m2) - 1);
+          if (f2 > L0) {
+            const double tot2 = __shfl_sync(0xffffffffu, inc2, f2 - 1);
+            sum = (S2 + tot2) * xd_pow2(e2 - 52);
           }
-          j = f2;
-          if (j < cntg) {  // one true floating-point addition, exactly what the serial loop does
-            const double pj = __shfl_sync(0xffffffffu, p, j);
-            sum = sum + pj;
-            j++;
-          }
+        }
+        L0 = f2;
+        if (L0 < 32) {  // the 8 elements of lane L0 by true floating-point additions, exactly as the serial loop
+          double t = sum;
+#pragma unroll
+          for (int j = 0; j < 8; j++) t = t + pr[j];
+          sum = __shfl_sync(0xffffffffu, t, L0);
+          L0++;
         }
       }
       pos++;
@@ -596,8 +643,25 @@ static int dot_launch(Ctx* c, const double* a, const double* b, int slot, int po
     CG_LAUNCH_CHECK(c);
     k_xdot_stats<<<g, 256, 0, KS(c, "k_xdot_stats")>>>(c->ndof, nch, a, b, c->xd_tsum, st, c->cnt, skip_done);
     CG_LAUNCH_CHECK(c);
-    k_xdot_walk<<<c->B, 32, 0, KS(c, "k_xdot_walk")>>>(A, nch, a, b, st, c->scal, c->cnt, skip_done);
-    CG_LAUNCH_CHECK(c);
+    {
+      const size_t cache_bytes = (size_t)XD_CACHE * XD_CHUNK * 8, stat_bytes = (size_t)nch * sizeof(XChunk);
+      if (cache_bytes + stat_bytes <= 200 * 1024) {
+        if (!c->xd_attr_set) {
+          CG_CUDA(cudaFuncSetAttribute(k_xdot_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+          c->xd_attr_set = true;
+        }
+        k_xdot_walk<true><<<c->B, XD_WALK_THREADS, cache_bytes + stat_bytes, KS(c, "k_xdot_walk")>>>(A, nch, a, b, st, c->scal,
+                                                                                                c->cnt, skip_done);
+      } else {
+        if (!c->xd_attr_set) {
+          CG_CUDA(cudaFuncSetAttribute(k_xdot_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+          c->xd_attr_set = true;
+        }
+        k_xdot_walk<false><<<c->B, XD_WALK_THREADS, cache_bytes, KS(c, "k_xdot_walk")>>>(A, nch, a, b, st, c->scal, c->cnt,
+                                                                                    skip_done);
+      }
+      CG_LAUNCH_CHECK(c);
+    }
     return CLOTHGPU_OK;
   }
   dim3 g(std::min(div_up(c->ndof, 256), c->npartial), c->B);

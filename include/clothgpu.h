@@ -202,6 +202,33 @@ int clothgpu_step_internal_cg(clothgpu_ctx* ctx, const clothgpu_params* p, doubl
 /* UpdateIntermidiateVelocity, solve_internal_sparse.h:329-369: XYZ -> UVW */
 int clothgpu_update_intermediate_velocity(clothgpu_ctx* ctx, const clothgpu_params* p);
 
+/* ------------------------------------------------------------------------------------------------ element level */
+/* The reference's per-element free functions as batches of n independent elements on the GPU (current device, no
+ * context, synchronous).  The scalar forms of include/clothgpu_compat/ call them with n = 1; the values are the ones
+ * the fused step computes.
+ * MakePositiveDefinite_Sim22, cloth_internal_physics.h:15-67: s2, s3 = n x {s00, s11, s01} */
+int clothgpu_elem_psd_sym22(int n, const double* s2, double* s3);
+/* WdWddW_CST, cloth_internal_physics.h:70-176: C, c = n x [3][3] rest / current positions; W[n]; dW = n x [3][3];
+ * ddW = n x [ino][jno][idim][jdim] (81 per element) */
+int clothgpu_elem_cst(int n, const double* C, const double* c, double lambda, double myu, double* W, double* dW,
+                      double* ddW);
+/* WdWddW_Bend, cloth_internal_physics.h:180-238: C, c = n x [4][3] (vertices 2,3 = shared edge); dW = n x [4][3];
+ * ddW = n x [4][4][3][3] (144 per element).  W is returned from zero (the reference adds to its argument) */
+int clothgpu_elem_bend(int n, const double* C, const double* c, double stiff, double* W, double* dW, double* ddW);
+/* WdWddW_Contact, cloth_internal_physics.h:243-280: pd_normal = n x {pd, nx, ny, nz} as returned by the caller's
+ * penetrationDepth callback (host code); dW = n x 3; ddW = n x [3][3] */
+int clothgpu_elem_contact(int n, const double* pd_normal, double stiff_contact, double contact_clearance, double* W,
+                          double* dW, double* ddW);
+/* DistanceFaceVertex, bvh_aabb.cpp:321-340: p = n x {p0, p1, p2, p3} (12 doubles) -> dist, w0, w1 */
+int clothgpu_dist_face_vertex(int n, const double* p, double* dist, double* w0, double* w1);
+/* DistanceEdgeEdge, bvh_aabb.cpp:343-384: p = n x {p0, p1, q0, q1} -> dist, ratio_p, ratio_q */
+int clothgpu_dist_edge_edge(int n, const double* p, double* dist, double* ratio_p, double* ratio_q);
+/* FindCoplanerInterp, bvh_aabb.cpp:598-662: s, e = n x 4 points at the start / end of the step -> t (or -1) */
+int clothgpu_coplanar_interp(int n, const double* s, const double* e, double* t);
+/* MakeNormal, self_contact_sparse/main.cpp:183-211: unit vertex normals of one scene from a positions buffer (the
+ * demos hand them to the renderer; not part of the timed step).  normals: np*3 doubles out */
+int clothgpu_make_normal(clothgpu_ctx* ctx, int buf_xyz, int scene, double* normals);
+
 /* ------------------------------------------------------------------------------------------------ self collision */
 /* BuildBoundingBoxChild_Prx, bvh_aabb.cpp:23-61: positions buffer -> BOXES */
 int clothgpu_bvh_refit_prx(clothgpu_ctx* ctx, int buf_xyz, double delta);

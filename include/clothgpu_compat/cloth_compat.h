@@ -6,8 +6,9 @@
 // signatures; their bodies (cloth_sim_self_collision_b200/compat/cloth_compat.cpp -> libclothcompat.so) forward to
 // the extern "C" clothgpu_* entry points, which are the only symbols that cross into CUDA code.  The per-reference
 // header names (matrix_square_sparse.h, ilu_sparse.h, solve_internal_sparse.h, self_collision_cloth.h, bvh_aabb.h,
-// jagged_array.h, aabb.h) in this directory just include this file, so a caller compiled with
-// -Iinclude/clothgpu_compat builds unchanged.
+// jagged_array.h, aabb.h, cloth_internal_physics.h) in this directory just include this file; utility.h and vector3d.h
+// are small host-side value helpers of their own.  tests/cpp/Makefile builds the reference's UNCHANGED demo sources
+// (self_contact_sparse/main.cpp, internal_cloth_sparse/main.cpp) against this directory -- see INTEGRATION.md.
 //
 // Semantics kept from the reference: the caller owns all std::vectors; every call takes its inputs from them and
 // writes its outputs back (positions/velocities cross the PCIe bus once per call -- the "e2e" path of bench.py).
@@ -19,7 +20,21 @@
 #include <set>
 #include <vector>
 
+#include "utility.h"   // utility.h:15-123 (double[3] helpers, camera quaternions)
+#include "vector3d.h"  // vector3d.h:33-295 (CVector3D)
+
 struct clothgpu_ctx;
+
+// ---- cloth_internal_physics.h:15-280: the element energies, evaluated on the GPU (clothgpu_elem_*; one element per
+// call here, batches through the C ABI).  Same values as the fused assembly computes.
+void MakePositiveDefinite_Sim22(const double s2[3], double s3[3]);
+void WdWddW_CST(double& W, double dW[3][3], double ddW[3][3][3][3], const double C[3][3], const double c[3][3],
+                const double lambda, const double myu);
+// (the reference ADDS the bending energy to its W argument, cloth_internal_physics.h:235; kept)
+void WdWddW_Bend(double& W, double dW[4][3], double ddW[4][4][3][3], const double C[4][3], const double c[4][3],
+                 double stiff);
+void WdWddW_Contact(double& W, double dW[3], double ddW[3][3], const double c[3], double stiff_contact,
+                    double contact_clearance, void (*penetrationDepth)(double&, double*, const double*));
 
 // ---- jagged_array.h:21-262 (setup side: adjacency lists; the hot path consumes index/array)
 class CJaggedArray {
@@ -66,9 +81,18 @@ public:
   int ino0, ino1, ino2, ino3;
 };
 
-// Setup: a BVH topology over the triangles, root index returned (bvh_aabb.h:25-28).  The reference's builder fails on
-// square grids; this one is a median split over triangle centroids -- any valid binary tree over the
-// triangles is an admissible input of the hot path (node numbering parent < child, leaf: ichild[1] == -1).
+// ---- bvh_aabb.h:49-61: the geometric predicates behind the narrow phase and the impulses, evaluated on the GPU
+// (clothgpu_dist_face_vertex / _edge_edge / clothgpu_coplanar_interp with n = 1)
+double DistanceFaceVertex(const CVector3D& p0, const CVector3D& p1, const CVector3D& p2, const CVector3D& p3,
+                          double& w0, double& w1);
+double DistanceEdgeEdge(const CVector3D& p0, const CVector3D& p1, const CVector3D& q0, const CVector3D& q1,
+                        double& ratio_p, double& ratio_q);
+double FindCoplanerInterp(const CVector3D& s0, const CVector3D& s1, const CVector3D& s2, const CVector3D& s3,
+                          const CVector3D& e0, const CVector3D& e1, const CVector3D& e2, const CVector3D& e3);
+
+// Setup: the BVH topology over the triangles (bvh_aabb.h:25-28, bvh_aabb.cpp:294-313): node for node the array the
+// reference builds (clothgpu_bvh_build_topdown); where the reference crashes on exactly square grids
+// the split falls back to the longest axis.  Returns 0 (the root index the demos store in iroot_bvh).
 int MakeBVHTopology_TopDown(const std::vector<int>& aTri, const std::vector<double>& aXYZ,
                             std::vector<CNodeBVH>& aNodeBVH);
 void BuildBoundingBoxChild_Prx(int ibvh, double delta, const std::vector<double>& aXYZ, const std::vector<int>& aTri,

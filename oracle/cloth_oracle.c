@@ -623,6 +623,27 @@ void orc_cg(int np, const int* rowptr, const int* colidx, const double* valDia, 
   free(Ap); free(p);
 }
 
+/* MakeNormal, self_contact_sparse/main.cpp:183-211 (visualisation hand-off, not part of the timed step): unit triangle
+ * normals (UnitNormalAreaTri3D, utility.h:58-73) scattered to the three corners in triangle order, then normalised */
+void orc_make_normal(int np, int ntri, const int* tri, const double* xyz, double* normal) {
+  int t, a, k, ip;
+  for (k = 0; k < np * 3; k++) normal[k] = 0;
+  for (t = 0; t < ntri; t++) {
+    double n[3], area, invlen;
+    tri_normal(n, xyz + tri[t * 3] * 3, xyz + tri[t * 3 + 1] * 3, xyz + tri[t * 3 + 2] * 3);
+    area = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]) * 0.5;
+    invlen = 0.5 / area;
+    n[0] *= invlen; n[1] *= invlen; n[2] *= invlen;
+    for (a = 0; a < 3; a++)
+      for (k = 0; k < 3; k++) normal[tri[t * 3 + a] * 3 + k] += n[k];
+  }
+  for (ip = 0; ip < np; ip++) {
+    const double sq = normal[ip * 3] * normal[ip * 3] + normal[ip * 3 + 1] * normal[ip * 3 + 1] + normal[ip * 3 + 2] * normal[ip * 3 + 2];
+    const double inv = 1.0 / sqrt(sq);
+    normal[ip * 3] *= inv; normal[ip * 3 + 1] *= inv; normal[ip * 3 + 2] *= inv;
+  }
+}
+
 /* UpdateIntermidiateVelocity, solve_internal_sparse.h:329-369 */
 void orc_update_intermediate_velocity(int np, int ntri, int nquad, const int* tri, const int* quad, const int* bc,
                                       const double* xyz0, const double* xyz, double* uvw, double dt, double lambda,

@@ -39,6 +39,7 @@ void orc_pcg(int np, const int* rowptr, const int* colidx, const double* valDia,
              const double* iluDia, const double* iluCrs, double* r, double* x, double* conv_ratio, int* iteration);
 void orc_cg(int np, const int* rowptr, const int* colidx, const double* valDia, const double* valCrs, double* r,
             double* x, double* conv_ratio, int* iteration);
+void orc_make_normal(int np, int ntri, const int* tri, const double* xyz, double* normal);
 void orc_update_intermediate_velocity(int np, int ntri, int nquad, const int* tri, const int* quad, const int* bc,
                                       const double* xyz0, const double* xyz, double* uvw, double dt, double lambda,
                                       double myu, double stiff_bend, const double* gravity, double mass_point);

@@ -100,6 +100,25 @@ def internal(ref):
     print("traj_internal17: iters", its[:10])
 
 
+def internal26(ref):
+    """The internal_cloth_sparse demo exactly as shipped (internal_cloth_sparse/main.cpp:137-154: ndiv 25, cloth 1 x 1)
+    with the sphere collider (two presses of the space key, :481-488), 40 steps."""
+    sc = S.square_cloth_xy(25, 1.0)
+    p = T.params_for(sc, S.INTERNAL_CLOTH, col_kind=2, col_par=(0.1, 0.5, -0.8, 0.3))
+    sim = ref.sim(sc)
+    xs, vs, its = [], [], []
+    for step in range(1, 41):
+        cr, it = sim.step_internal(p)
+        its.append(it)
+        if step in (10, 40):
+            x, v = sim.get_state()
+            xs.append(x)
+            vs.append(v)
+    np.savez_compressed(os.path.join(OUT, "traj_internal26.npz"), steps=np.array([10, 40]), x=np.array(xs),
+                        v=np.array(vs), iters=np.array(its, dtype=np.int32))
+    print("traj_internal26: iters", its[:10])
+
+
 def bvh_hashes(ref):
     """sha256 of the CNodeBVH arrays MakeBVHTopology_TopDown builds (tests/test_bvh_builder.py::GOLDEN_CASES)."""
     import hashlib
@@ -121,4 +140,5 @@ if __name__ == "__main__":
     phases(ref)
     trajectory(ref)
     internal(ref)
+    internal26(ref)
     bvh_hashes(ref)

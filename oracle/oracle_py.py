@@ -177,6 +177,13 @@ class OracleLib:
                       _dp(r), _dp(x), C.byref(cr), C.byref(it))
         return x, r, cr.value, it.value
 
+    def make_normal(self, sc, xyz):
+        """MakeNormal (self_contact_sparse/main.cpp:183-211); only in the C restatement (the reference keeps it in its
+        GLUT demo source)."""
+        out = np.zeros(sc["np"] * 3)
+        self._f("make_normal")(_i(sc["np"]), _i(sc["ntri"]), _ip(_ci(sc["tri"])), _dp(_cd(xyz)), _dp(out))
+        return out
+
     def update_intermediate_velocity(self, sc, xyz, uvw, p):
         uvw = _cd(uvw).copy()
         self._f("update_intermediate_velocity")(

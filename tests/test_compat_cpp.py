@@ -69,3 +69,69 @@ def test_compat_demo_reproduces_reference_trajectory(demo, tmp_path):
     ex = np.abs(x - gold["x"][k]).max() / np.abs(gold["x"][k]).max()
     ev = np.abs(v - gold["v"][k]).max() / np.abs(gold["v"][k]).max()
     assert np.array_equal(x, gold["x"][k]) and np.array_equal(v, gold["v"][k]), (ex, ev)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's own demo sources, UNCHANGED, compiled against include/clothgpu_compat (tests/cpp/Makefile: a shadow
+# tree makes their "../x.h" includes resolve to the drop-in headers, tests/cpp/glut_stub stands in for GLUT).  The
+# binaries are built where /root/reference exists and travel with the snapshot.
+REF_BINS = {name: os.path.join(ROOT, "tests", "cpp", "_build", "ref_" + name)
+            for name in ("self_contact_sparse", "internal_cloth_sparse")}
+
+
+@pytest.fixture(scope="module")
+def ref_demos(demo):
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")])
+    missing = [b for b in REF_BINS.values() if not os.path.exists(b)]
+    if missing:
+        pytest.skip("reference demos not built (needs /root/reference at build time): %s" % missing)
+    return REF_BINS
+
+
+def _run_demo(binary, keys, steps, dump):
+    env = dict(os.environ, CLOTHGPU_GLUT_KEYS=keys, CLOTHGPU_GLUT_STEPS=str(steps), CLOTHGPU_GLUT_DUMP=str(dump))
+    return subprocess.run([binary], capture_output=True, text=True, env=env, timeout=900)
+
+
+def _read_dump(path):
+    raw = open(path, "rb").read()
+    npnt, = struct.unpack("i", raw[:4])
+    x = np.frombuffer(raw, dtype=np.float64, count=npnt * 3, offset=4)
+    v = np.frombuffer(raw, dtype=np.float64, count=npnt * 3, offset=4 + npnt * 24)
+    return npnt, x, v
+
+
+def test_reference_demos_refuse_to_compute_without_gpu(ref_demos, tmp_path):
+    if G.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    for b in ref_demos.values():
+        out = _run_demo(b, "a", 1, tmp_path / "o.bin")
+        assert out.returncode != 0 and "no CPU fallback" in out.stderr
+
+
+@pytest.mark.gpu
+def test_unchanged_self_contact_sparse_main_reproduces_reference(ref_demos, tmp_path):
+    """self_contact_sparse/main.cpp as shipped: its own main() (scene, MakeBVHTopology_TopDown, SetPattern,
+    Initialize_ILU0) and StepTime() through the drop-in, 40 steps: bit-identical to the reference's trajectory."""
+    gold = np.load(os.path.join(GOLD, "traj_config1.npz"))
+    steps = [int(s) for s in gold["steps"]]
+    for step in (10, 40):
+        out = _run_demo(ref_demos["self_contact_sparse"], "a", step, tmp_path / "o.bin")
+        assert out.returncode == 0, out.stderr + out.stdout
+        npnt, x, v = _read_dump(tmp_path / "o.bin")
+        k = steps.index(step)
+        assert npnt == 255
+        assert np.array_equal(x, gold["x"][k]) and np.array_equal(v, gold["v"][k]), step
+
+
+@pytest.mark.gpu
+def test_unchanged_internal_cloth_sparse_main_reproduces_reference(ref_demos, tmp_path):
+    """internal_cloth_sparse/main.cpp as shipped (26 x 26, pinned row), sphere collider selected with two presses of the
+    space key, then 'a': the host callback collider goes through the per-vertex table path."""
+    gold = np.load(os.path.join(GOLD, "traj_internal26.npz"))
+    for k, step in enumerate(int(s) for s in gold["steps"]):
+        out = _run_demo(ref_demos["internal_cloth_sparse"], "  a", step, tmp_path / "o.bin")
+        assert out.returncode == 0, out.stderr + out.stdout
+        npnt, x, v = _read_dump(tmp_path / "o.bin")
+        assert npnt == 26 * 26
+        assert np.array_equal(x, gold["x"][k]) and np.array_equal(v, gold["v"][k]), step

@@ -750,3 +750,62 @@ def test_tree_dot_fast_mode(oracle, monkeypatch):
     assert runs[0][1] == oits
     assert rel_err(runs[0][0][0], ox) < RTOL and rel_err(runs[0][0][1], ov) < 1.0e-7
     assert not np.array_equal(runs[0][0][1], ov), "the tree mode is not expected to be bit-identical"
+
+
+def test_element_level_entry_points(oracle):
+    """The reference's per-element free functions (cloth_internal_physics.h, bvh_aabb.h:49-61) as GPU batches through
+    the C ABI: bit-identical to the oracle, element by element."""
+    rng = np.random.default_rng(23)
+    n = 300
+    C3 = rng.standard_normal((n, 3, 3))
+    c3 = C3 + 0.3 * rng.standard_normal((n, 3, 3))
+    for lam, myu in ((0.0, 30.0), (1.0, 4.0)):
+        W, dW, ddW = G.elem_cst(C3, c3, lam, myu)
+        for k in range(0, n, 7):
+            ow, odw, oddw = oracle.cst(C3[k], c3[k], lam, myu)
+            assert W[k] == ow and np.array_equal(dW[k].ravel(), np.ravel(odw)) and np.array_equal(ddW[k].ravel(), np.ravel(oddw))
+    C4 = rng.standard_normal((n, 4, 3))
+    c4 = C4 + 0.2 * rng.standard_normal((n, 4, 3))
+    W, dW, ddW = G.elem_bend(C4, c4, 1.0e-2)
+    for k in range(0, n, 7):
+        ow, odw, oddw = oracle.bend(C4[k], c4[k], 1.0e-2)
+        assert W[k] == ow and np.array_equal(dW[k].ravel(), np.ravel(odw)) and np.array_equal(ddW[k].ravel(), np.ravel(oddw))
+    # contact: the plane collider's (pd, n) evaluated here like the host callback would
+    pts = rng.standard_normal((n, 3))
+    pdn = np.stack([-0.5 - pts[:, 2], np.zeros(n), np.zeros(n), np.ones(n)], axis=1)
+    W, dW, ddW = G.elem_contact(pdn, 300.0, 0.01)
+    for k in range(0, n, 7):
+        ow, odw, oddw = oracle.contact(pts[k], 300.0, 0.01, 1, (-0.5, 0, 0, 0))
+        assert W[k] == ow and np.array_equal(dW[k], np.ravel(odw)) and np.array_equal(ddW[k].ravel(), np.ravel(oddw))
+    assert (W > 0).any() and (W == 0).any()
+    # stress clamp
+    s2 = rng.standard_normal((n, 3)) * np.array([1.0, 1.0, 0.5])
+    s3 = G.elem_psd_sym22(s2)
+    lam_min = 0.5 * (s3[:, 0] + s3[:, 1]) - np.sqrt(0.25 * (s3[:, 0] - s3[:, 1]) ** 2 + s3[:, 2] ** 2)
+    assert np.all(lam_min > -1e-12)
+    psd = 0.5 * (s2[:, 0] + s2[:, 1]) - np.sqrt(0.25 * (s2[:, 0] - s2[:, 1]) ** 2 + s2[:, 2] ** 2) > 1e-20
+    assert np.array_equal(s3[psd], s2[psd]) and psd.any() and (~psd).any()
+    # geometric predicates
+    P = rng.standard_normal((n, 4, 3))
+    P[::5, 1] = P[::5, 0] + 1e-13 * rng.standard_normal((len(P[::5]), 3))  # nearly degenerate / parallel cases
+    d, w0, w1 = G.dist_face_vertex(P)
+    e, rp, rq = G.dist_edge_edge(P)
+    Q = P + 0.3 * rng.standard_normal((n, 4, 3))
+    t = G.coplanar_interp(P, Q)
+    for k in range(n):
+        assert (d[k], w0[k], w1[k]) == tuple(oracle.dist_fv(P[k]))
+        assert (e[k], rp[k], rq[k]) == tuple(oracle.dist_ee(P[k]))
+        assert t[k] == oracle.coplanar(P[k], Q[k])
+    assert (t >= 0).any() and (t < 0).any()
+
+
+def test_make_normal(oracle, sc_contact):
+    """clothgpu_make_normal == MakeNormal of the demos (self_contact_sparse/main.cpp:183-211), bit for bit."""
+    sc = S.square_cloth_xz(30, 17, 0.1)
+    x, v = T.wavy_state(sc)
+    g = G.ClothGPU(sc, with_bvh=False)
+    g.upload_state(x, v)
+    nrm = g.make_normal(G.BUF_XYZ)
+    assert np.array_equal(nrm, oracle.make_normal(sc, x))
+    assert np.allclose(np.linalg.norm(nrm.reshape(-1, 3), axis=1), 1.0)
+    g.close()
