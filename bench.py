@@ -447,6 +447,15 @@ def run_ours(args):
         barrier()
         nleaf_b = int(len(gb.leaf_pairs(0)))
         bsum = [BT.state_checksum(gb.download_state(s)[0]) for s in range(Sb)]
+        bkern = None
+        if rank == 0:  # where the batch step spends its time: per-kernel device times of one more step
+            gb.set_kernel_timing(True)
+            gb.step_self_contact(p, 1)
+            bk = gb.kernel_times()
+            gb.set_kernel_timing(False)
+            btot = sum(v[1] for v in bk.values())
+            bkern = {"step_ms_sum_of_kernels": btot,
+                     "top": {k: {"launches": n, "ms": ms} for k, (n, ms) in sorted(bk.items(), key=lambda kv: -kv[1][1])[:14]}}
         gb.close()
         if dist is not None:
             bms = BT.max_over_ranks(dist, [bms], device="cuda")[0]
@@ -462,7 +471,8 @@ def run_ours(args):
                  "algorithmic_bytes_per_scene_step": per_scene_bytes, "achieved_GBps_per_gpu": gbps,
                  "frac_of_hbm_peak": gbps / peak if gbps else None, "peak": peak,
                  "stats_scene0_last": [int(k) for k in bst[0][:5]],
-                 "pcg_iters_mean": its, "detection_passes_mean": passes, "checksums": bsum[:4]}
+                 "pcg_iters_mean": its, "detection_passes_mean": passes, "checksums": bsum[:4],
+                 "kernels_one_step": bkern}
 
     # ---- max over ranks
     if dist is not None:

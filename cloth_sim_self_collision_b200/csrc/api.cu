@@ -38,7 +38,7 @@ int run_resolve(Ctx* c, const clothgpu_params& p, int* applied, int* stats, bool
   // main stream has already joined it.
   if (!prox_prelaunched) {
     CG_CHECK(set_active(c, nullptr));
-    phase_begin(c);
+    phase_begin(c, 3);
     CG_CHECK(launch_refit(c, x, nullptr, delta, 0));
     phase_end(c, 3);
   }
@@ -52,7 +52,7 @@ int run_resolve(Ctx* c, const clothgpu_params& p, int* applied, int* stats, bool
   // (with a skipped detection the reference applies the proximity impulse to an empty set: the element list of an
   // earlier pass must not be picked up)
   if (delta * 0.5 > 0) {
-    phase_begin(c);
+    phase_begin(c, 6);
     CG_CHECK(launch_impulse(c, x, v, delta, p.stiff_contact, dt, p.mass_point, 0));
     phase_end(c, 6);
   }
@@ -61,7 +61,7 @@ int run_resolve(Ctx* c, const clothgpu_params& p, int* applied, int* stats, bool
   for (int itr = 0; itr < 5 && nactive > 0; itr++) {
     // from the second pass on only the velocities of the vertices the impulses touched have changed: incremental
     const bool inc = c->incremental_ccd && itr > 0;
-    phase_begin(c);
+    phase_begin(c, 3);
     CG_CHECK(launch_refit(c, x, v, dt, 1, inc));
     phase_end(c, 3);
     CG_CHECK(run_contacts(c, x, v, dt, delta, 1, n.data(), false, inc));
@@ -74,7 +74,7 @@ int run_resolve(Ctx* c, const clothgpu_params& p, int* applied, int* stats, bool
     }
     if (nactive == 0) break;
     CG_CHECK(set_active(c, act.data()));
-    phase_begin(c);
+    phase_begin(c, 6);
     CG_CHECK(launch_impulse(c, x, v, delta, p.stiff_contact, dt, p.mass_point, 1));
     phase_end(c, 6);
   }
@@ -83,7 +83,7 @@ int run_resolve(Ctx* c, const clothgpu_params& p, int* applied, int* stats, bool
     CG_CHECK(copy_vec(c, v, c->uvw0));
     CG_CHECK(launch_riz_reset(c));
     for (int itr = 0; itr < 100 && nactive > 0; itr++) {
-      phase_begin(c);
+      phase_begin(c, 3);
       CG_CHECK(launch_refit(c, x, v, dt, 1, c->incremental_ccd));
       phase_end(c, 3);
       CG_CHECK(run_contacts(c, x, v, dt, delta, 1, n.data(), false, c->incremental_ccd));
@@ -100,7 +100,7 @@ int run_resolve(Ctx* c, const clothgpu_params& p, int* applied, int* stats, bool
       }
       if (nactive == 0) break;
       CG_CHECK(set_active(c, act.data()));
-      phase_begin(c);
+      phase_begin(c, 7);
       CG_CHECK(launch_riz_make(c));
       CG_CHECK(launch_riz_apply(c, x, v));
       phase_end(c, 7);
@@ -372,7 +372,7 @@ int clothgpu_step_self_contact(clothgpu_ctx* c, const clothgpu_params* p, int ns
     for (int s = 0; s < c->B; s++) any = any || applied[s];
     if (any) {  // :246-261: re-integrate positions, then the half-step force correction
       CG_CHECK(set_active(c, applied.data()));
-      phase_begin(c);
+      phase_begin(c, 8);
       dim3 g(std::min(div_up(c->ndof, 256), 296), c->B);
       k_reintegrate<<<g, 256, 0, KS(c, "k_reintegrate")>>>(c->ndof, p->dt, c->xyz_prev, c->uvw, c->xyz, c->cnt);
       CG_LAUNCH_CHECK(c);

@@ -690,7 +690,7 @@ int run_contacts(Ctx* c, const double* xyz, const double* uvw, double dt, double
                  bool prelaunched, bool incremental) {
   if (c->nnode == 0) { set_error("context has no BVH"); return CLOTHGPU_ERR_STATE; }
   for (int attempt = 0;; attempt++) {
-    phase_begin(c);
+    phase_begin(c, 4);
     // a retry after a queue overflow is always a full pass (the previous raw list does not survive the regrowth)
     if (!(prelaunched && attempt == 0)) CG_CHECK(traverse_and_test(c, xyz, uvw, dt, delta, ccd, incremental && attempt == 0));
     CG_CHECK(fetch_counters(c));
@@ -701,7 +701,7 @@ int run_contacts(Ctx* c, const double* xyz, const double* uvw, double dt, double
     if (attempt >= 12) { set_error("contact work queues keep overflowing"); return CLOTHGPU_ERR_CAPACITY; }
     CG_CHECK(grow_queues(c, bits));
   }
-  phase_begin(c);
+  phase_begin(c, 5);
   for (int s = 0; s < c->B; s++) {
     if (!c->h_cnt[s * NCNT + CNT_ACTIVE]) continue;
     CG_CHECK(canonical_set(c, s, c->h_cnt[s * NCNT + CNT_RAW]));

@@ -12,6 +12,8 @@
 #include <cstring>
 #include <limits>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "ctx.h"
 
 namespace cg {
@@ -136,10 +138,16 @@ void ktime_end(Ctx* c) {
   c->kt_name = nullptr;
 }
 
-void phase_begin(Ctx* c) {
+// phases of a step: NVTX ranges always (free without a tool attached; nsys / ncu --nvtx show them), device timers
+// only in profiling mode (they synchronise)
+static const char* const kPhaseName[CLOTHGPU_NPHASE] = {"assembly", "ilu_factor", "pcg", "bvh_refit", "traverse_narrow",
+                                                        "sort_unique", "impulse", "riz", "velocity_fixup"};
+void phase_begin(Ctx* c, int phase) {
+  nvtxRangePushA((phase >= 0 && phase < CLOTHGPU_NPHASE && kPhaseName[phase]) ? kPhaseName[phase] : "clothgpu");
   if (c->profiling) cudaEventRecord(c->evp0, c->stream);
 }
 void phase_end(Ctx* c, int phase) {
+  nvtxRangePop();
   if (!c->profiling) return;
   cudaEventRecord(c->evp1, c->stream);
   cudaEventSynchronize(c->evp1);

@@ -247,7 +247,7 @@ int buf_info(Ctx* c, int buf, int scene, BufInfo* out);
 double* vec_buf(Ctx* c, int buf);  // scene 0 pointer of a np*3 vector buffer, or null
 
 // phase timing helpers (no-ops unless profiling is on)
-void phase_begin(Ctx* c);
+void phase_begin(Ctx* c, int phase);
 void phase_end(Ctx* c, int phase);
 
 // ---- kernels' host launchers (one translation unit each)

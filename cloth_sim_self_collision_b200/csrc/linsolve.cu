@@ -809,19 +809,19 @@ int run_cg(Ctx* c, double tol, int max_iter, double* conv_out, int* iter_out) {
 
 // StepTime_InternalDynamicsILU (solve_internal_sparse.h:255-326) / StepTime_InternalDynamics (:185-253)
 int run_step_internal(Ctx* c, const clothgpu_params& p, bool use_ilu, double* conv_out, int* iter_out) {
-  phase_begin(c);
+  phase_begin(c, 0);
   CG_CHECK(launch_assemble(c, p, true));
   phase_end(c, 0);
   if (use_ilu) {
-    phase_begin(c);
+    phase_begin(c, 1);
     CG_CHECK(launch_ilu_setvalue(c));
     CG_CHECK(launch_ilu_factor(c));
     phase_end(c, 1);
-    phase_begin(c);
+    phase_begin(c, 2);
     CG_CHECK(run_pcg(c, 1.0e-4, 100, conv_out, iter_out));
     phase_end(c, 2);
   } else {
-    phase_begin(c);
+    phase_begin(c, 2);
     CG_CHECK(run_cg(c, 1.0e-4, 1000, conv_out, iter_out));
     phase_end(c, 2);
   }

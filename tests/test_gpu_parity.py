@@ -792,10 +792,13 @@ def test_element_level_entry_points(oracle):
     e, rp, rq = G.dist_edge_edge(P)
     Q = P + 0.3 * rng.standard_normal((n, 4, 3))
     t = G.coplanar_interp(P, Q)
+    def bits(*vals):  # bit patterns: the nearly degenerate inputs give inf / nan on both sides
+        return np.array(vals, dtype=np.float64).tobytes()
+
     for k in range(n):
-        assert (d[k], w0[k], w1[k]) == tuple(oracle.dist_fv(P[k]))
-        assert (e[k], rp[k], rq[k]) == tuple(oracle.dist_ee(P[k]))
-        assert t[k] == oracle.coplanar(P[k], Q[k])
+        assert bits(d[k], w0[k], w1[k]) == bits(*oracle.dist_fv(P[k])), k
+        assert bits(e[k], rp[k], rq[k]) == bits(*oracle.dist_ee(P[k])), k
+        assert bits(t[k]) == bits(oracle.coplanar(P[k], Q[k])), k
     assert (t >= 0).any() and (t < 0).any()
 
 
