@@ -17,7 +17,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libclothgpu.so")
 
-NSTATS = 128
+NSTATS = 256
 NPHASE = 16
 PHASE_NAMES = ["assembly", "ilu_factor", "pcg", "bvh_refit", "traverse_narrow", "sort_unique", "impulse", "riz",
                "velocity_fixup"]
@@ -130,6 +130,25 @@ def _ip(a):
 
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def build_adjacency(elem, nnoel, nnode, with_diagonal=False):
+    """CJaggedArray::SetEdgeOfElem + Sort on the GPU (clothgpu_build_adjacency): (index[nnode+1], array[nnz]) with
+    ascending unique columns -- the block-CRS pattern for the hinge quads, aEdge for the triangles."""
+    lib = load()
+    elem = _ci(elem).ravel()
+    nelem = elem.size // nnoel
+    index = np.zeros(nnode + 1, dtype=np.int32)
+    n = lib.clothgpu_build_adjacency(C.c_int(nelem), C.c_int(nnoel), _ip(elem), C.c_int(nnode), C.c_int(int(with_diagonal)),
+                                     _ip(index), None, C.c_int(0))
+    if n < 0:
+        raise ClothGPUError("clothgpu error %d: %s" % (-n, lib.clothgpu_last_error().decode()))
+    array = np.zeros(max(n, 1), dtype=np.int32)
+    n2 = lib.clothgpu_build_adjacency(C.c_int(nelem), C.c_int(nnoel), _ip(elem), C.c_int(nnode), C.c_int(int(with_diagonal)),
+                                      _ip(index), _ip(array), C.c_int(array.size))
+    if n2 != n:
+        raise ClothGPUError("clothgpu error: %s" % lib.clothgpu_last_error().decode())
+    return index, array[:n]
 
 
 def _elem_call(fn, n, ins, outs, scalars=()):

@@ -94,6 +94,8 @@ int run_resolve(Ctx* c, const clothgpu_params& p, int* applied, int* stats, bool
           stats[s * CLOTHGPU_NSTATS + 16 + itr] = n[s];
           stats[s * CLOTHGPU_NSTATS + 3] = itr + 1;
           stats[s * CLOTHGPU_NSTATS + 5] = itr == 0 ? 0 : c->h_cnt[s * NCNT + CNT_RIZ_NODES];
+          stats[s * CLOTHGPU_NSTATS + 128 + itr] = stats[s * CLOTHGPU_NSTATS + 5];
+          if (n[s] == 0) stats[s * CLOTHGPU_NSTATS + 6] = 1;
         }
         if (n[s] == 0) act[s] = 0;
         else nactive++;

@@ -135,6 +135,8 @@ void ktime_end(Ctx* c) {
   auto& e = c->ktimes[c->kt_name];
   e.first += ms;
   e.second += 1;
+  static const bool trace = getenv("CLOTHGPU_KTRACE") != nullptr;  // one line per launch (measurement aid)
+  if (trace) fprintf(stderr, "ktrace %s %.3f us\n", c->kt_name, ms * 1000.0);
   c->kt_name = nullptr;
 }
 
@@ -200,7 +202,8 @@ int buf_info(Ctx* c, int buf, int scene, BufInfo* o) {
 
 // ---------------------------------------------------------------------------------------------- precomputation
 static int build_topology(Ctx* c, const int* tri, const int* quad, const int* rowptr, const int* colidx) {
-  const int np = c->np, ntri = c->ntri, nquad = c->nquad, ncrs = c->ncrs;
+  const int np = c->np;
+  (void)tri; (void)quad;
   // Initialize_ILU0's m_diaInd (ilu_sparse.cpp:114-134): first slot of the row whose column is above the diagonal
   std::vector<int> dia(np);
   for (int i = 0; i < np; i++) {
@@ -208,13 +211,8 @@ static int build_topology(Ctx* c, const int* tri, const int* quad, const int* ro
     for (int j = rowptr[i]; j < rowptr[i + 1]; j++)
       if (colidx[j] > i) { dia[i] = j; break; }
   }
-  CG_CHECK(dev_upload(&c->diaind, dia));
-  {
-    std::vector<int> slot_row(ncrs);
-    for (int i = 0; i < np; i++)
-      for (int j = rowptr[i]; j < rowptr[i + 1]; j++) slot_row[j] = i;
-    CG_CHECK(dev_upload(&c->slot_row, slot_row));
-  }
+  // (the device copy of diaind, the slot -> row map and the assembly gather lists are built on the device: setup.cu)
+  CG_CHECK(build_topology_device(c));
 
   // dependency levels of the forward (L) and backward (U) sweeps; rows of one level are mutually independent
   auto levelize = [&](bool fwd, int& nlev, int& maxrows, int** d_ptr, int** d_rows) -> int {
@@ -308,62 +306,6 @@ static int build_topology(Ctx* c, const int* tri, const int* quad, const int* ro
     CG_CHECK(dev_upload(&c->ops, ops));
   }
 
-  // assembly gather lists.  The reference scatters element by element (AddWdWddW_Cloth, solve_internal_sparse.h:
-  // 36-75: triangles ascending, then hinges ascending), so every destination sums its contributions in element
-  // order; listing them per destination in that order makes the sum bit-identical and atomic-free.
-  {
-    std::vector<int> vt_ptr(np + 1, 0), vq_ptr(np + 1, 0), st_ptr(ncrs + 1, 0), sq_ptr(ncrs + 1, 0);
-    auto find_slot = [&](int row, int col) -> int {
-      const int* b = colidx + rowptr[row];
-      const int* e = colidx + rowptr[row + 1];
-      const int* it = std::lower_bound(b, e, col);
-      return (it != e && *it == col) ? (int)(it - colidx) : -1;
-    };
-    for (int pass = 0; pass < 2; pass++) {
-      std::vector<int> vt_fill, vq_fill, st_fill, sq_fill;
-      std::vector<int> vt_ent, vq_ent, st_ent, sq_ent;
-      if (pass == 1) {
-        for (int i = 0; i < np; i++) { vt_ptr[i + 1] += vt_ptr[i]; vq_ptr[i + 1] += vq_ptr[i]; }
-        for (int j = 0; j < ncrs; j++) { st_ptr[j + 1] += st_ptr[j]; sq_ptr[j + 1] += sq_ptr[j]; }
-        vt_fill.assign(vt_ptr.begin(), vt_ptr.end() - 1);
-        vq_fill.assign(vq_ptr.begin(), vq_ptr.end() - 1);
-        st_fill.assign(st_ptr.begin(), st_ptr.end() - 1);
-        sq_fill.assign(sq_ptr.begin(), sq_ptr.end() - 1);
-        vt_ent.resize(vt_ptr[np]); vq_ent.resize(vq_ptr[np]);
-        st_ent.resize(st_ptr[ncrs]); sq_ent.resize(sq_ptr[ncrs]);
-      }
-      for (int t = 0; t < ntri; t++) {
-        const int* n = tri + t * 3;
-        for (int a = 0; a < 3; a++) {
-          if (pass == 0) vt_ptr[n[a] + 1]++; else vt_ent[vt_fill[n[a]]++] = t * 3 + a;
-          for (int b = 0; b < 3; b++) {
-            if (a == b) continue;
-            const int s = find_slot(n[a], n[b]);
-            if (s < 0) continue;  // Mearge drops blocks outside the pattern (matrix_square_sparse.cpp:122)
-            if (pass == 0) st_ptr[s + 1]++; else st_ent[st_fill[s]++] = t * 9 + a * 3 + b;
-          }
-        }
-      }
-      for (int q = 0; q < nquad; q++) {
-        const int* n = quad + q * 4;
-        for (int a = 0; a < 4; a++) {
-          if (pass == 0) vq_ptr[n[a] + 1]++; else vq_ent[vq_fill[n[a]]++] = q * 4 + a;
-          for (int b = 0; b < 4; b++) {
-            if (a == b) continue;
-            const int s = find_slot(n[a], n[b]);
-            if (s < 0) continue;
-            if (pass == 0) sq_ptr[s + 1]++; else sq_ent[sq_fill[s]++] = q * 16 + a * 4 + b;
-          }
-        }
-      }
-      if (pass == 1) {
-        CG_CHECK(dev_upload(&c->vt_ptr, vt_ptr)); CG_CHECK(dev_upload(&c->vt_ent, vt_ent));
-        CG_CHECK(dev_upload(&c->vq_ptr, vq_ptr)); CG_CHECK(dev_upload(&c->vq_ent, vq_ent));
-        CG_CHECK(dev_upload(&c->st_ptr, st_ptr)); CG_CHECK(dev_upload(&c->st_ent, st_ent));
-        CG_CHECK(dev_upload(&c->sq_ptr, sq_ptr)); CG_CHECK(dev_upload(&c->sq_ent, sq_ent));
-      }
-    }
-  }
   return CLOTHGPU_OK;
 }
 
@@ -693,6 +635,15 @@ int clothgpu_set_scene_gravity(clothgpu_ctx* c, int scene, const double* g) {
   }
   if (scene >= c->B || !g) { set_error("bad argument"); return CLOTHGPU_ERR_ARG; }
   for (int k = 0; k < 3; k++) c->gravity_override[(size_t)scene * 3 + k] = g[k];
+  return CLOTHGPU_OK;
+}
+
+int clothgpu_last_solver(clothgpu_ctx* c, double* conv_ratio, int* iteration) {
+  if (!c) { set_error("null context"); return CLOTHGPU_ERR_ARG; }
+  for (int s = 0; s < c->B; s++) {
+    if (conv_ratio) conv_ratio[s] = c->h_scal[s * NSCAL + SC_CONV];
+    if (iteration) iteration[s] = c->h_cnt[s * NCNT + CNT_PCG_ITER];
+  }
   return CLOTHGPU_OK;
 }
 

@@ -290,6 +290,7 @@ int ensure_scratch(Ctx* c, size_t bytes);
 int ensure_sort_capacity(Ctx* c, long long n);
 int grow_queues(Ctx* c, int overflow_bits);
 int set_active(Ctx* c, const int* active);
+int build_topology_device(Ctx* c);  // setup.cu: diaind, slot rows, assembly gather lists
 int bvh_build_topdown_host(int ntri, const int* tri, int np, const double* xyz, std::vector<int>& nodes, int* nfallback);  // per-scene participation flags (null: all scenes)
 
 }  // namespace cg

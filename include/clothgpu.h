@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CLOTHGPU_VERSION 100
+#define CLOTHGPU_VERSION 200
 
 typedef struct clothgpu_ctx clothgpu_ctx;
 
@@ -99,9 +99,10 @@ enum {
 
 /* per-step statistics, the machine-readable form of the reference's stdout prints
  * (solve_internal_sparse.h:321, self_collision_cloth.cpp:386,415,448) */
-enum { CLOTHGPU_NSTATS = 128 };
+enum { CLOTHGPU_NSTATS = 256 };
 /* stats[0]=PCG iteration, [1]=#proximity elems, [2]=#CCD impulse passes run, [3]=#RIZ rounds run,
- * [4]=is_impulse_applied, [5]=last "NNode In RIZ", [8..13)=CCD elems per impulse pass, [16..116)=CCD elems per RIZ round */
+ * [4]=is_impulse_applied, [5]=last "NNode In RIZ", [6]=1 if the RIZ loop ended with "Resolved All Collisions",
+ * [8..13)=CCD elems per impulse pass, [16..116)=CCD elems per RIZ round, [128..228)="NNode In RIZ" per RIZ round */
 
 /* ------------------------------------------------------------------------------------------------ life cycle */
 const char* clothgpu_last_error(void);
@@ -119,6 +120,14 @@ int clothgpu_create(clothgpu_ctx** out, int device, int nscene, int np, int ntri
                     const int* crs_colidx, int nnode, const int* bvh_nodes, const int* edge_index,
                     const int* edge_array);
 void clothgpu_destroy(clothgpu_ctx* ctx);
+
+/* CJaggedArray::SetEdgeOfElem + Sort (jagged_array.h:158-207, 71-90), i.e. the input of CMatrixSquareSparse::SetPattern
+ * (matrix_square_sparse.cpp:140-163) when called with the hinge quads and aEdge when called with the triangles: the
+ * vertex -> vertex adjacency of an element list as CSR with ascending, unique columns, built on the GPU (one 64-bit
+ * radix sort + unique of the (row, col) pairs).  elem: nelem x nnoel; index[nnode+1], array[cap] out (array may be
+ * NULL to query the size).  Returns the number of entries, or -CLOTHGPU_ERR_*. */
+int clothgpu_build_adjacency(int nelem, int nnoel, const int* elem, int nnode, int with_diagonal, int* index,
+                             int* array, int cap);
 
 /* MakeBVHTopology_TopDown, bvh_aabb.cpp:294-313 (MakeTriSurTri :109-138, DevideTriAryConnex :156-290): BVH topology
  * over the triangles, node for node the array the reference builds (same splits, same list orders, same numbering)
@@ -199,6 +208,9 @@ int clothgpu_cg(clothgpu_ctx* ctx, double* conv_ratio, int* iteration);
 int clothgpu_step_internal_ilu(clothgpu_ctx* ctx, const clothgpu_params* p, double* conv_ratio, int* iteration);
 /* StepTime_InternalDynamics, solve_internal_sparse.h:185-253 (CG, 1e-4 / 1000) */
 int clothgpu_step_internal_cg(clothgpu_ctx* ctx, const clothgpu_params* p, double* conv_ratio, int* iteration);
+/* conv_ratio / iteration of the most recent PCG or CG solve of the context (the values the reference prints at
+ * solve_internal_sparse.h:248,321), nscene values each; either pointer may be NULL.  No device work. */
+int clothgpu_last_solver(clothgpu_ctx* ctx, double* conv_ratio, int* iteration);
 /* UpdateIntermidiateVelocity, solve_internal_sparse.h:329-369: XYZ -> UVW */
 int clothgpu_update_intermediate_velocity(clothgpu_ctx* ctx, const clothgpu_params* p);
 

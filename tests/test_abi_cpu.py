@@ -34,7 +34,7 @@ def test_exports_every_declared_symbol(lib):
 
 
 def test_version_and_struct_layout(lib):
-    assert lib.clothgpu_version() == 100
+    assert lib.clothgpu_version() == 200
     # clothgpu_params: 10 doubles, 2 ints, 4 doubles
     assert C.sizeof(G.Params) == 10 * 8 + 2 * 4 + 4 * 8
 

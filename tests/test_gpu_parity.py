@@ -812,3 +812,33 @@ def test_make_normal(oracle, sc_contact):
     assert np.array_equal(nrm, oracle.make_normal(sc, x))
     assert np.allclose(np.linalg.norm(nrm.reshape(-1, 3), axis=1), 1.0)
     g.close()
+
+
+def test_device_side_setup(oracle):
+    """Topology set-up on the device (csrc/setup.cu): clothgpu_build_adjacency gives the pattern SetPattern takes
+    (SetEdgeOfElem on the hinge quads + Sort) and aEdge (on the triangles); the gather lists / diaind built on the device
+    at context creation are exercised by every assembly test (bit-exact matrices) -- here once more on a renumbered
+    mesh whose rows have scattered neighbours."""
+    for sc in (S.square_cloth_xz(7, 5, 0.1), S.relabelled(S.square_cloth_xz(23, 30, 0.1)), S.config3_256()):
+        for elem, nnoel, key_i, key_a in ((sc["quad"], 4, "rowptr", "colidx"), (sc["tri"], 3, "edge_index", "edge_array")):
+            index, array = G.build_adjacency(elem, nnoel, sc["np"])
+            assert np.array_equal(index, sc[key_i]) and np.array_equal(array, sc[key_a])
+        if sc["np"] < 2000:
+            oi, oa = oracle.edge_of_elem(sc["quad"], 4, sc["np"], True)
+            index, array = G.build_adjacency(sc["quad"], 4, sc["np"])
+            assert np.array_equal(index, oi) and np.array_equal(array, oa)
+            di, da = G.build_adjacency(sc["tri"], 3, sc["np"], with_diagonal=True)
+            assert len(da) == len(sc["edge_array"]) + sc["np"]
+    with pytest.raises(G.ClothGPUError):
+        G.build_adjacency(np.array([0, 1, 99], dtype=np.int32), 3, 5)
+    sc = S.relabelled(S.square_cloth_xz(23, 30, 0.1))
+    p = T.params_for(sc, S.SELF_CONTACT)
+    x = sc["xyz0"] + 0.01 * np.random.default_rng(2).standard_normal(sc["np"] * 3)
+    v = np.random.default_rng(3).standard_normal(sc["np"] * 3)
+    g = G.ClothGPU(sc, with_bvh=False)
+    g.upload_state(x, v)
+    g.assemble(p)
+    dia, crs, b = oracle.assemble(sc, x, v, p)
+    assert np.array_equal(g.read(G.BUF_VAL_DIA), dia) and np.array_equal(g.read(G.BUF_VAL_CRS), crs)
+    assert np.array_equal(g.read(G.BUF_VEC_R), b)
+    g.close()
