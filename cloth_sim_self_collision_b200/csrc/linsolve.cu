@@ -12,6 +12,10 @@
 // The triangular solves and the factorisation are dependency chains over the rows (1021 levels on a 256^2 grid in
 // the reference's natural ordering, which parity forces us to keep): one CTA per scene walks the levels with a
 // block barrier per level; rows of a level are independent.  Batches of scenes run one CTA each, concurrently.
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+
 #include "ctx.h"
 
 namespace cg {
@@ -289,57 +293,25 @@ __global__ void __launch_bounds__(256) k_xdot_stats(int n, int nch, const double
   if (lane == 0) st[(size_t)s * nch + c] = out;
 }
 
-enum { XD_WALK_THREADS = 256, XD_CACHE = 24 };  // product cache: chunks whose slow path is foreseeable
+enum { XD_WALK_THREADS = 256, XD_CACHE = 24 };  // cached "suspect" chunks: those whose slow path is foreseeable
 
-// one CTA per scene: all threads stage the chunk statistics (and the products of the chunks that will foreseeably
-// need the slow path: flagged ones, and those where the predicted binade changes) in shared memory, then warp 0 walks
-template <bool SMEM_STATS>
-__global__ void __launch_bounds__(XD_WALK_THREADS) k_xdot_walk(DotArgs A, int nch, const double* __restrict__ a,
-                                                                const double* __restrict__ b,
-                                                                const XChunk* __restrict__ st, double* __restrict__ scal,
-                                                                int* __restrict__ cnt, int skip_done) {
-  extern __shared__ __align__(16) unsigned char xsm[];
-  __shared__ int ncached;
-  __shared__ int cached_chunk[XD_CACHE];
-  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-  int* cn = cnt + s * NCNT;
-  if (skip_done && cn[CNT_PCG_DONE]) return;
-  const int n = A.n;
-  const double* as = a + (size_t)s * n;
-  const double* bs = b + (size_t)s * n;
-  const XChunk* cs = st + (size_t)s * nch;
-  double* pcache = reinterpret_cast<double*>(xsm);                          // XD_CACHE x 256 products
-  XChunk* sst = reinterpret_cast<XChunk*>(xsm + XD_CACHE * XD_CHUNK * 8);   // nch chunk statistics (SMEM_STATS)
-  if (tid == 0) ncached = 0;
-  if (SMEM_STATS) {
-    const int4* src = reinterpret_cast<const int4*>(cs);
-    int4* dst = reinterpret_cast<int4*>(sst);
-    for (int k = tid; k < nch * 2; k += XD_WALK_THREADS) dst[k] = src[k];
-  }
-  __syncthreads();
-  const XChunk* S = SMEM_STATS ? sst : cs;
-  for (int c = tid; c < nch; c += XD_WALK_THREADS) {
-    const bool suspect = c == 0 || S[c].bad || (c + 1 < nch && S[c + 1].e != S[c].e);
-    if (suspect) {
-      const int k = atomicAdd(&ncached, 1);
-      if (k < XD_CACHE) cached_chunk[k] = c;
-    }
-  }
-  __syncthreads();
-  const int nc = min(ncached, XD_CACHE);
-  for (int k = tid; k < nc * XD_CHUNK; k += XD_WALK_THREADS) {
-    const int i = cached_chunk[k >> 8] * XD_CHUNK + (k & 255);
-    pcache[k] = i < n ? as[i] * bs[i] : 0.0;
-  }
-  __syncthreads();
-  if (tid >= 32) return;
-
-  double sum = 0.0;
-  int pos = 0;
-  while (pos < nch) {
+// ---- pieces of the walk, executed by one warp
+// chunks [beg, end) 32 at a time with their precomputed statistics; a chunk that cannot be accepted is redone with the
+// true running sum (products from global memory, lane statistics on the fly)
+struct XVariant {  // lane statistics of one cached chunk for one binade, with the scan over the lanes done
+  int e;                   // the binade (INT_MIN: not available)
+  const double4* st;       // per lane {exclusive prefix of the lane totals, lmin, lmax, bad}
+  const double* inc;       // per lane inclusive prefix
+};
+__device__ __forceinline__ void xd_slow_chunk(double& sum, const double (&pr)[8], const double* __restrict__ prs, int lane,
+                                              const XVariant& VA, const XVariant& VB);
+__device__ void xd_group_walk(double& sum, const XChunk* __restrict__ S, int beg, int end, const double* __restrict__ as,
+                              const double* __restrict__ bs, int n, int lane) {
+  int pos = beg;
+  while (pos < end) {
     const int c = pos + lane;
     XChunk ch;
-    if (c < nch) ch = S[c];
+    if (c < end) ch = S[c];
     else { ch.K = 0; ch.pmin = 0; ch.pmax = 0; ch.e = 0; ch.bad = 1; }
     int e = 0;
     const bool okbin = xd_binade(sum, e);
@@ -358,55 +330,247 @@ __global__ void __launch_bounds__(XD_WALK_THREADS) k_xdot_walk(DotArgs A, int nc
       sum = (S0 + tot) * xd_pow2(e - 52);
     }
     pos += f;
-    if (f < 32 && pos < nch) {
-      // ---- the chunk at pos is redone with the true running sum: lane l owns its elements l*8 .. l*8+7
+    if (f < 32 && pos < end) {
       double pr[8];
-      int slot = -1;
-      for (int k = 0; k < nc; k++)
-        if (cached_chunk[k] == pos) slot = k;
-      if (slot >= 0) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) pr[j] = pcache[slot * XD_CHUNK + lane * 8 + j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const int i = pos * XD_CHUNK + lane * 8 + j;
-          pr[j] = i < n ? as[i] * bs[i] : 0.0;
-        }
+      for (int j = 0; j < 8; j++) {
+        const int i = pos * XD_CHUNK + lane * 8 + j;
+        pr[j] = i < n ? as[i] * bs[i] : 0.0;
       }
-      // (products beyond n are exact zeros: adding them changes nothing, in either path)
-      int L0 = 0;
-      while (L0 < 32) {
-        int e2 = 0;
-        int f2 = L0;
-        if (xd_binade(sum, e2)) {
-          double run, lmin, lmax;
-          bool bad;
-          xd_lane_stats(pr, xd_pow2(-(e2 - 52)), run, lmin, lmax, bad);
-          if (lane < L0) { run = 0; lmin = 0; lmax = 0; bad = false; }
-          const double inc2 = xd_scan_incl(run, lane);
-          const double S2 = sum * xd_pow2(-(e2 - 52));
-          const bool okl = lane < L0 || (!bad && xd_inside(sum > 0, S2 + (inc2 - run), lmin, lmax));
-          const unsigned m2 = __ballot_sync(0xffffffffu, okl);
-          f2 = (m2 == 0xffffffffu) ? 32 : (__ffs(~m2) - 1);
-          if (f2 > L0) {
-            const double tot2 = __shfl_sync(0xffffffffu, inc2, f2 - 1);
-            sum = (S2 + tot2) * xd_pow2(e2 - 52);
-          }
-        }
-        L0 = f2;
-        if (L0 < 32) {  // the 8 elements of lane L0 by true floating-point additions, exactly as the serial loop
-          double t = sum;
-#pragma unroll
-          for (int j = 0; j < 8; j++) t = t + pr[j];
-          sum = __shfl_sync(0xffffffffu, t, L0);
-          L0++;
-        }
-      }
+      const XVariant none = {INT_MIN, nullptr, nullptr};
+      xd_slow_chunk(sum, pr, nullptr, lane, none, none);
       pos++;
     }
   }
+}
+
+// one chunk with the true running sum: lane l owns its elements l*8 .. l*8+7 (pr; prs = the same 256 products in
+// shared memory, or null).  VA / VB: lane statistics precomputed for two foreseeable binades, already scanned over the
+// lanes, so that a step costs a few loads, a ballot and no shuffle; any other binade is evaluated on the fly.
+// Lanes are accepted up to the first one whose prefix leaves the binade (or holds a tie); that lane's 8 products are
+// added by true floating-point additions, exactly as the serial loop does, and the rest continues in the new binade.
+// (products beyond n are exact zeros: adding them changes nothing, in either path)
+__device__ __forceinline__ void xd_slow_chunk(double& sum, const double (&pr)[8], const double* __restrict__ prs, int lane,
+                                              const XVariant& VA, const XVariant& VB) {
+  int L0 = 0;
+  while (L0 < 32) {
+    int e2 = 0;
+    int f2 = L0;
+    if (xd_binade(sum, e2)) {
+      const double S2 = sum * xd_pow2(-(e2 - 52));
+      if (e2 == VA.e || e2 == VB.e) {
+        const XVariant& V = e2 == VA.e ? VA : VB;
+        const double base = L0 > 0 ? V.inc[L0 - 1] : 0.0;
+        const double4 q = V.st[lane];
+        const bool okl = lane < L0 || (q.w == 0.0 && xd_inside(sum > 0, S2 + (q.x - base), q.y, q.z));
+        const unsigned m2 = __ballot_sync(0xffffffffu, okl);
+        f2 = (m2 == 0xffffffffu) ? 32 : (__ffs(~m2) - 1);
+        if (f2 > L0) sum = (S2 + (V.inc[f2 - 1] - base)) * xd_pow2(e2 - 52);
+      } else {
+        double run, lmin, lmax;
+        bool bad;
+        xd_lane_stats(pr, xd_pow2(-(e2 - 52)), run, lmin, lmax, bad);
+        if (lane < L0) { run = 0; lmin = 0; lmax = 0; bad = false; }
+        const double inc2 = xd_scan_incl(run, lane);
+        const bool okl = lane < L0 || (!bad && xd_inside(sum > 0, S2 + (inc2 - run), lmin, lmax));
+        const unsigned m2 = __ballot_sync(0xffffffffu, okl);
+        f2 = (m2 == 0xffffffffu) ? 32 : (__ffs(~m2) - 1);
+        if (f2 > L0) {
+          const double tot2 = __shfl_sync(0xffffffffu, inc2, f2 - 1);
+          sum = (S2 + tot2) * xd_pow2(e2 - 52);
+        }
+      }
+    }
+    L0 = f2;
+    if (L0 < 32) {
+      double t = sum;
+      if (prs) {  // every lane adds the same eight products (shared-memory broadcast): no shuffle on the chain
+#pragma unroll
+        for (int j = 0; j < 8; j++) t = t + prs[L0 * 8 + j];
+        sum = t;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) t = t + pr[j];
+        sum = __shfl_sync(0xffffffffu, t, L0);
+      }
+      L0++;
+    }
+  }
+}
+
+// One CTA per scene.  All warps prepare, warp 0 walks:
+//   1. chunk statistics -> shared memory; "suspect" chunks (flagged, the first, and those where the predicted binade
+//      changes) are listed in order; the runs of chunks between two suspects are "segments" (one binade, no flags)
+//   2. for the first XD_CACHE suspects: products and lane statistics for the two foreseeable binades (the predicted one
+//      at the chunk's start and at the next chunk's start) -> shared memory; for every segment: its combined
+//      statistics (integer total, min / max of the prefix sums) -> one O(1) check replaces the chunk-by-chunk walk
+//   3. the walk: segment, suspect, segment, ...: ~2 x (number of binade crossings) short steps instead of nch / 32
+template <bool SMEM_STATS>
+__global__ void __launch_bounds__(XD_WALK_THREADS) k_xdot_walk(DotArgs A, int nch, const double* __restrict__ a,
+                                                                const double* __restrict__ b,
+                                                                const XChunk* __restrict__ st, double* __restrict__ scal,
+                                                                int* __restrict__ cnt, int skip_done) {
+  extern __shared__ __align__(16) unsigned char xsm[];
+  __shared__ int nsus_total;
+  __shared__ int sus[XD_CACHE];
+  __shared__ int sus_e[XD_CACHE][2];
+  __shared__ double seg_K[XD_CACHE + 1], seg_min[XD_CACHE + 1], seg_max[XD_CACHE + 1];
+  __shared__ int seg_e[XD_CACHE + 1], seg_ok[XD_CACHE + 1];
+  __shared__ int wcount[XD_WALK_THREADS / 32];
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int* cn = cnt + s * NCNT;
+  if ((skip_done & 1) && cn[CNT_PCG_DONE]) return;
+  const bool dbg = (skip_done & 2) != 0;  // CLOTHGPU_XDOT_DEBUG: phase cycle counts of scene 0 (measurement aid)
+  long long tk[6] = {0, 0, 0, 0, 0, 0};
+  if (dbg) tk[0] = clock64();
+  const int n = A.n;
+  const double* as = a + (size_t)s * n;
+  const double* bs = b + (size_t)s * n;
+  const XChunk* cs = st + (size_t)s * nch;
+  double* pcache = reinterpret_cast<double*>(xsm);                                        // XD_CACHE x 256 products
+  double4* lstat = reinterpret_cast<double4*>(xsm + XD_CACHE * XD_CHUNK * 8);             // XD_CACHE x 2 x 32 lanes
+  double* linc = reinterpret_cast<double*>(xsm + XD_CACHE * XD_CHUNK * 8 + XD_CACHE * 2 * 32 * 32);
+  XChunk* sst = reinterpret_cast<XChunk*>(xsm + XD_CACHE * XD_CHUNK * 8 + XD_CACHE * 2 * 32 * 40);  // nch (SMEM_STATS)
+  if (SMEM_STATS) {
+    const int4* src = reinterpret_cast<const int4*>(cs);
+    int4* dst = reinterpret_cast<int4*>(sst);
+    for (int k = tid; k < nch * 2; k += XD_WALK_THREADS) dst[k] = src[k];
+  }
+  __syncthreads();
+  const XChunk* S = SMEM_STATS ? sst : cs;
+  // ---- 1. ordered list of the suspect chunks: thread t looks at a contiguous range of chunks
+  const int per = (nch + XD_WALK_THREADS - 1) / XD_WALK_THREADS;
+  const int c0 = tid * per, c1 = min(nch, c0 + per);
+  int mine = 0;
+  for (int c = c0; c < c1; c++) mine += (c == 0 || S[c].bad || (c + 1 < nch && S[c + 1].e != S[c].e)) ? 1 : 0;
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) wcount[warp] = incl;
+  __syncthreads();
+  int base = 0;
+  for (int w = 0; w < warp; w++) base += wcount[w];
+  if (tid == XD_WALK_THREADS - 1) nsus_total = base + incl;
+  int posn = base + incl - mine;
+  for (int c = c0; c < c1; c++) {
+    if (c == 0 || S[c].bad || (c + 1 < nch && S[c + 1].e != S[c].e)) {
+      if (posn < XD_CACHE) {
+        sus[posn] = c;
+        sus_e[posn][0] = S[c].bad && S[c].e == 0 ? INT_MIN : S[c].e;
+        sus_e[posn][1] = (c + 1 < nch && !(S[c + 1].bad && S[c + 1].e == 0) && S[c + 1].e != S[c].e) ? S[c + 1].e : INT_MIN;
+      }
+      posn++;
+    }
+  }
+  __syncthreads();
+  const int nsus = min(nsus_total, XD_CACHE);
+  if (dbg) tk[1] = clock64();
+  // ---- 2a. products of the cached suspects
+  {  // (all loads of a thread issued before the first use: one global-memory latency, not one per suspect)
+    double pa[XD_CACHE], pb[XD_CACHE];
+#pragma unroll
+    for (int q = 0; q < XD_CACHE; q++) {
+      const int i = q < nsus ? sus[q] * XD_CHUNK + tid : n;
+      pa[q] = i < n ? as[i] : 0.0;
+      pb[q] = i < n ? bs[i] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < XD_CACHE; q++)
+      if (q < nsus) pcache[q * XD_CHUNK + tid] = pa[q] * pb[q];
+  }
+  // ---- 2b. segment statistics: segment g = chunks between suspect g-1 and suspect g (the last one runs to nch)
+  for (int g = warp; g <= nsus; g += XD_WALK_THREADS / 32) {
+    const int beg = g == 0 ? 0 : sus[g - 1] + 1, end = g < nsus ? sus[g] : nch;
+    const int len = max(end - beg, 0), lp = (len + 31) / 32;
+    const int b0 = beg + lane * lp, b1 = min(end, b0 + lp);
+    double run = 0, mn = 0, mx = 0;
+    bool bad = false;
+    for (int c = b0; c < b1; c++) {
+      const XChunk ch = S[c];
+      bad = bad || ch.bad || ch.e != S[beg].e;
+      mn = fmin(mn, run + ch.pmin);
+      mx = fmax(mx, run + ch.pmax);
+      run += ch.K;
+    }
+    const double inc = xd_scan_incl(run, lane);
+    mn += inc - run;
+    mx += inc - run;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    const bool anybad = __any_sync(0xffffffffu, bad);
+    const double tot = __shfl_sync(0xffffffffu, inc, 31);
+    if (lane == 0) {
+      seg_K[g] = tot; seg_min[g] = fmin(mn, 0.0); seg_max[g] = fmax(mx, 0.0);
+      seg_e[g] = len > 0 ? S[beg].e : 0;
+      // the tail segment is only trustworthy when every suspect is cached (otherwise it contains uncached suspects)
+      seg_ok[g] = (len > 0 && !anybad && (g < nsus || nsus_total <= XD_CACHE)) ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  if (dbg) tk[2] = clock64();
+  // ---- 2c. lane statistics of the cached suspects for their two foreseeable binades
+  for (int k = warp; k < nsus * 2; k += XD_WALK_THREADS / 32) {
+    const int e = sus_e[k >> 1][k & 1];
+    if (e == INT_MIN) continue;
+    double pr[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) pr[j] = pcache[(k >> 1) * XD_CHUNK + lane * 8 + j];
+    double run, lmin, lmax;
+    bool bad;
+    xd_lane_stats(pr, xd_pow2(-(e - 52)), run, lmin, lmax, bad);
+    const double inc = xd_scan_incl(run, lane);
+    const double exc = inc - run;
+    // the scanned form is only used when every prefix is an exactly represented integer (|.| < 2^52)
+    const bool big = !(fabs(exc + lmin) < 4503599627370496.0) || !(fabs(exc + lmax) < 4503599627370496.0);
+    if (__any_sync(0xffffffffu, big)) {
+      if (lane == 0) sus_e[k >> 1][k & 1] = INT_MIN;
+      continue;
+    }
+    lstat[k * 32 + lane] = make_double4(exc, lmin, lmax, bad ? 1.0 : 0.0);
+    linc[k * 32 + lane] = inc;
+  }
+  __syncthreads();
+  if (tid >= 32) return;
+  if (dbg) tk[3] = clock64();
+
+  // ---- 3. the walk
+  double sum = 0.0;
+  int nslow_seg = 0;
+  for (int g = 0; g <= nsus; g++) {
+    const int beg = g == 0 ? 0 : sus[g - 1] + 1, end = g < nsus ? sus[g] : nch;
+    if (end > beg) {
+      int e = 0;
+      bool fast = false;
+      if (seg_ok[g] && xd_binade(sum, e) && e == seg_e[g]) {
+        const double S0 = sum * xd_pow2(-(e - 52));
+        if (xd_inside(sum > 0, S0, seg_min[g], seg_max[g])) {
+          sum = (S0 + seg_K[g]) * xd_pow2(e - 52);
+          fast = true;
+        }
+      }
+      if (!fast) { xd_group_walk(sum, S, beg, end, as, bs, n, lane); nslow_seg++; }
+    }
+    if (g < nsus) {
+      double pr[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) pr[j] = pcache[g * XD_CHUNK + lane * 8 + j];
+      const XVariant VA = {sus_e[g][0], lstat + (g * 2) * 32, linc + (g * 2) * 32};
+      const XVariant VB = {sus_e[g][1], lstat + (g * 2 + 1) * 32, linc + (g * 2 + 1) * 32};
+      xd_slow_chunk(sum, pr, pcache + g * XD_CHUNK, lane, VA, VB);
+    }
+  }
   if (lane == 0) dot_post(A, sum, scal + s * NSCAL, cn);
+  if (dbg && lane == 0 && s == 0) {
+    tk[4] = clock64();
+    printf("xdot walk: suspects %d (cached %d), segments walked slowly %d; cycles: stats+list %lld, products+segments %lld, "
+           "lane stats %lld, walk %lld\n", nsus_total, nsus, nslow_seg, tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3]);
+  }
 }
 
 // PCG update (ilu_sparse.cpp:674-682): alpha = rPr / pAp; r += (-alpha) Ap; x += alpha p; then r.r
@@ -639,26 +803,27 @@ static int dot_launch(Ctx* c, const double* a, const double* b, int slot, int po
     const int nch = c->xd_nch;
     dim3 g(div_up(nch, 8), c->B);
     XChunk* st = reinterpret_cast<XChunk*>(c->xd_stat);
+    static const int xdbg = getenv("CLOTHGPU_XDOT_DEBUG") ? 2 : 0;
     k_xdot_partial<<<g, 256, 0, KS(c, "k_xdot_partial")>>>(c->ndof, nch, a, b, c->xd_tsum, c->cnt, skip_done);
     CG_LAUNCH_CHECK(c);
     k_xdot_stats<<<g, 256, 0, KS(c, "k_xdot_stats")>>>(c->ndof, nch, a, b, c->xd_tsum, st, c->cnt, skip_done);
     CG_LAUNCH_CHECK(c);
     {
-      const size_t cache_bytes = (size_t)XD_CACHE * XD_CHUNK * 8, stat_bytes = (size_t)nch * sizeof(XChunk);
+      const size_t cache_bytes = (size_t)XD_CACHE * XD_CHUNK * 8 + (size_t)XD_CACHE * 2 * 32 * 40, stat_bytes = (size_t)nch * sizeof(XChunk);
       if (cache_bytes + stat_bytes <= 200 * 1024) {
         if (!c->xd_attr_set) {
           CG_CUDA(cudaFuncSetAttribute(k_xdot_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
           c->xd_attr_set = true;
         }
         k_xdot_walk<true><<<c->B, XD_WALK_THREADS, cache_bytes + stat_bytes, KS(c, "k_xdot_walk")>>>(A, nch, a, b, st, c->scal,
-                                                                                                c->cnt, skip_done);
+                                                                                                c->cnt, skip_done | xdbg);
       } else {
         if (!c->xd_attr_set) {
-          CG_CUDA(cudaFuncSetAttribute(k_xdot_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+          CG_CUDA(cudaFuncSetAttribute(k_xdot_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
           c->xd_attr_set = true;
         }
         k_xdot_walk<false><<<c->B, XD_WALK_THREADS, cache_bytes, KS(c, "k_xdot_walk")>>>(A, nch, a, b, st, c->scal, c->cnt,
-                                                                                    skip_done);
+                                                                                    skip_done | xdbg);
       }
       CG_LAUNCH_CHECK(c);
     }
