@@ -168,7 +168,25 @@ def algorithmic_bytes(sc, nleaf):
         "k_gather_slot": Cc * 72 + T * 6 * 72,
         "k_gather_vertex": P * (72 + 24 + 48) + T * 3 * (72 + 24),
         "k_refit": 12 * T + 48 * P + 2 * 48 * N,
+        # exact dot product: both vectors are read by the chunk-sum pass and again by the statistics pass
+        "k_xdot_partial": 48 * P,
+        "k_xdot_stats": 48 * P,
     }
+
+
+# what bounds the kernels that have no meaningful bandwidth figure
+LIMITERS = {
+    "k_imp_flow": "latency: the Gauss-Seidel impulse sweep is one dependency chain (depth ~0.9 E; ~1.1 us of dependent "
+                  "fp64 arithmetic per hop: coplanarity cubic + 14 bisection halvings + 7 divisions, 85-95 % of the "
+                  "elements write); algorithmic bytes E*212",
+    "k_ilu_factor_strips": "latency: 1021 dependency levels of the reference's row ordering, strip-pipelined wavefront",
+    "k_trisolve_fwd": "latency: 1021 dependency levels, strip-pipelined wavefront (one CTA per strip)",
+    "k_trisolve_bwd": "latency: 1021 dependency levels, strip-pipelined wavefront (one CTA per strip)",
+    "k_xdot_walk": "latency: one warp per scene replays the ~15 binade crossings of the serial sum",
+    "k_trav_step": "launch / L2 latency: one launch per BVH level, small frontiers",
+    "k_narrow": "fp64 pipe + load latency: full predicates (cubic solves) on the culled candidates",
+    "k_cull": "L2 bandwidth / load latency: 15 cheap predicate prefixes per leaf pair, operands re-read from L2",
+}
 
 
 def traffic_table():
@@ -512,6 +530,8 @@ def run_ours(args):
         top = sorted(kt.items(), key=lambda kv: -kv[1][1])
         peak, peak_src = load_peaks()
         ab = algorithmic_bytes(sc, nleaf)
+        if "k_imp_flow" in kt and kt["k_imp_flow"][0] > 0:  # E * (20 + 4 * 48) bytes per sweep
+            ab["k_imp_flow"] = 212.0 * imp_elems / kt["k_imp_flow"][0]
         traffic = traffic_table()
         dom_name, (dom_n, dom_ms) = top[0]
         roof = {"bound": "hbm", "kernel": dom_name, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
@@ -523,12 +543,16 @@ def run_ours(args):
             roof["algorithmic_bytes_per_launch"] = per_launch
             roof["achieved"] = per_launch / (dom_ms / dom_n * 1.0e-3) / 1.0e9
             roof["frac"] = roof["achieved"] / peak
+        if dom_name in LIMITERS:
+            roof["limiter"] = LIMITERS[dom_name]
         roof["per_kernel"] = {}
         for name, (n, ms) in top[:12]:
             e = {"launches_per_step": n / ks, "ms_per_step": ms / ks, "share": ms / tot}
             if name in ab:
                 e["achieved_GBps"] = ab[name] * Sn / (ms / n * 1.0e-3) / 1.0e9
                 e["frac_of_peak"] = e["achieved_GBps"] / peak
+            if name in LIMITERS:
+                e["limiter"] = LIMITERS[name].split(":")[0]
             roof["per_kernel"][name] = e
         roof["phase_ms_per_step"] = {k: v / ks for k, v in phases.items()}
         roof["impulse_elements_per_step"] = imp_elems / ks

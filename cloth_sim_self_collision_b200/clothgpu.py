@@ -15,7 +15,9 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libclothgpu.so")
+# CLOTHGPU_FAST=1 selects the non-parity fast build (libclothgpu_fast.so: FMA contraction on, tree reductions)
+FAST = os.environ.get("CLOTHGPU_FAST", "0") not in ("", "0")
+LIB_PATH = os.path.join(HERE, "libclothgpu_fast.so" if FAST else "libclothgpu.so")
 
 NSTATS = 256
 NPHASE = 16
@@ -83,6 +85,7 @@ def load():
                             "there is no CPU fallback")
     lib = C.CDLL(LIB_PATH)
     lib.clothgpu_last_error.restype = C.c_char_p
+    lib.clothgpu_build_mode.restype = C.c_char_p
     lib.clothgpu_buf_len.restype = C.c_longlong
     lib.clothgpu_launch_count.restype = C.c_longlong
     lib.clothgpu_buf_len.argtypes = [C.c_void_p, C.c_int]

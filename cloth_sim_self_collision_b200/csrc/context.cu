@@ -408,7 +408,11 @@ static int create_impl(Ctx* c, int nscene, int np, int ntri, int nquad, const in
     CG_CHECK(dev_zeros(&st, (long long)B * c->xd_nch * 32));
     c->xd_stat = st;
     const char* dm = getenv("CLOTHGPU_DOT");
+#ifdef CLOTHGPU_FAST_MODE
+    c->exact_dot = dm && strcmp(dm, "exact") == 0;  // the fast build reduces with trees unless asked otherwise
+#else
     c->exact_dot = !(dm && strcmp(dm, "tree") == 0);
+#endif
   }
   CG_CHECK(dev_zeros(&c->cnt, B * NCNT));
   CG_CUDA(cudaMallocHost((void**)&c->h_cnt, sizeof(int) * NCNT * B));
@@ -462,6 +466,13 @@ extern "C" {
 
 const char* clothgpu_last_error(void) { return g_err.c_str(); }
 int clothgpu_version(void) { return CLOTHGPU_VERSION; }
+const char* clothgpu_build_mode(void) {
+#ifdef CLOTHGPU_FAST_MODE
+  return "fast: -fmad=true, tree reductions (NOT bit-compatible with the reference)";
+#else
+  return "parity: -fmad=false, serial-order dot products (bit-compatible with the reference)";
+#endif
+}
 int clothgpu_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {

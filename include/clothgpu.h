@@ -107,6 +107,10 @@ enum { CLOTHGPU_NSTATS = 256 };
 /* ------------------------------------------------------------------------------------------------ life cycle */
 const char* clothgpu_last_error(void);
 int clothgpu_version(void);
+/* which build of the library this is: libclothgpu.so is the parity build (no multiply-add contraction, the
+ * reference's serial dot products: bit-compatible); libclothgpu_fast.so is the same source compiled with contraction
+ * on and tree reductions -- the non-parity fast mode of SURVEY.md 8(f)-4.  The string starts with "parity" or "fast". */
+const char* clothgpu_build_mode(void);
 /* number of visible CUDA devices (0 without a driver/GPU); never fails */
 int clothgpu_device_count(void);
 

@@ -842,3 +842,35 @@ def test_device_side_setup(oracle):
     assert np.array_equal(g.read(G.BUF_VAL_DIA), dia) and np.array_equal(g.read(G.BUF_VAL_CRS), crs)
     assert np.array_equal(g.read(G.BUF_VEC_R), b)
     g.close()
+
+
+def test_fast_library_variant(oracle, tmp_path):
+    """libclothgpu_fast.so (the same sources with multiply-add contraction on and tree reductions) is a
+    separate, explicitly non-parity build: selected with CLOTHGPU_FAST=1, it reports its mode, and a contact-free
+    implicit step agrees with the reference to rounding (1e-9) but not bit for bit."""
+    import subprocess
+    import sys
+    code = ("import numpy as np, sys\n"
+            "from cloth_sim_self_collision_b200 import clothgpu as G, scenes as S\n"
+            "from tests import common as T\n"
+            "assert G.load().clothgpu_build_mode().startswith(b'fast')\n"
+            "sc = S.square_cloth_xy(24, 24 * 0.04)\n"
+            "p = T.params_for(sc, S.INTERNAL_CLOTH, col_kind=2, col_par=(0.4, 0.5, -0.6, 0.3))\n"
+            "g = G.ClothGPU(sc, with_bvh=False)\n"
+            "its = [int(g.step_internal(p)[0]) for _ in range(5)]\n"
+            "x, v = g.download_state()\n"
+            "np.savez(sys.argv[1], x=x, v=v, its=np.array(its))\n")
+    out = tmp_path / "fast.npz"
+    r = subprocess.run([sys.executable, "-c", code, str(out)], env=dict(os.environ, CLOTHGPU_FAST="1"),
+                       cwd=os.path.dirname(GOLD[:-len("/golden")]), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = np.load(out)
+    sc = S.square_cloth_xy(24, 24 * 0.04)
+    p = T.params_for(sc, S.INTERNAL_CLOTH, col_kind=2, col_par=(0.4, 0.5, -0.6, 0.3))
+    sim = oracle.sim(sc)
+    oits = [int(sim.step_internal(p)[1]) for _ in range(5)]
+    ox, ov = sim.get_state()
+    assert list(got["its"]) == oits
+    assert rel_err(got["x"], ox) < RTOL and rel_err(got["v"], ov) < 1.0e-7
+    assert not np.array_equal(got["v"], ov)
+    assert G.load().clothgpu_build_mode().startswith(b"parity")  # this process runs the parity build
