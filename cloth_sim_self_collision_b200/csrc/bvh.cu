@@ -517,6 +517,15 @@ __global__ void k_keep_clean(int np, const RawElem* __restrict__ prev, long long
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const RawElem r = prev[(size_t)s * cap_raw + i];
     if (vd[r.n[0]] | vd[r.n[1]] | vd[r.n[2]] | vd[r.n[3]]) continue;
+    if (i > 0) {
+      // prev is sorted by (key, DFS rank): an exact duplicate (a carried-over element that the dirty-restricted
+      // traversal emitted again through a third dirty vertex of its leaf pair) sits right behind its twin; carrying
+      // both would let the list grow pass after pass
+      const RawElem q = prev[(size_t)s * cap_raw + i - 1];
+      if (q.n[0] == r.n[0] && q.n[1] == r.n[1] && q.n[2] == r.n[2] && q.n[3] == r.n[3] && q.pre == r.pre &&
+          q.path_hi == r.path_hi && q.path_lo == r.path_lo && q.slot == r.slot)
+        continue;
+    }
     const int k = atomicAdd(&c[CNT_RAW], 1);
     if (k >= cap_raw) { atomicOr(&c[CNT_OVERFLOW], 4); continue; }
     raw[(size_t)s * cap_raw + k] = r;

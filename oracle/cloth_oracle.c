@@ -546,8 +546,8 @@ void orc_pcg(int np, const int* rowptr, const int* colidx, const double* valDia,
     if (sq0 < 1.0e-30) { *conv_ratio = 0.0; *iteration = 0; return; }
     inv_sq0 = 1.0 / sq0;
   }
-  Pr = (double*)malloc(sizeof(double) * (size_t)ndof);
-  p = (double*)malloc(sizeof(double) * (size_t)ndof);
+  Pr = (double*)calloc((size_t)ndof, sizeof(double));
+  p = (double*)calloc((size_t)ndof, sizeof(double));
   dia = (int*)malloc(sizeof(int) * (size_t)np);
   orc_ilu_diaind(np, rowptr, colidx, dia);
   memcpy(Pr, r, sizeof(double) * (size_t)ndof);
@@ -599,8 +599,10 @@ void orc_cg(int np, const int* rowptr, const int* colidx, const double* valDia, 
   sq = orc_dot(ndof, r, r);
   if (sq < 1.0e-30) { *conv_ratio = 0.0; *iteration = 0; return; }
   inv_sq0 = 1.0 / sq;
-  Ap = (double*)malloc(sizeof(double) * (size_t)ndof);
-  p = (double*)malloc(sizeof(double) * (size_t)ndof);
+  /* the reference's work vectors are zero-initialised std::vectors; MatVec scales its output by beta = 0 first
+   * (matrix_square_sparse.cpp:218-242), so garbage here (NaN * 0) would poison the solve */
+  Ap = (double*)calloc((size_t)ndof, sizeof(double));
+  p = (double*)calloc((size_t)ndof, sizeof(double));
   memcpy(p, r, sizeof(double) * (size_t)ndof);
   *iteration = mx_iter;
   for (it = 1; it < mx_iter; it++) {
