@@ -18,6 +18,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # CLOTHGPU_FAST=1 selects the non-parity fast build (libclothgpu_fast.so: FMA contraction on, tree reductions)
 FAST = os.environ.get("CLOTHGPU_FAST", "0") not in ("", "0")
 LIB_PATH = os.path.join(HERE, "libclothgpu_fast.so" if FAST else "libclothgpu.so")
+# development switch: A/B a variant build of the same sources (tools/build_variant.sh), e.g. different -D tunables
+if os.environ.get("CLOTHGPU_LIB_PATH"):
+    LIB_PATH = os.path.abspath(os.environ["CLOTHGPU_LIB_PATH"])
 
 NSTATS = 256
 NPHASE = 16

@@ -267,7 +267,14 @@ static int build_topology(Ctx* c, const int* tri, const int* quad, const int* ro
         // without band structure (hundreds of far operands per micro-step) do not fit -- those contexts factorise
         // with the level-scheduled kernel (k_ilu_factor) instead, same arithmetic
         FacPlanHost F;
-        CG_CHECK(build_facplan_host(np, rowptr, colidx, dia.data(), H, F));
+        // the factorisation may use narrower strips than the forward sweep (CLOTHGPU_FAC_STRIPS; default below): its
+        // micro-step is bound by shared-memory traffic per row, so fewer rows per step and CTA shorten the step while
+        // the number of steps on the critical path (the dependency levels) stays the same
+        const char* ffs = getenv("CLOTHGPU_FAC_STRIPS");
+        const int fac_ns = ffs ? atoi(ffs) : 0;
+        TriPlanHost HF;
+        if (fac_ns > 0 && fac_ns != H.ns) CG_CHECK(build_triplan_host(np, rowptr, colidx, dia.data(), true, fac_ns, HF));
+        CG_CHECK(build_facplan_host(np, rowptr, colidx, dia.data(), (fac_ns > 0 && fac_ns != H.ns) ? HF : H, F));
         const int rc = upload_facplan(c, F, c->plan_fac);
         if (rc == CLOTHGPU_ERR_CAPACITY) {
           free_facplan(c->plan_fac);

@@ -50,11 +50,16 @@ struct TriPlanHost {
   std::vector<int> strip_ms, strip_gh, ms_rows, pk_src, gh_row, gh_src, gh_need, meta;
 };
 // strip-pipelined factorisation (ilufactor.cu): follows the forward sweep's strips and micro-steps
+#ifndef FC_SPLIT
+#define FC_SPLIT 1  // compute warps per row triplet (2: every bundle of independent updates is split between two warps)
+#endif
 enum { FC_H = 8, FC_NST = 3, FC_NIB = 3, FC_META_HDR = 48, FC_SMEM_HDR = 256, FC_BUNDLE = 6,
        FC_RWARPS = 4,              // row triplets per micro-step (10 rows -> 4 triplets)
-       FC_CWARPS = 8,              // compute warps: two per triplet, each takes half of every bundle
-       FC_HB = 3,                  // FC_BUNDLE / 2
-       FC_THREADS = (8 + 3) * 32 };
+       FC_CWARPS = FC_RWARPS * FC_SPLIT,  // compute warps
+       FC_HB = FC_BUNDLE / FC_SPLIT,      // updates of a bundle one warp issues
+       FC_NDI = 4,                 // micro-steps of D^-1 hand-off slots (compute -> drain warps)
+       FC_DWARPS = 3,              // drain warps: one thread per (row, block entry) copies finished blocks to global
+       FC_THREADS = (FC_CWARPS + 2 + FC_DWARPS) * 32 };  // compute, loader, import, drain
 struct FacPlanHost {
   int ns = 0, R = 0, nms = 0, H = 0, gmaxB = 0, gmaxU = 0, gmaxOps = 0, max_imp = 0, meta_stride = 0, row_stride = 0;
   int max_steps = 0, gmaxLo = 0, gT = 0, kg_stride = 0, imp_bytes = 0;

@@ -293,7 +293,7 @@ int upload_facplan(Ctx* c, const FacPlanHost& H, FacPlan& D) {
     const int urow0 = round_up(std::max(H.gmaxU, 1) * 72, 16);
     const long long need = (long long)FC_SMEM_HDR + (long long)FC_H * std::max(H.gmaxU, 1) * 9 * 128 + 128 +
                            (long long)FC_NIB * round_up(std::max(H.max_imp, 1) * urow0, 128) +
-                           (long long)FC_NST * ((long long)H.meta_stride * 4 + (long long)H.row_stride * 8);
+                           (long long)FC_NST * ((long long)H.meta_stride * 4 + (long long)H.row_stride * 8) + FC_NDI * 768;
     if (need > 227 * 1024) { set_error("factor plan does not fit shared memory"); return CLOTHGPU_ERR_CAPACITY; }
   }
   D.ns = H.ns; D.R = H.R; D.nms = H.nms; D.gmaxB = H.gmaxB; D.gmaxU = H.gmaxU; D.gmaxOps = H.gmaxOps;
@@ -313,7 +313,7 @@ int upload_facplan(Ctx* c, const FacPlanHost& H, FacPlan& D) {
   CG_CUDA(cudaMemset(D.ticket, 0, sizeof(unsigned long long)));
   const int urow = round_up(D.gmaxU * 72, 16);
   D.smem_bytes = FC_SMEM_HDR + FC_H * D.gmaxU * 9 * 128 + 128 + FC_NIB * round_up(std::max(D.max_imp, 1) * urow, 128) +
-                 FC_NST * (D.meta_stride * 4 + D.row_stride * 8);
+                 FC_NST * (D.meta_stride * 4 + D.row_stride * 8) + FC_NDI * 768;
   if (D.smem_bytes > 227 * 1024) { set_error("factor plan does not fit shared memory"); return CLOTHGPU_ERR_CAPACITY; }
   return CLOTHGPU_OK;
 }
@@ -386,16 +386,20 @@ struct FacArgs {
   unsigned long long* dbg;  // optional: 8 counters per CTA (clothgpu_debug_trisolve, slot of the forward sweep)
 };
 
-// one CTA per (strip, scene): warps 0-7 compute -- warp w and warp w+4 share three rows (nine lanes per row = one lane
-// per block entry) and split every bundle of independent updates / upper blocks between them -- warp 8 lane 0 streams
-// row data, warp 9 lane 0 publishes, warp 10 lane 0 imports
+// one CTA per (strip, scene).  Compute warps: one per row triplet (FC_SPLIT = 1; nine lanes per row = one lane per
+// block entry) -- with FC_SPLIT = 2, warp w and warp w + 4 share a triplet and split every bundle of independent
+// updates / upper blocks.  Then one loader warp (lane 0 streams row data), one import warp (lane 0) and three drain
+// warps: the compute warps leave their results in shared memory (the row blocks of the stage, the ring of upper parts,
+// a D^-1 slot) and never touch global memory; one drain thread per (row, block entry) copies the finished micro-step
+// to iluCrs / iluDia / uexp, then one of them publishes the strip's progress device-wide and hands the stage back to
+// the loader.
 template <bool DBG>
 __global__ void __launch_bounds__(FC_THREADS, 1) k_ilu_factor_strips(const FacArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);        // FC_NST
   uint64_t* empty = full + FC_NST;                            // FC_NST
   uint64_t* ifull = empty + FC_NST;                           // FC_NIB
-  uint32_t* flags = reinterpret_cast<uint32_t*>(smem + 128);  // [0] micro-steps done, [2] ticket
+  uint32_t* flags = reinterpret_cast<uint32_t*>(smem + 128);  // [0] micro-steps computed, [2] ticket
   const int urow = (A.gmaxU * 72 + 15) / 16 * 16;     // bytes of one exported upper part (dense 3x3 blocks)
   const int ring_bytes = FC_H * A.gmaxU * 9 * 128;    // [step mod FC_H][upper block][16 row slots][9 entries] doubles
   unsigned char* ring = smem + FC_SMEM_HDR;          // + a zero block right behind it
@@ -403,6 +407,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_ilu_factor_strips(const FacAr
   const int imp_bytes = (max(A.max_imp, 1) * urow + 127) / 128 * 128;
   unsigned char* stages = imp + (size_t)FC_NIB * imp_bytes;
   const int meta_bytes = A.meta_stride * 4, row_bytes = A.row_stride * 8, stage_bytes = meta_bytes + row_bytes;
+  unsigned char* dinv = stages + (size_t)FC_NST * stage_bytes;  // [step mod FC_NDI][96 lane slots] doubles: D_i^-1
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
@@ -429,13 +434,23 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_ilu_factor_strips(const FacAr
   if (warp < FC_CWARPS) {
     // ---------------------------------------------------------------- compute warps
     // lane -> (row group q, block entry e = r*3 + c); lanes 27..31 idle on the slots of a spare group
-    const int wq = warp % FC_RWARPS, half = warp / FC_RWARPS;  // row triplet, half of every bundle
+    const int wq = warp % FC_RWARPS, half = warp / FC_RWARPS;  // row triplet, share of every bundle
     const int gl = lane / 9, e9 = lane - gl * 9, r = e9 / 3, cc = e9 - r * 3;
     const bool act = gl < 3 && wq * 3 + gl < TS_ROWS;
     const int gq = act ? wq * 3 + gl : TS_ROWS;        // group TS_ROWS (slots 90..95 of every block) is scratch for idle lanes
     const int gm = act ? gq : TS_ROWS - 1;               // metadata column the lane reads
     const int slot8 = act ? (gq * 9 + e9) * 8 : (90 + (lane % 6)) * 8;  // byte offset of the lane's entry inside a block
     const int rowbase8 = gq * 72;                         // byte offset of the group's entries inside a block
+    // cofactor of the lane's own entry of D^-1 (CalcInvMat3): inv[e] = t[i1] * t[i2] - t[i3] * t[i4], byte offsets
+    int o1, o2, o3, o4;
+    {
+      // entries e = 0..8: (4,8,5,7) (2,7,1,8) (1,5,2,4) (5,6,3,8) (0,8,2,6) (2,3,0,5) (3,7,4,6) (1,6,0,7) (0,4,1,3)
+      const unsigned long long t1 = 0x013205124ULL, t2 = 0x467386578ULL, t3 = 0x104023215ULL, t4 = 0x376568487ULL;  // nibble e9
+      o1 = (int)((t1 >> (4 * e9)) & 15ULL) * 8;
+      o2 = (int)((t2 >> (4 * e9)) & 15ULL) * 8;
+      o3 = (int)((t3 >> (4 * e9)) & 15ULL) * 8;
+      o4 = (int)((t4 >> (4 * e9)) & 15ULL) * 8;
+    }
     const bool dbg = DBG && warp == 0;  // cycle counters are compiled out of the production instantiation
     unsigned long long t_begin = 0, w_full = 0, w_imp = 0, w_ops = 0, w_tail = 0, w_inv = 0, w_bar = 0;
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
@@ -449,12 +464,14 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_ilu_factor_strips(const FacAr
       if (dbg) c2 = clock64();
       const int* M = reinterpret_cast<const int*>(stages + (size_t)st * stage_bytes);
       unsigned char* sc = stages + (size_t)st * stage_bytes + meta_bytes;  // this step's row blocks
-      const int nops = M[0], nupmax = M[2], lomax = M[3];
       const int row = act ? M[4 + gm] : -1;
+      // a warp whose triplet holds no row in this micro-step (narrow wavefronts, narrow strips) skips the arithmetic
+      const bool wact = __any_sync(0xffffffffu, row >= 0);
+      const int nops = wact ? M[0] : 0, nupmax = wact ? M[2] : 0;
       // ---- updates A_ij -= A_ik U'_kj in the reference's order.  Lane (r, c) owns entry (r, c) of every block of
       // its row.  The updates of one lower block k hit distinct targets: they are issued FC_BUNDLE at a time (loads,
-      // math, stores); consecutive k-groups are separated by __syncwarp (a later A_ik may be an earlier target,
-      // written by the other lanes of the row)
+      // math, stores); consecutive k-groups are ordered (a later A_ik may be an earlier target, written by the other
+      // lanes of the row)
       for (int kg = 0; kg < nops; kg++) {
         const int* K = M + FC_META_HDR + kg * A.kg_stride;
         const unsigned char* pk = sc + K[gm] + (act ? rowbase8 : 720) + r * 24;  // A_ik[r][0..2]
@@ -480,43 +497,43 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_ilu_factor_strips(const FacAr
 #pragma unroll
           for (int j = 0; j < FC_HB; j++) *reinterpret_cast<double*>(pt[j]) = t[j];
         }
-        // the two warps of a row triplet have written disjoint targets: both must see all of them before the next A_ik
-        asm volatile("bar.sync %0, 64;" ::"r"(2 + wq) : "memory");
+        // with one warp per triplet the ordering is warp-local; two warps have written disjoint targets and both must
+        // see all of them before the next A_ik
+        if (FC_SPLIT == 1) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(2 + wq), "n"(FC_SPLIT * 32) : "memory");
       }
       if (dbg) c3 = clock64();
-      // ---- D_i <- D_i^-1 by cofactors (CalcInvMat3, ilu_sparse.cpp:77-97); a singular pivot is left as is (:541-551)
-      double a[9];
-      {
+      // ---- D_i <- D_i^-1 by cofactors (CalcInvMat3, ilu_sparse.cpp:77-97); a singular pivot is left as is (:541-551).
+      // Every lane evaluates the determinant (all nine entries, the reference's expression) but only the cofactor of
+      // its own entry; the row of D^-1 it needs for U' comes back through the D^-1 slot in shared memory, which is
+      // also where the drain warps pick the block up.  (Both warps of a split triplet write the same values.)
+      unsigned char* dslot = dinv + (size_t)(m % FC_NDI) * 768;
+      if (wact) {
         const unsigned char* pd = sc + (A.gmaxB - 1) * 768 + (act ? rowbase8 : 720);
+        double a[9];
 #pragma unroll
         for (int k = 0; k < 9; k++) a[k] = *reinterpret_cast<const double*>(pd + k * 8);
+        const double p1 = *reinterpret_cast<const double*>(pd + o1), p2 = *reinterpret_cast<const double*>(pd + o2);
+        const double p3 = *reinterpret_cast<const double*>(pd + o3), p4 = *reinterpret_cast<const double*>(pd + o4);
+        double mine = *reinterpret_cast<const double*>(pd + e9 * 8);
         const double det = +a[0] * a[4] * a[8] + a[3] * a[7] * a[2] + a[6] * a[1] * a[5] - a[0] * a[7] * a[5] -
                            a[6] * a[4] * a[2] - a[3] * a[1] * a[8];
+        const double cof = p1 * p2 - p3 * p4;
         if (fabs(det) > 1.0e-30) {
           const double inv_det = 1.0 / det;
-          double t[9];
-#pragma unroll
-          for (int k = 0; k < 9; k++) t[k] = a[k];
-          a[0] = inv_det * (t[4] * t[8] - t[5] * t[7]);
-          a[1] = inv_det * (t[2] * t[7] - t[1] * t[8]);
-          a[2] = inv_det * (t[1] * t[5] - t[2] * t[4]);
-          a[3] = inv_det * (t[5] * t[6] - t[3] * t[8]);
-          a[4] = inv_det * (t[0] * t[8] - t[2] * t[6]);
-          a[5] = inv_det * (t[2] * t[3] - t[0] * t[5]);
-          a[6] = inv_det * (t[3] * t[7] - t[4] * t[6]);
-          a[7] = inv_det * (t[1] * t[6] - t[0] * t[7]);
-          a[8] = inv_det * (t[0] * t[4] - t[1] * t[3]);
-        } else if (row >= 0 && e9 == 0) {
+          mine = inv_det * cof;
+        } else if (row >= 0 && e9 == 0 && half == 0) {
           atomicAdd(&A.cnt[scene * NCNT + CNT_NSING], 1);
         }
+        *reinterpret_cast<double*>(dslot + slot8) = mine;
       }
-      const double ar0 = r == 0 ? a[0] : (r == 1 ? a[3] : a[6]);
-      const double ar1 = r == 0 ? a[1] : (r == 1 ? a[4] : a[7]);
-      const double ar2 = r == 0 ? a[2] : (r == 1 ? a[5] : a[8]);
-      const int crs0 = act ? M[14 + gm] : 0, nlo = act ? M[24 + gm] : 0, nup = act ? M[34 + gm] : 0;
-      if (row >= 0 && half == 0) dia[(size_t)row * 9 + e9] = cc == 0 ? ar0 : (cc == 1 ? ar1 : ar2);
+      __syncwarp();
+      const unsigned char* prow = dslot + (act ? rowbase8 : 720) + (act ? r * 24 : 0);
+      const double ar0 = *reinterpret_cast<const double*>(prow), ar1 = *reinterpret_cast<const double*>(prow + 8),
+                   ar2 = *reinterpret_cast<const double*>(prow + 16);
+      const int nlo = act ? M[24 + gm] : 0, nup = act ? M[34 + gm] : 0;
       if (dbg) c4 = clock64();
-      // ---- U'_ij = D_i^-1 U_ij (:556-567): to the ring (next steps of this strip), the ILU array and the export copy
+      // ---- U'_ij = D_i^-1 U_ij (:556-567) into the ring: operand of the next steps of this strip, source of the drain
       unsigned char* myring = ring + (size_t)(((m % FC_H) * A.gmaxU * 16 + (act ? gq : 15)) * 9 + e9) * 8;
       for (int u0 = half * FC_HB; u0 < nupmax; u0 += FC_BUNDLE) {
         double v[FC_HB];
@@ -530,24 +547,13 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_ilu_factor_strips(const FacAr
 #pragma unroll
         for (int j = 0; j < FC_HB; j++) {
           const int u = u0 + j;
-          if (row >= 0 && u < nup) {
-            *reinterpret_cast<double*>(myring + (size_t)u * 16 * 72) = v[j];
-            crs[(size_t)(crs0 + nlo + u) * 9 + e9] = v[j];
-            uexp[(size_t)row * (urow / 8) + u * 9 + e9] = v[j];
-          }
+          if (row >= 0 && u < nup) *reinterpret_cast<double*>(myring + (size_t)u * 16 * 72) = v[j];
         }
       }
-      // ---- the finished lower part L_ik
-      for (int b = half; b < lomax; b += 2) {
-        if (row >= 0 && b < nlo) crs[(size_t)(crs0 + b) * 9 + e9] = *reinterpret_cast<const double*>(sc + b * 768 + slot8);
-      }
-      // ---- all compute warps have finished the step: ring visible, stage reusable, progress published
+      // ---- all compute warps have finished the step: ring and D^-1 slot visible to the next steps and to the drain
       if (dbg) c5 = clock64();
       asm volatile("bar.sync 1, %0;" ::"n"(FC_CWARPS * 32) : "memory");
-      if (warp == 0 && lane == 0) {
-        f_st_release_cta(&flags[0], (uint32_t)(m + 1));
-        f_mbar_arrive(&empty[st]);
-      }
+      if (warp == 0 && lane == 0) f_st_release_cta(&flags[0], (uint32_t)(m + 1));
       if (dbg) {
         w_full += (unsigned long long)(c1 - c0); w_imp += (unsigned long long)(c2 - c1);
         w_ops += (unsigned long long)(c3 - c2); w_inv += (unsigned long long)(c4 - c3); w_tail += (unsigned long long)(c5 - c4);
@@ -575,20 +581,6 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_ilu_factor_strips(const FacAr
       }
     }
   } else if (warp == FC_CWARPS + 1) {
-    // ---------------------------------------------------------------- publisher: the compute warps store its results itself
-    // (fire and forget); this warp turns "step done" into a device-wide release of the strip's progress counter
-    if (lane == 0) {
-      unsigned long long* prog = A.progress + (size_t)scene * A.ns + strip;
-      uint32_t pub = 0;
-      while (pub < (uint32_t)nsteps) {
-        uint32_t d;
-        while ((d = f_ld_acquire_cta(&flags[0])) <= pub) __nanosleep(20);
-        __threadfence();
-        f_st_release_gpu(prog, A.pbase + d);
-        pub = d;
-      }
-    }
-  } else {
     // ---------------------------------------------------------------- import lane: operands that are not in the ring
     if (lane == 0) {
       const unsigned long long* prog = A.progress + (size_t)scene * A.ns;
@@ -615,6 +607,43 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_ilu_factor_strips(const FacAr
           asm volatile("fence.proxy.async.global;" ::: "memory");
           f_bulk_g2s(imp + (size_t)ibuf * imp_bytes + (size_t)e * urow, uexp + (size_t)kr * (urow / 8), (uint32_t)urow, &ifull[ibuf]);
         }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- drain warps: shared memory -> iluCrs / iluDia / uexp
+    // thread d < 90 owns entry e9 = d % 9 of row group q = d / 9.  After the copies of a micro-step the three warps
+    // meet at a named barrier; one thread then releases the strip's progress counter device-wide (the importers of
+    // other strips, and of this strip for rows that left the ring, acquire it) and returns the stage to the loader.
+    const int d = tid - (FC_CWARPS + 2) * 32;
+    const int q = d / 9, e9 = d - q * 9;
+    const bool mine = d < TS_ROWS * 9;
+    unsigned long long* prog = A.progress + (size_t)scene * A.ns + strip;
+    for (int m = 0; m < nsteps; m++) {
+      const int st = m % FC_NST;
+      while (f_ld_acquire_cta(&flags[0]) < (uint32_t)(m + 1)) __nanosleep(20);
+      const int* M = reinterpret_cast<const int*>(stages + (size_t)st * stage_bytes);
+      const unsigned char* sc = stages + (size_t)st * stage_bytes + meta_bytes;
+      const int row = mine ? M[4 + q] : -1;
+      if (row >= 0) {
+        const int crs0 = M[14 + q], nlo = M[24 + q], nup = M[34 + q];
+        const unsigned char* src = sc + (q * 9 + e9) * 8;
+        double* out = crs + (size_t)crs0 * 9 + e9;
+        for (int b = 0; b < nlo; b++) out[(size_t)b * 9] = *reinterpret_cast<const double*>(src + b * 768);  // L_ik
+        out += (size_t)nlo * 9;
+        const unsigned char* rg = ring + (size_t)(((m % FC_H) * A.gmaxU * 16 + q) * 9 + e9) * 8;
+        double* ue = uexp + (size_t)row * (urow / 8) + e9;
+        for (int u = 0; u < nup; u++) {
+          const double v = *reinterpret_cast<const double*>(rg + (size_t)u * 16 * 72);  // U'_ij
+          out[(size_t)u * 9] = v;
+          ue[u * 9] = v;
+        }
+        dia[(size_t)row * 9 + e9] = *reinterpret_cast<const double*>(dinv + (size_t)(m % FC_NDI) * 768 + (q * 9 + e9) * 8);
+      }
+      asm volatile("bar.sync 7, %0;" ::"n"(FC_DWARPS * 32) : "memory");
+      if (d == 0) {
+        __threadfence();
+        f_st_release_gpu(prog, A.pbase + (unsigned long long)(m + 1));
+        f_mbar_arrive(&empty[st]);
       }
     }
   }
