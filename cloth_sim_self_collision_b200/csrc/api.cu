@@ -110,7 +110,10 @@ int run_resolve(Ctx* c, const clothgpu_params& p, int* applied, int* stats, bool
   }
   for (int s = 0; s < B; s++) {
     if (applied) applied[s] = app[s];
-    if (stats) stats[s * CLOTHGPU_NSTATS + 4] = app[s];
+    if (stats) {
+      stats[s * CLOTHGPU_NSTATS + 4] = app[s];
+      stats[s * CLOTHGPU_NSTATS + 7] = c->h_cnt[s * NCNT + CNT_IMP_SLOW];  // as of the last counter fetch
+    }
   }
   return CLOTHGPU_OK;
 }

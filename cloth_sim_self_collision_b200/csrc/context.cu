@@ -270,10 +270,15 @@ static int build_topology(Ctx* c, const int* tri, const int* quad, const int* ro
         // the factorisation may use narrower strips than the forward sweep (CLOTHGPU_FAC_STRIPS; default below): its
         // micro-step is bound by shared-memory traffic per row, so fewer rows per step and CTA shorten the step while
         // the number of steps on the critical path (the dependency levels) stays the same
+        // (a single scene leaves most SMs idle, so it takes twice the strips; batches are throughput bound and keep
+        // the forward sweep's strips: every CTA pays the fixed per-step cost)
         const char* ffs = getenv("CLOTHGPU_FAC_STRIPS");
-        const int fac_ns = ffs ? atoi(ffs) : 0;
+        int fac_ns = ffs ? atoi(ffs) : (c->B == 1 && 2 * H.ns <= 148 ? 2 * H.ns : 0);
         TriPlanHost HF;
-        if (fac_ns > 0 && fac_ns != H.ns) CG_CHECK(build_triplan_host(np, rowptr, colidx, dia.data(), true, fac_ns, HF));
+        if (fac_ns > 0 && fac_ns != H.ns && build_triplan_host(np, rowptr, colidx, dia.data(), true, fac_ns, HF) != CLOTHGPU_OK) {
+          if (ffs) return CLOTHGPU_ERR_ARG;  // a forced count must fit
+          fac_ns = 0;
+        }
         CG_CHECK(build_facplan_host(np, rowptr, colidx, dia.data(), (fac_ns > 0 && fac_ns != H.ns) ? HF : H, F));
         const int rc = upload_facplan(c, F, c->plan_fac);
         if (rc == CLOTHGPU_ERR_CAPACITY) {
@@ -451,7 +456,13 @@ static int create_impl(Ctx* c, int nscene, int np, int ntri, int nquad, const in
       CG_CUDA(cudaGetDeviceProperties(&pr, c->device));
       c->trav_sms = pr.multiProcessorCount;
       const char* it = getenv("CLOTHGPU_IMP_THREADS");
-      if (it) c->imp_threads = std::min(256, std::max(32, atoi(it) / 32 * 32));
+      if (it) c->imp_threads = std::min(1024, std::max(32, atoi(it) / 32 * 32));
+      const char* isl = getenv("CLOTHGPU_IMP_SLEEP");
+      if (isl) c->imp_sleep_ns = std::min(100000, std::max(0, atoi(isl)));
+      const char* il = getenv("CLOTHGPU_IMP_LANES");
+      if (il) c->imp_lanes = std::min(32, std::max(1, atoi(il)));
+      const char* ifa = getenv("CLOTHGPU_IMP_FAST");
+      c->imp_fast = !(ifa && atoi(ifa) == 0);
       const char* tc = getenv("CLOTHGPU_FUSED_TRAVERSAL");
       c->trav_coop = (pr.cooperativeLaunch && !(tc && atoi(tc) == 0)) ? trav_all_max_scenes() : 0;
     }

@@ -105,6 +105,7 @@ enum {
   CNT_CAND = 11,     // narrow-phase candidates (leaf pair, test slot) that survived the cheap culls
   CNT_RAWPREV = 12,  // raw contact elements of the previous detection pass (incremental CCD passes)
   CNT_GBAR = 13,     // arrival counter of the level barrier of the fused traversal kernel
+  CNT_IMP_SLOW = 14, // impulse elements whose fast arithmetic could not be certified (cumulative, diagnostic)
   CNT_FRONT = 16     // frontier sizes per traversal depth: CNT_FRONT + depth  (depth < 72)
 };
 // per-scene device scalars (doubles): layout of scal[]
@@ -181,6 +182,9 @@ struct Ctx {
   int *vdirty = nullptr, *ndirty = nullptr;
   bool incremental_ccd = true;  // CLOTHGPU_INCREMENTAL=0 re-runs every pass in full
   int imp_threads = 256;        // CLOTHGPU_IMP_THREADS: threads of the data-flow impulse kernel
+  int imp_sleep_ns = 100;       // CLOTHGPU_IMP_SLEEP: nanoseconds between two polls of a predecessor's flag
+  int imp_lanes = 32;           // CLOTHGPU_IMP_LANES: working lanes per warp of the data-flow impulse kernel
+  bool imp_fast = true;         // CLOTHGPU_IMP_FAST=0: impulses with the plain IEEE divisions / square roots only (imp_fast.cuh)
   int trav_coop = 0;            // max scenes for which the fused (cooperative) traversal is co-resident; 0 = off
   int trav_sms = 148;
   double *scal = nullptr, *partials = nullptr;

@@ -18,11 +18,17 @@
 // reduced sequentially, so the sums are bit-identical too.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <climits>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
+
+#include <cmath>
 
 #include "ctx.h"
 #include "dev_math.cuh"
+#include "imp_fast.cuh"
 
 namespace cg {
 
@@ -31,6 +37,18 @@ __device__ __forceinline__ void add3(double* v, int i, V3 n, double a, double b)
   v[i * 3 + 0] += n.x * a * b;
   v[i * 3 + 1] += n.y * a * b;
   v[i * 3 + 2] += n.z * a * b;
+}
+// the same updates from velocities that are already in registers (the four vertices of an element are distinct, so
+// the value in memory is the one loaded at the start of the element): no reload behind the previous vertex's stores
+__device__ __forceinline__ void upd3(double* v, int i, V3 old, V3 n, double a, double b) {
+  v[i * 3 + 0] = old.x + n.x * a * b;
+  v[i * 3 + 1] = old.y + n.y * a * b;
+  v[i * 3 + 2] = old.z + n.z * a * b;
+}
+__device__ __forceinline__ void upd3s(double* v, int i, V3 old, V3 n, double a) {
+  v[i * 3 + 0] = old.x + n.x * a;
+  v[i * 3 + 1] = old.y + n.y * a;
+  v[i * 3 + 2] = old.z + n.z * a;
 }
 __device__ __forceinline__ void add3s(double* v, int i, V3 n, double a) {
   v[i * 3 + 0] += n.x * a;
@@ -46,6 +64,11 @@ struct PrxGeom {
   double wa, wb, wc;  // FV: w0, w1, w2 ; EE: w01, w23 (wc unused)
   V3 norm;
   double p_depth;
+  // velocity-independent pieces of the update, evaluated while the element waits for its predecessors
+  double thr;     // 0.1 * p_depth / dt
+  double imp_el;  // dt * stiffness * p_depth
+  double den;     // 1 + w0^2 + w1^2 + w2^2  /  w01^2 + (1 - w01)^2 + w23^2 + (1 - w23)^2
+  double yden;    // estimate of 1 / den for the certified quotient
 };
 __device__ __forceinline__ void impulse_prx_geom(const int* n, const double* xyz, double delta, PrxGeom& G) {
   const V3 p0 = ld3(xyz, n[0]), p1 = ld3(xyz, n[1]), p2 = ld3(xyz, n[2]), p3 = ld3(xyz, n[3]);
@@ -75,6 +98,60 @@ __device__ __forceinline__ void impulse_prx_geom(const int* n, const double* xyz
     G.wa = w01; G.wb = w23; G.wc = 0.0;
   }
   G.ok = true;
+}
+// the velocity-independent scalars of impulse_prx_apply (same expressions, same operand order)
+__device__ __forceinline__ void impulse_prx_geom_more(PrxGeom& G, double stiffness, double dt) {
+  if (!G.ok) return;
+  G.thr = 0.1 * G.p_depth / dt;
+  G.imp_el = dt * stiffness * G.p_depth;
+  if (G.fv) G.den = 1 + G.wa * G.wa + G.wb * G.wb + G.wc * G.wc;
+  else G.den = G.wa * G.wa + (1 - G.wa) * (1 - G.wa) + G.wb * G.wb + (1 - G.wb) * (1 - G.wb);
+  G.yden = rcp_newton(G.den);
+}
+#ifdef IMP_TRACE
+__device__ long long g_imp_stamp[4];  // thread-private use is enough for the averages: written by the chain's current lane
+#define IMP_STAMP(I_, DEP_) do { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) : "d"(DEP_) : "memory"); tr_stamp[I_] = t_; } while (0)
+#else
+#define IMP_STAMP(I_, DEP_) do { } while (0)
+#endif
+// impulse_prx_apply with the two divisions of the chain (2 imp / den, / mass) taken from early reciprocals; falls back
+// to the plain divisions when a quotient cannot be certified.  Returns false if the reference path had to be used.
+__device__ __forceinline__ bool impulse_prx_apply_fast(const int* n, const PrxGeom& G, double* uvw, const ImpConst& K
+#ifdef IMP_TRACE
+                                                       , long long* tr_stamp
+#endif
+) {
+  if (!G.ok) return true;
+  const V3 v0 = ld3(uvw, n[0]), v1 = ld3(uvw, n[1]), v2 = ld3(uvw, n[2]), v3v = ld3(uvw, n[3]);
+  IMP_STAMP(0, v0.x + v1.x + v2.x + v3v.x + v0.y + v1.y + v2.y + v3v.y + v0.z + v1.z + v2.z + v3v.z);
+  const V3 norm = G.norm;
+  double rel_v;
+  if (G.fv) rel_v = dot(((v3v - G.wa * v0) - G.wb * v1) - G.wc * v2, norm);
+  else rel_v = dot((((1 - G.wb) * v2 + G.wb * v3v) - (1 - G.wa) * v0) - G.wa * v1, norm);
+  if (rel_v > G.thr) return true;
+  const double imp_ie = K.mass * (G.thr - rel_v);
+  const double imp_min = (G.imp_el < imp_ie) ? G.imp_el : imp_ie;
+  bool ok = true;
+  double imp_mod = div_cert(2 * imp_min, G.den, G.yden, ok);
+  imp_mod = div_cert(imp_mod, K.mass, K.inv_mass, ok);
+  if (!ok) {
+    imp_mod = 2 * imp_min / G.den;
+    imp_mod /= K.mass;
+  }
+  imp_mod *= 0.25;
+  IMP_STAMP(1, imp_mod);
+  if (G.fv) {
+    upd3(uvw, n[0], v0, -norm, imp_mod, G.wa);
+    upd3(uvw, n[1], v1, -norm, imp_mod, G.wb);
+    upd3(uvw, n[2], v2, -norm, imp_mod, G.wc);
+    upd3s(uvw, n[3], v3v, norm, imp_mod);
+  } else {
+    upd3(uvw, n[0], v0, -norm, imp_mod, 1 - G.wa);
+    upd3(uvw, n[1], v1, -norm, imp_mod, G.wa);
+    upd3(uvw, n[2], v2, norm, imp_mod, 1 - G.wb);
+    upd3(uvw, n[3], v3v, norm, imp_mod, G.wb);
+  }
+  return ok;
 }
 __device__ __forceinline__ void impulse_prx_apply(const int* n, const PrxGeom& G, double* uvw, double stiffness, double dt,
                                                   double mass) {
@@ -178,6 +255,91 @@ __device__ __forceinline__ void impulse_ccd_apply(const int* n, V3 p0, V3 p1, V3
   }
 }
 
+// impulse_ccd_apply with certified fast arithmetic (imp_fast.cuh): same expressions, same operand order; the square
+// roots / quotients of the chain are replaced by their certified forms and the two distance gates by comparisons of
+// the squared distance.  Returns 0: certified, nothing written; 1: certified, velocities written; 2: not certified,
+// nothing written -- the caller runs impulse_ccd_apply.
+__device__ __forceinline__ int impulse_ccd_fast(const int* n, V3 p0, V3 p1, V3 p2, V3 p3, double* uvw, const ImpConst& K) {
+  bool ok = true;
+  const V3 v0 = ld3(uvw, n[0]), v1 = ld3(uvw, n[1]), v2 = ld3(uvw, n[2]), v3v = ld3(uvw, n[3]);
+  const double t = coplanar_time_cert(p0, p1, p2, p3, p0 + v0, p1 + v1, p2 + v2, p3 + v3v, ok);
+  if (t < 0 || t > 1) return ok ? 0 : 2;
+  const V3 p0m = p0 + t * v0, p1m = p1 + t * v1, p2m = p2 + t * v2, p3m = p3 + t * v3v;
+  const double mass = K.mass;
+  if (n[4]) {
+    double w0, w1;
+    {  // DistanceFaceVertex (dev_math.cuh: dist_face_vertex), distance gate on the square
+      const V3 v20 = p0m - p2m, v21 = p1m - p2m;
+      const double t0 = dot(v20, v20), t1 = dot(v21, v21), t2 = dot(v20, v21);
+      const double t3 = dot(v20, p3m - p2m), t4 = dot(v21, p3m - p2m);
+      const double det = t0 * t1 - t2 * t2;
+      const double invdet = rcp_cert(det, rcp_newton(det), ok);
+      w0 = (+t1 * t3 - t2 * t4) * invdet;
+      w1 = (-t2 * t3 + t0 * t4) * invdet;
+      const double w2m = 1 - w0 - w1;
+      const V3 pw = (w0 * p0m + w1 * p1m) + w2m * p2m;
+      const V3 dd = pw - p3m;
+      const double d2 = dd.x * dd.x + dd.y * dd.y + dd.z * dd.z;
+      if (w0 < 0 || w0 > 1) return ok ? 0 : 2;
+      if (w1 < 0 || w1 > 1) return ok ? 0 : 2;
+      if (d2 > K.dist2) return ok ? 0 : 2;
+    }
+    const double w2 = 1.0 - w0 - w1;
+    const V3 pc = (w0 * p0 + w1 * p1) + w2 * p2;
+    const double den = 1.0 + w0 * w0 + w1 * w1 + w2 * w2;
+    const double yden = rcp_newton(den);
+    const V3 norm = normalized_cert(p3 - pc, ok);
+    const double rel_v = dot(((v3v - w0 * v0) - w1 * v1) - w2 * v2, norm);
+    if (rel_v > K.thr_ccd) return ok ? 0 : 2;
+    const double imp = mass * (K.thr_ccd - rel_v);
+    double imp_mod = div_cert(2 * imp, den, yden, ok);
+    imp_mod = div_cert(imp_mod, mass, K.inv_mass, ok);
+    imp_mod *= 0.1;
+    if (!ok) return 2;
+    upd3(uvw, n[0], v0, -norm, imp_mod, w0);
+    upd3(uvw, n[1], v1, -norm, imp_mod, w1);
+    upd3(uvw, n[2], v2, -norm, imp_mod, w2);
+    upd3s(uvw, n[3], v3v, norm, imp_mod);
+  } else {
+    double w01, w23;
+    {  // DistanceEdgeEdge (dev_math.cuh: dist_edge_edge); the (nearly) parallel configuration goes to the reference path
+      const V3 vp = p1m - p0m, vq = p3m - p2m;
+      const V3 cr = cross(vp, vq);
+      if (cr.x * cr.x + cr.y * cr.y + cr.z * cr.z < K.par2) return 2;
+      const double t0 = dot(vp, vp), t1 = dot(vq, vq), t2 = dot(vp, vq);
+      const double t3 = dot(vp, p2m - p0m), t4 = dot(vq, p2m - p0m);
+      const double det = t0 * t1 - t2 * t2;
+      const double invdet = rcp_cert(det, rcp_newton(det), ok);
+      w01 = (+t1 * t3 - t2 * t4) * invdet;
+      w23 = (+t2 * t3 - t0 * t4) * invdet;
+      const V3 pc = p0m + w01 * vp;
+      const V3 qc = p2m + w23 * vq;
+      const V3 dd = pc - qc;
+      const double d2 = dd.x * dd.x + dd.y * dd.y + dd.z * dd.z;
+      if (w01 < 0 || w01 > 1) return ok ? 0 : 2;
+      if (w23 < 0 || w23 > 1) return ok ? 0 : 2;
+      if (d2 > K.dist2) return ok ? 0 : 2;
+    }
+    const V3 c01 = (1 - w01) * p0 + w01 * p1;
+    const V3 c23 = (1 - w23) * p2 + w23 * p3;
+    const double den = w01 * w01 + (1 - w01) * (1 - w01) + w23 * w23 + (1 - w23) * (1 - w23);
+    const double yden = rcp_newton(den);
+    const V3 norm = normalized_cert(c23 - c01, ok);
+    const double rel_v = dot((((1 - w23) * v2 + w23 * v3v) - (1 - w01) * v0) - w01 * v1, norm);
+    if (rel_v > K.thr_ccd) return ok ? 0 : 2;
+    const double imp = mass * (K.thr_ccd - rel_v);
+    double imp_mod = div_cert(2 * imp, den, yden, ok);
+    imp_mod = div_cert(imp_mod, mass, K.inv_mass, ok);
+    imp_mod *= 0.1;
+    if (!ok) return 2;
+    upd3(uvw, n[0], v0, -norm, imp_mod, 1 - w01);
+    upd3(uvw, n[1], v1, -norm, imp_mod, w01);
+    upd3(uvw, n[2], v2, norm, imp_mod, 1 - w23);
+    upd3(uvw, n[3], v3v, norm, imp_mod, w23);
+  }
+  return 1;
+}
+
 // (vertex, element*4+corner) pairs in element order
 __global__ void k_imp_pairs(int ne, const int* __restrict__ elems, unsigned* __restrict__ keys, int* __restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -266,13 +428,18 @@ __global__ void __launch_bounds__(1024) k_imp_run(int ccd, int np, long long cap
 // runnable and its owner is working on it, so the loop cannot dead-lock; independent dependency chains overlap
 // instead of meeting at a barrier per level, and geometry (positions, indices) is fetched before the wait.
 // Consecutive elements (which usually share their first vertex) are spread over different warps.
+#ifdef IMP_TRACE
+// development build (tools/build_variant.sh trace -DIMP_TRACE): per element {clock when its predecessors were done,
+// clock when it was done, outcome}; launch_impulse prints a summary to stderr
+__device__ long long* g_imp_trace;
+#endif
 __global__ void __launch_bounds__(256) k_imp_flow(int ccd, int np, long long cap_elem, const int* __restrict__ elems_all,
                                                     const int* __restrict__ pred_all, const double* __restrict__ xyz_all,
-                                                    double* uvw_all, double delta, double stiffness, double dt,
-                                                    double mass, const int* __restrict__ cnt) {
+                                                    double* uvw_all, const ImpConst K, int* cnt) {
   extern __shared__ unsigned char done_sm[];
+  const double delta = K.delta, stiffness = K.stiffness, dt = K.dt, mass = K.mass;
   const int s = blockIdx.x;
-  const int* c = cnt + s * NCNT;
+  int* c = cnt + s * NCNT;
   if (!c[CNT_ACTIVE]) return;
   const int ne = c[CNT_ELEM];
   if (ne == 0) return;
@@ -285,32 +452,92 @@ __global__ void __launch_bounds__(256) k_imp_flow(int ccd, int np, long long cap
   __syncthreads();
   // thread <-> element: element k of a round goes to warp (k % nwarp), lane (k / nwarp).  The sweep is nearly serial
   // (chain depth ~0.9 ne), so the thread count hardly matters: 256 measured best (512: +3 %, 32: +28 % dense window)
+  // Only K.lanes lanes of every warp work: a waiting lane polls, and the polls of the lanes of one warp are issued one
+  // divergent group after the other, in the same instruction stream as the lane that is working on the chain.
   const int nwarp = blockDim.x >> 5;
+  if ((int)(threadIdx.x & 31) >= K.lanes) return;
   const int slot = (threadIdx.x & 31) * nwarp + (threadIdx.x >> 5);
-  for (int k = slot; k < ne; k += blockDim.x) {
+  for (int k = slot; k < ne; k += nwarp * K.lanes) {
     const int4 p = pred[k];
     int n[5];
 #pragma unroll
     for (int a = 0; a < 5; a++) n[a] = elems[(size_t)k * 5 + a];
     PrxGeom G;
     V3 q0 = v3(0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
-    if (!ccd) impulse_prx_geom(n, xyz, delta, G);  // velocity independent: in the shadow of the wait
-    else { q0 = ld3(xyz, n[0]); q1 = ld3(xyz, n[1]); q2 = ld3(xyz, n[2]); q3 = ld3(xyz, n[3]); }
+    if (!ccd) {  // velocity independent: in the shadow of the wait
+      impulse_prx_geom(n, xyz, delta, G);
+      if (K.fast) impulse_prx_geom_more(G, stiffness, dt);
+    } else {
+      q0 = ld3(xyz, n[0]); q1 = ld3(xyz, n[1]); q2 = ld3(xyz, n[2]); q3 = ld3(xyz, n[3]);
+    }
     // waiting lanes sleep between polls: a tight poll loop keeps the whole warp in "branch resolving" stalls (ncu: the
     // top stall of this kernel) and slows the one lane of the warp that is working on the chain.  Measured: 0 ns
     // 30.4 ms, 20..200 ns 29.6-29.8 ms, 500 ns 30.8 ms, 1000 ns 33.3 ms per step in the dense window
-#ifndef IMP_SLEEP
-#define IMP_SLEEP 100
-#endif
-#define IMP_WAIT(P_) if ((P_) >= 0) while (!done[(P_)]) { if (IMP_SLEEP > 0) __nanosleep(IMP_SLEEP); }
+    const unsigned sleep_ns = (unsigned)K.sleep_ns;
+#define IMP_WAIT(P_) if ((P_) >= 0) while (!done[(P_)]) { if (sleep_ns > 0) __nanosleep(sleep_ns); }
     IMP_WAIT(p.x) IMP_WAIT(p.y) IMP_WAIT(p.z) IMP_WAIT(p.w)
 #undef IMP_WAIT
     __threadfence_block();
-    if (ccd) impulse_ccd_apply(n, q0, q1, q2, q3, uvw, delta, dt, mass);
-    else impulse_prx_apply(n, G, uvw, stiffness, dt, mass);
+#ifdef IMP_TRACE
+    const long long tr0 = clock64();
+    int tr_how = 3;
+#endif
+    // certified fast arithmetic first (imp_fast.cuh); what cannot be certified is recomputed with the reference's
+    // plain IEEE operations (CNT_IMP_SLOW counts those elements)
+    if (ccd) {
+      const int how = K.fast ? impulse_ccd_fast(n, q0, q1, q2, q3, uvw, K) : 2;
+#ifdef IMP_TRACE
+      tr_how = how;
+#endif
+      if (how == 2) {
+        if (K.fast) atomicAdd(&c[CNT_IMP_SLOW], 1);
+        impulse_ccd_apply(n, q0, q1, q2, q3, uvw, delta, dt, mass);
+      }
+    } else if (K.fast) {
+#ifdef IMP_TRACE
+      long long tr_stamp[2] = {tr0, tr0};
+      if (!impulse_prx_apply_fast(n, G, uvw, K, tr_stamp)) atomicAdd(&c[CNT_IMP_SLOW], 1);
+      if (s == 0) { atomicAdd((unsigned long long*)&g_imp_stamp[0], (unsigned long long)(tr_stamp[0] - tr0));
+                    atomicAdd((unsigned long long*)&g_imp_stamp[1], (unsigned long long)(tr_stamp[1] - tr0)); }
+#else
+      if (!impulse_prx_apply_fast(n, G, uvw, K)) atomicAdd(&c[CNT_IMP_SLOW], 1);
+#endif
+    } else {
+      impulse_prx_apply(n, G, uvw, stiffness, dt, mass);
+    }
     __threadfence_block();
     done[k] = 1;
+#ifdef IMP_TRACE
+    if (s == 0) { g_imp_trace[k * 3 + 0] = tr0; g_imp_trace[k * 3 + 1] = clock64(); g_imp_trace[k * 3 + 2] = tr_how; }
+#endif
   }
+}
+
+// smallest x with sqrt(x) >= c / largest x with sqrt(x) <= c (the host sqrt is the correctly rounded IEEE operation)
+static double sqrt_ge_threshold(double c) {
+  double x = c * c;
+  while (x > 0 && std::sqrt(x) >= c) x = std::nextafter(x, -INFINITY);
+  while (std::sqrt(x) < c) x = std::nextafter(x, INFINITY);
+  return x;
+}
+static double sqrt_le_threshold(double c) {
+  double x = c * c;
+  while (std::sqrt(x) <= c) x = std::nextafter(x, INFINITY);
+  while (x > 0 && std::sqrt(x) > c) x = std::nextafter(x, -INFINITY);
+  return x;
+}
+static ImpConst make_imp_const(const Ctx* c, double delta, double stiffness, double dt, double mass) {
+  ImpConst K;
+  K.delta = delta; K.stiffness = stiffness; K.dt = dt; K.mass = mass;
+  K.inv_mass = 1.0 / mass;
+  K.thr_ccd = 0.1 * delta / dt;
+  K.par2 = sqrt_ge_threshold(1.0e-10);
+  K.dist2 = delta > 0 ? sqrt_le_threshold(delta) : 0.0;
+  // the certified path needs finite positive parameters; anything else keeps the reference arithmetic
+  K.lanes = c->imp_lanes;
+  K.sleep_ns = c->imp_sleep_ns;
+  K.fast = c->imp_fast && delta > 0 && mass > 0 && dt > 0 && std::isfinite(K.inv_mass) && std::isfinite(K.thr_ccd);
+  return K;
 }
 
 int launch_impulse(Ctx* c, const double* xyz, double* uvw, double delta, double stiffness, double dt, double mass, int ccd) {
@@ -345,8 +572,42 @@ int launch_impulse(Ctx* c, const double* xyz, double* uvw, double delta, double 
     const int smem = (ne_max + 127) / 128 * 128;
     CG_CUDA(cudaFuncSetAttribute(k_imp_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(smem, 48 * 1024)));
     const int imp_threads = c->imp_threads;
-    k_imp_flow<<<c->B, imp_threads, smem, KS(c, "k_imp_flow")>>>(ccd, c->np, c->cap_elem, c->elems, c->imp_pred, xyz, uvw, delta,
-                                                  stiffness, dt, mass, c->cnt);
+#ifdef IMP_TRACE
+    static long long* tr_dev = nullptr;
+    const int tr_cap = 1 << 20;
+    if (!tr_dev) {
+      CG_CUDA(cudaMalloc((void**)&tr_dev, sizeof(long long) * 3 * tr_cap));
+      CG_CUDA(cudaMemcpyToSymbol(g_imp_trace, &tr_dev, sizeof(tr_dev)));
+    }
+#endif
+    k_imp_flow<<<c->B, imp_threads, smem, KS(c, "k_imp_flow")>>>(ccd, c->np, c->cap_elem, c->elems, c->imp_pred, xyz, uvw,
+                                                  make_imp_const(c, delta, stiffness, dt, mass), c->cnt);
+#ifdef IMP_TRACE
+    {
+      const int ne = std::min(c->h_cnt[CNT_ELEM], tr_cap);
+      std::vector<long long> tr((size_t)ne * 3);
+      std::vector<int> pred((size_t)ne * 4);
+      CG_CUDA(cudaStreamSynchronize(c->stream));
+      CG_CUDA(cudaMemcpy(tr.data(), tr_dev, sizeof(long long) * 3 * ne, cudaMemcpyDeviceToHost));
+      CG_CUDA(cudaMemcpy(pred.data(), c->imp_pred, sizeof(int) * 4 * ne, cudaMemcpyDeviceToHost));
+      double comp = 0, hand = 0;
+      long long nh = 0, how[4] = {0, 0, 0, 0}, tmin = LLONG_MAX, tmax = 0;
+      for (int k = 0; k < ne; k++) {
+        comp += (double)(tr[k * 3 + 1] - tr[k * 3 + 0]);
+        how[tr[k * 3 + 2] & 3]++;
+        long long last = -1;
+        for (int a = 0; a < 4; a++) if (pred[k * 4 + a] >= 0) last = std::max(last, tr[(size_t)pred[k * 4 + a] * 3 + 1]);
+        if (last >= 0) { hand += (double)(tr[k * 3 + 0] - last); nh++; }
+        tmin = std::min(tmin, tr[k * 3 + 0]); tmax = std::max(tmax, tr[k * 3 + 1]);
+      }
+      long long stamp[4] = {0, 0, 0, 0}, zero[4] = {0, 0, 0, 0};
+      CG_CUDA(cudaMemcpyFromSymbol(stamp, g_imp_stamp, sizeof(stamp)));
+      CG_CUDA(cudaMemcpyToSymbol(g_imp_stamp, zero, sizeof(zero)));
+      if (!ccd && ne) fprintf(stderr, "imptrace prx: loads arrive +%.0f, arithmetic done +%.0f (cycles after the wait)\n", (double)stamp[0] / ne, (double)stamp[1] / ne);
+      fprintf(stderr, "imptrace ccd=%d ne=%d span=%lld cyc  compute/elem=%.0f  handoff/elem=%.0f (n=%lld)  nowrite=%lld write=%lld slow=%lld prx=%lld\n",
+              ccd, ne, ne ? tmax - tmin : 0, ne ? comp / ne : 0.0, nh ? hand / nh : 0.0, nh, how[0], how[1], how[2], how[3]);
+    }
+#endif
   } else {
     k_imp_run<<<c->B, 1024, 0, KS(c, "k_imp_run")>>>(ccd, c->np, c->cap_elem, c->elems, c->imp_pred, c->imp_level, c->imp_order,
                                             c->imp_lptr, xyz, uvw, delta, stiffness, dt, mass, c->cnt);
@@ -535,4 +796,69 @@ int launch_riz_apply(Ctx* c, const double* xyz, double* uvw) {
   return CLOTHGPU_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ self test
+// The certified helpers of imp_fast.cuh against the plain IEEE operations on pseudo-random operands (random mantissas,
+// exponents in [-60, 60], half of the quotients placed next to a rounding boundary): a certified result must equal the
+// hardware result bit for bit.  out[2k] = mismatches, out[2k+1] = uncertified samples of test k: 0 quotient with a
+// Newton reciprocal, 1 quotient with the correctly rounded reciprocal, 2 reciprocal, 3 square root, 4 reciprocal of
+// the root from the coupled iteration.
+__device__ __forceinline__ unsigned long long splitmix(unsigned long long& x) {
+  x += 0x9e3779b97f4a7c15ULL;
+  unsigned long long z = x;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ double rnd_double(unsigned long long& st) {
+  const unsigned long long m = splitmix(st);
+  const unsigned long long e = 1023 - 60 + (splitmix(st) % 121);
+  return __longlong_as_double((long long)((m & 0x800fffffffffffffULL) | (e << 52)));
+}
+__global__ void k_cert_selftest(long long per_thread, unsigned long long seed, unsigned long long* out) {
+  unsigned long long st = seed + 0x1234567ULL * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x);
+  unsigned long long bad[5] = {0, 0, 0, 0, 0}, unc[5] = {0, 0, 0, 0, 0};
+  for (long long i = 0; i < per_thread; i++) {
+    double a = rnd_double(st);
+    const double b = rnd_double(st);
+    if (i & 1) {  // a / b next to the midpoint of two neighbouring doubles
+      const double q = rnd_double(st);
+      a = __fma_rn(b, q, 0.5 * (b * ulp_of(q)));
+    }
+    { bool ok = true; const double q = div_cert(a, b, rcp_newton(b), ok); if (!ok) unc[0]++; else if (q != a / b) bad[0]++; }
+    { bool ok = true; const double q = div_cert(a, b, 1.0 / b, ok); if (!ok) unc[1]++; else if (q != a / b) bad[1]++; }
+    { bool ok = true; const double y = rcp_cert(b, rcp_newton(b), ok); if (!ok) unc[2]++; else if (y != 1.0 / b) bad[2]++; }
+    {
+      bool ok = true;
+      double h;
+      const double s = fabs(a);
+      const double g = sqrt_cert(s, h, ok);
+      if (!ok) unc[3]++; else if (g != sqrt(s)) bad[3]++;
+      bool ok2 = ok;
+      const double y = rcp_cert(g, h + h, ok2);
+      if (!ok2) unc[4]++; else if (y != 1.0 / sqrt(s)) bad[4]++;
+    }
+  }
+  for (int k = 0; k < 5; k++) {
+    atomicAdd(&out[2 * k], bad[k]);
+    atomicAdd(&out[2 * k + 1], unc[k]);
+  }
+}
+
 }  // namespace cg
+
+extern "C" int clothgpu_selftest_certified_math(int device, long long samples, unsigned long long seed, long long* out10) {
+  using namespace cg;
+  if (!out10 || samples <= 0) { set_error("clothgpu_selftest_certified_math: bad argument"); return CLOTHGPU_ERR_ARG; }
+  CG_CUDA(cudaSetDevice(device));
+  unsigned long long* d = nullptr;
+  CG_CUDA(cudaMalloc((void**)&d, sizeof(unsigned long long) * 10));
+  CG_CUDA(cudaMemset(d, 0, sizeof(unsigned long long) * 10));
+  const int blocks = 148 * 4, threads = 128;
+  const long long per_thread = (samples + (long long)blocks * threads - 1) / ((long long)blocks * threads);
+  k_cert_selftest<<<blocks, threads>>>(per_thread, seed, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(out10, d, sizeof(unsigned long long) * 10, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  CG_CUDA(e);
+  return CLOTHGPU_OK;
+}

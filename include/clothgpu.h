@@ -102,6 +102,8 @@ enum {
 enum { CLOTHGPU_NSTATS = 256 };
 /* stats[0]=PCG iteration, [1]=#proximity elems, [2]=#CCD impulse passes run, [3]=#RIZ rounds run,
  * [4]=is_impulse_applied, [5]=last "NNode In RIZ", [6]=1 if the RIZ loop ended with "Resolved All Collisions",
+ * [7]=diagnostic, not a reference quantity: impulse elements (cumulative over the context's life) whose certified
+ *     fast arithmetic had to fall back to the plain IEEE operations (same result either way),
  * [8..13)=CCD elems per impulse pass, [16..116)=CCD elems per RIZ round, [128..228)="NNode In RIZ" per RIZ round */
 
 /* ------------------------------------------------------------------------------------------------ life cycle */
@@ -197,6 +199,12 @@ int clothgpu_ilu_solve(clothgpu_ctx* ctx, int buf_vec);
  * force_ns > 0 fixes the strip count.  stats: NULL or 16 ints, per direction {strips, rows per strip, micro-steps,
  * longest strip, max ghosts, simulated makespan, micro-steps on the pipelined fast path, value bytes per stage} */
 int clothgpu_selftest_triplan(int np, const int* crs_rowptr, const int* crs_colidx, int force_ns, int* stats);
+/* Self test of the certified fast arithmetic of the impulse chain (csrc/imp_fast.cuh) against the plain IEEE
+ * division / square root on `samples` pseudo-random operand pairs (GPU).  out10[2k] = certified results that differ
+ * from the hardware result (must be 0), out10[2k+1] = samples that could not be certified (they take the plain
+ * operations), for k = 0 quotient from a Newton reciprocal, 1 quotient from the correctly rounded reciprocal,
+ * 2 reciprocal, 3 square root, 4 reciprocal of the root. */
+int clothgpu_selftest_certified_math(int device, long long samples, unsigned long long seed, long long* out10);
 /* Instrumentation of the triangular-solve kernels: while on, the compute warp of every CTA accumulates cycle counters.
  * out: NULL, or 2 x cap_ctas x 8 values of the last forward / backward launch {start ns, end ns, cycles waiting for
  * matrix chunks, cycles waiting for imported values, compute cycles, signalling cycles, micro-steps, strip};

@@ -9,8 +9,9 @@ top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 heads = [i for i, r in enumerate(rows) if "Source" in r and len(r) > 5]
-h0 = heads[0]
-end = heads[1] if len(heads) > 1 else len(rows)
+kidx = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+h0 = heads[kidx]
+end = heads[kidx + 1] if len(heads) > kidx + 1 else len(rows)
 hdr = rows[h0]
 ci = {h: i for i, h in enumerate(hdr)}
 s_all = ci["Warp Stall Sampling (All Samples)"]

@@ -573,10 +573,11 @@ def test_measurement_switches_do_not_change_results(oracle, monkeypatch):
     p = T.params_for(sc, c)
     x0, v0 = T.folded_state(sc, gap=0.006, vel=5.0)
     variants = [{}, {"CLOTHGPU_INCREMENTAL": "0"}, {"CLOTHGPU_FUSED_TRAVERSAL": "0"}, {"CLOTHGPU_TRISOLVE": "levels"},
-                {"CLOTHGPU_IMP_THREADS": "64"}]
+                {"CLOTHGPU_IMP_THREADS": "64"}, {"CLOTHGPU_IMP_FAST": "0"}]
     results = []
     for env in variants:
-        for k in ("CLOTHGPU_INCREMENTAL", "CLOTHGPU_FUSED_TRAVERSAL", "CLOTHGPU_TRISOLVE", "CLOTHGPU_IMP_THREADS"):
+        for k in ("CLOTHGPU_INCREMENTAL", "CLOTHGPU_FUSED_TRAVERSAL", "CLOTHGPU_TRISOLVE", "CLOTHGPU_IMP_THREADS",
+                  "CLOTHGPU_IMP_FAST"):
             monkeypatch.delenv(k, raising=False)
         for k, val in env.items():
             monkeypatch.setenv(k, val)
@@ -874,3 +875,20 @@ def test_fast_library_variant(oracle, tmp_path):
     assert rel_err(got["x"], ox) < RTOL and rel_err(got["v"], ov) < 1.0e-7
     assert not np.array_equal(got["v"], ov)
     assert G.load().clothgpu_build_mode().startswith(b"parity")  # this process runs the parity build
+
+
+def test_certified_fast_arithmetic_selftest():
+    """csrc/imp_fast.cuh: quotients / reciprocals / square roots of the impulse chain taken from early reciprocal
+    estimates and Newton iterations, each with an exact-residual certificate.  A certified result must be the IEEE
+    result bit for bit (0 mismatches over 2e8 operand pairs, half of them placed next to a rounding boundary); what
+    cannot be certified falls back to the plain operation and must be rare."""
+    import ctypes as C
+    lib = G.load()
+    out = (C.c_longlong * 10)()
+    n = 200_000_000
+    lib.clothgpu_selftest_certified_math.argtypes = [C.c_int, C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)]
+    assert lib.clothgpu_selftest_certified_math(0, n, 20261018, out) == 0, lib.clothgpu_last_error()
+    o = np.array(list(out), dtype=np.int64).reshape(5, 2)
+    print("certified math: mismatches / uncertified per test:", o.tolist())
+    assert (o[:, 0] == 0).all(), o
+    assert (o[:, 1] < 0.01 * n).all(), o
