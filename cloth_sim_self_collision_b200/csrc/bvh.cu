@@ -96,6 +96,88 @@ __global__ void __launch_bounds__(256) k_refit(int nnode, int np, const int* __r
   }
 }
 
+// Incremental refit (second and later CCD passes of a step: positions fixed, velocities changed on few vertices).  The
+// box of a leaf whose three vertices kept their velocity is unchanged, and so is every subtree without such a leaf:
+// only the dirty leaves and their ancestors are recomputed.
+//   k_refit_mark: every dirty leaf climbs and marks its ancestors dirty until it meets one that is marked already;
+//                 a node that turns dirty counts itself at its parent (nchild = number of dirty children, 1 or 2).
+//   k_refit_inc : every dirty leaf rebuilds its box and climbs; a parent with one dirty child is merged at once with
+//                 the sibling's box of the previous pass, a parent with two dirty children by the second arrival.
+__device__ __forceinline__ bool leaf_dirty(int i, const int* __restrict__ nodes, const int* __restrict__ tri,
+                                           const int* __restrict__ vd, int& n0, int& n1, int& n2) {
+  const int t = nodes[i * 3 + 1];
+  n0 = tri[t * 3 + 0]; n1 = tri[t * 3 + 1]; n2 = tri[t * 3 + 2];
+  return (vd[n0] | vd[n1] | vd[n2]) != 0;
+}
+__global__ void __launch_bounds__(256) k_refit_mark(int nnode, int np, const int* __restrict__ nodes,
+                                                     const int* __restrict__ tri, const int* __restrict__ vdirty,
+                                                     int* ndirty, int* nchild, const int* __restrict__ cnt) {
+  const int s = blockIdx.y;
+  if (!cnt[s * NCNT + CNT_ACTIVE]) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nnode) return;
+  if (nodes[i * 3 + 2] != -1) return;
+  int n0, n1, n2;
+  if (!leaf_dirty(i, nodes, tri, vdirty + (size_t)s * np, n0, n1, n2)) return;
+  int* nd = ndirty + (size_t)s * nnode;
+  int* nc = nchild + (size_t)s * nnode;
+  nd[i] = 1;
+  int x = i;
+  for (;;) {
+    const int p = nodes[x * 3 + 0];
+    if (p < 0) break;
+    atomicAdd(&nc[p], 1);
+    if (atomicExch(&nd[p], 1) != 0) break;  // an earlier climber continues from here
+    x = p;
+  }
+}
+__global__ void __launch_bounds__(256) k_refit_inc(int nnode, int np, const int* __restrict__ nodes,
+                                                    const int* __restrict__ tri, const double* __restrict__ xyz,
+                                                    const double* __restrict__ uvw, double par, double* boxes, int* flags,
+                                                    int* cnt, const int* __restrict__ vdirty,
+                                                    const int* __restrict__ nchild, int* __restrict__ dirty_list) {
+  const int s = blockIdx.y;
+  if (!cnt[s * NCNT + CNT_ACTIVE]) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nnode) return;
+  if (nodes[i * 3 + 2] != -1) return;
+  int n0, n1, n2;
+  if (!leaf_dirty(i, nodes, tri, vdirty + (size_t)s * np, n0, n1, n2)) return;
+  dirty_list[(size_t)s * nnode + atomicAdd(&cnt[s * NCNT + CNT_NDIRTY], 1)] = i;  // the leaves k_query starts from
+  const double* x = xyz + (size_t)s * np * 3;
+  const double* v = uvw + (size_t)s * np * 3;
+  double* bx = boxes + (size_t)s * nnode * 6;
+  int* fl = flags + (size_t)s * nnode;
+  const int* nc = nchild + (size_t)s * nnode;
+  Box b;
+  const double eps = 1.0e-10;  // BuildBoundingBoxChild_CCD, as in k_refit mode 1
+  box_init(b, ld3(x, n0), eps);
+  box_add(b, ld3(x, n1), eps);
+  box_add(b, ld3(x, n2), eps);
+  box_add(b, v3(x[n0 * 3] + par * v[n0 * 3], x[n0 * 3 + 1] + par * v[n0 * 3 + 1], x[n0 * 3 + 2] + par * v[n0 * 3 + 2]), eps);
+  box_add(b, v3(x[n1 * 3] + par * v[n1 * 3], x[n1 * 3 + 1] + par * v[n1 * 3 + 1], x[n1 * 3 + 2] + par * v[n1 * 3 + 2]), eps);
+  box_add(b, v3(x[n2 * 3] + par * v[n2 * 3], x[n2 * 3 + 1] + par * v[n2 * 3 + 1], x[n2 * 3 + 2] + par * v[n2 * 3 + 2]), eps);
+  st_box(bx, i, b);
+  int cur = nodes[i * 3 + 0];
+  while (cur >= 0) {
+    if (nc[cur] == 2) {
+      // both subtrees change: release ours / acquire the sibling's in one fenced atomic, the second arrival merges
+      int seen;
+      asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(seen) : "l"(fl + cur) : "memory");
+      if (seen == 0) return;
+    }
+    Box a = ld_box_cg(bx, nodes[cur * 3 + 1]);
+    const Box o = ld_box_cg(bx, nodes[cur * 3 + 2]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      a.hi[k] = (a.hi[k] > o.hi[k]) ? a.hi[k] : o.hi[k];
+      a.lo[k] = (a.lo[k] < o.lo[k]) ? a.lo[k] : o.lo[k];
+    }
+    st_box(bx, cur, a);
+    cur = nodes[cur * 3 + 0];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ traversal
 __global__ void k_trav_reset(int* cnt) {
   int* c = cnt + blockIdx.x * NCNT;
@@ -288,6 +370,137 @@ __global__ void __launch_bounds__(256) k_trav_all(int ndepth, int nnode, const i
   }
 }
 
+// Incremental passes without a frontier: a leaf pair survives the pair recursion iff the two leaf boxes intersect
+// (the boxes of the ancestors enclose them) and, in a dirty-restricted pass, iff one of the two leaves is dirty (the
+// ancestors of a dirty leaf are dirty).  So every dirty leaf queries the tree for the leaves its box meets -- one
+// launch, no level barriers.  A pair of two dirty leaves is reported by the one with the smaller node index.  The
+// pair is stored in the recursion's orientation (first = the leaf under child 0 of the lowest common ancestor); its
+// depth-first rank is not carried along but rebuilt from the two root-to-leaf paths for the (rare) narrow-phase hits
+// (pair_rank below): entries with pre == 0xffffffff are "lazy".
+enum { QRY_WARPS = 4, QRY_CAP = 256 };
+__global__ void __launch_bounds__(QRY_WARPS * 32) k_query(int nnode, const int* __restrict__ nodes,
+                                                           const double* __restrict__ boxes,
+                                                           const unsigned long long* __restrict__ npath,
+                                                           const int* __restrict__ ndirty,
+                                                           const int* __restrict__ dirty_list, PairEnt* __restrict__ leaf,
+                                                           long long cap_leaf, int* cnt) {
+  // one warp per dirty leaf, breadth first: the lanes test the children of up to 32 frontier nodes at once, so a query
+  // costs one round of dependent loads per tree level instead of one per visited node
+  __shared__ int q[QRY_WARPS][2][QRY_CAP];
+  const int s = blockIdx.y;
+  int* c = cnt + s * NCNT;
+  if (!c[CNT_ACTIVE]) return;
+  const int ndl = c[CNT_NDIRTY];
+  const int* nd = ndirty + (size_t)s * nnode;
+  const int* dl = dirty_list + (size_t)s * nnode;
+  const double* bx = boxes + (size_t)s * nnode * 6;
+  PairEnt* lf = leaf + (size_t)s * cap_leaf;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int w = blockIdx.x * QRY_WARPS + warp; w < ndl; w += gridDim.x * QRY_WARPS) {
+    const int i = dl[w];
+    const Box bl = ld_box(bx, i);
+    const unsigned long long pi = npath[i];
+    int cur = 0, ncur = 1;
+    if (lane == 0) q[warp][0][0] = 0;
+    __syncwarp();
+    while (ncur > 0) {
+      int nnext = 0;
+      for (int base = 0; base < ncur; base += 32) {
+        const int n = (base + lane < ncur) ? q[warp][cur][base + lane] : -1;
+        int ch[2] = {-1, -1};
+        bool hit[2] = {false, false}, isleaf[2] = {false, false};
+        if (n >= 0) {
+          ch[0] = nodes[n * 3 + 1];
+          ch[1] = nodes[n * 3 + 2];
+          if (ch[1] != -1) {  // (a single-leaf tree has no pairs)
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+              hit[k] = box_intersect(ld_box(bx, ch[k]), bl);
+              isleaf[k] = nodes[ch[k] * 3 + 2] == -1;
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          if (hit[k] && isleaf[k]) {
+            const int m = ch[k];
+            if (m != i && !(nd[m] && m < i)) {  // two dirty leaves: the smaller node index reports the pair
+              const int pos = atomicAdd(&c[CNT_LEAF], 1);
+              if (pos >= cap_leaf) {
+                atomicOr(&c[CNT_OVERFLOW], 2);
+              } else {
+                PairEnt e;
+                const bool first = pi < npath[m];  // 0 at the first differing choice = under child 0 of the common ancestor
+                e.i0 = first ? i : m;
+                e.i1 = first ? m : i;
+                e.pre = 0xffffffffu;
+                e.depth = 0;
+                e.path_hi = 0;
+                e.path_lo = 0;
+                lf[pos] = e;
+              }
+            }
+          }
+        }
+        const int npush = (hit[0] && !isleaf[0] ? 1 : 0) + (hit[1] && !isleaf[1] ? 1 : 0);
+        int incl = npush;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        int pos = nnext + incl - npush;
+        nnext += __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          if (hit[k] && !isleaf[k]) {
+            if (pos < QRY_CAP) q[warp][cur ^ 1][pos] = ch[k];
+            pos++;
+          }
+        }
+      }
+      if (nnext > QRY_CAP) {  // a frontier wider than the queue: the host repeats the pass with the frontier traversal
+        if (lane == 0) atomicOr(&c[CNT_OVERFLOW], 16);
+        nnext = 0;
+      }
+      __syncwarp();
+      cur ^= 1;
+      ncur = nnext;
+    }
+  }
+}
+
+// depth-first rank of the leaf pair (i0, i1) of the pair recursion: preorder rank of the lowest common ancestor (the
+// node whose self() call starts the recursion on its two children) and the child codes of the descents
+__device__ void pair_rank(int i0, int i1, const int* __restrict__ nodes, const uint32_t* __restrict__ pre,
+                          const unsigned long long* __restrict__ npath, const int* __restrict__ ndepth, PairEnt& e) {
+  const unsigned long long pa = npath[i0], pb = npath[i1];
+  const int da = ndepth[i0], db = ndepth[i1];
+  const int dl = __clzll((long long)(pa ^ pb));  // depth of the lowest common ancestor
+  int lca = i0;
+  for (int k = da; k > dl; k--) lca = nodes[lca * 3 + 0];
+  e.pre = pre[lca];
+  e.depth = 0;
+  e.path_hi = 0;
+  e.path_lo = 0;
+  int la = da - dl - 1, lb = db - dl - 1;       // descents left on either side below the ancestor's children
+  unsigned long long ra = pa << (dl + 1), rb = pb << (dl + 1);  // (dl + 1 <= 61)
+  while (la > 0 || lb > 0) {
+    unsigned code;
+    if (la > 0 && lb > 0) {
+      code = (unsigned)(ra >> 63) | ((unsigned)(rb >> 63) << 1);
+      ra <<= 1; rb <<= 1; la--; lb--;
+    } else if (la > 0) {
+      code = (unsigned)(ra >> 63);
+      ra <<= 1; la--;
+    } else {
+      code = (unsigned)(rb >> 63);
+      rb <<= 1; lb--;
+    }
+    path_push(e, code);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ narrow phase
 // CContactElement's canonical ordering (bvh_aabb.h:67-95)
 __device__ __forceinline__ void canon_fv(int j0, int j1, int j2, int j3, int* n) {
@@ -455,7 +668,10 @@ __global__ void __launch_bounds__(128, NARROW_B) k_narrow(int ccd, int nnode, in
                                                  const double* __restrict__ xyz, const double* __restrict__ uvw,
                                                  double dt, double delta, const PairEnt* __restrict__ leaf,
                                                  long long cap_leaf, const int4* __restrict__ cand, long long cap_cand,
-                                                 RawElem* __restrict__ raw, long long cap_raw, int* cnt) {
+                                                 RawElem* __restrict__ raw, long long cap_raw, int* cnt,
+                                                 const int* __restrict__ nodes, const uint32_t* __restrict__ pre,
+                                                 const unsigned long long* __restrict__ npath,
+                                                 const int* __restrict__ ndepth) {
   const int s = blockIdx.y;
   int* c = cnt + s * NCNT;
   if (!c[CNT_ACTIVE]) return;
@@ -482,7 +698,9 @@ __global__ void __launch_bounds__(128, NARROW_B) k_narrow(int ccd, int nnode, in
       int key[4];
       if (slot < 6) canon_fv(S.n[0], S.n[1], S.n[2], S.n[3], key);
       else canon_ee(S.n[0], S.n[1], S.n[2], S.n[3], key);
-      emit(lf[cs.w], slot, key, rw, cap_raw, c);  // the pair's DFS rank is only needed for the (rare) hits
+      PairEnt e = lf[cs.w];  // the pair's DFS rank is only needed for the (rare) hits
+      if (e.pre == 0xffffffffu) pair_rank(e.i0, e.i1, nodes, pre, npath, ndepth, e);
+      emit(e, slot, key, rw, cap_raw, c);
     }
   }
 }
@@ -492,11 +710,12 @@ __global__ void __launch_bounds__(128, NARROW_B) k_narrow(int ccd, int nnode, in
 // velocity are carried over; everything else is re-tested by the dirty-restricted traversal.  Carried-over and
 // re-found elements may coincide (same key, same DFS rank): the canonical set removes the duplicates.
 __global__ void k_mark_dirty(int np, const double* __restrict__ uvw, double* __restrict__ snap, int* __restrict__ vdirty,
-                             const int* __restrict__ cnt) {
+                             int* cnt) {
   const int s = blockIdx.y;
   if (!cnt[s * NCNT + CNT_ACTIVE]) return;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= np) return;
+  if (v == 0) cnt[s * NCNT + CNT_NDIRTY] = 0;  // the incremental refit that follows rebuilds the dirty-leaf list
   const size_t o = ((size_t)s * np + v) * 3;
   int d = 0;
 #pragma unroll
@@ -598,6 +817,17 @@ int launch_refit(Ctx* c, const double* xyz, const double* uvw, double par, int m
   CG_CUDA(cudaMemsetAsync(c->refit_flag, 0, sizeof(int) * (size_t)c->B * c->nnode, c->stream));
   dim3 g(div_up(c->nnode, 256), c->B);
   const bool inc = mode == 1 && incremental;
+  if (inc && c->inc_refit) {
+    // only the dirty leaves and their ancestors are rebuilt; every other box is the one of the previous pass
+    CG_CUDA(cudaMemsetAsync(c->ndirty, 0, sizeof(int) * (size_t)c->B * c->nnode, c->stream));
+    CG_CUDA(cudaMemsetAsync(c->refit_nchild, 0, sizeof(int) * (size_t)c->B * c->nnode, c->stream));
+    k_refit_mark<<<g, 256, 0, KS(c, "k_refit_mark")>>>(c->nnode, c->np, c->nodes, c->tri, c->vdirty, c->ndirty, c->refit_nchild, c->cnt);
+    CG_LAUNCH_CHECK(c);
+    k_refit_inc<<<g, 256, 0, KS(c, "k_refit_inc")>>>(c->nnode, c->np, c->nodes, c->tri, xyz, uvw, par, c->boxes, c->refit_flag, c->cnt,
+                                             c->vdirty, c->refit_nchild, c->dirty_list);
+    CG_LAUNCH_CHECK(c);
+    return CLOTHGPU_OK;
+  }
   k_refit<<<g, 256, 0, KS(c, "k_refit")>>>(c->nnode, c->np, c->nodes, c->tri, xyz, uvw, par, mode, c->boxes, c->refit_flag, c->cnt,
                                    inc ? c->vdirty : nullptr, inc ? c->ndirty : nullptr);
   CG_LAUNCH_CHECK(c);
@@ -614,17 +844,23 @@ static int traverse_and_test(Ctx* c, const double* xyz, const double* uvw, doubl
     k_keep_clean<<<gk, 256, 0, KS(c, "k_keep_clean")>>>(c->np, c->raw_sorted, c->cap_raw, c->raw, c->vdirty, c->cnt);
     CG_LAUNCH_CHECK(c);
   }
-  {
+  const bool query = incremental && c->query_trav && c->inc_refit;  // (the incremental refit lists the dirty leaves)
+  if (query) {
+    dim3 g(std::max(8, 148 * 8 / c->B), c->B);
+    k_query<<<g, QRY_WARPS * 32, 0, KS(c, "k_query")>>>(c->nnode, c->nodes, c->boxes, c->npath, nd, c->dirty_list, c->leaf, c->cap_leaf,
+                                                c->cnt);
+    CG_LAUNCH_CHECK(c);
+  } else {
     dim3 g(div_up(c->ninternal, 256), c->B);
     k_trav_init<<<g, 256, 0, KS(c, "k_trav_init")>>>(c->ninternal, c->internal_list, c->nodes, c->pre, c->frontA, c->cap_front, c->cnt,
                                              c->nnode, nd);
     CG_LAUNCH_CHECK(c);
   }
   // every descent moves at least one side of the pair one level down: bvh_height + 1 steps reach all leaf pairs
-  bool fused = false;
+  bool fused = query;
   // (used for the incremental passes only: their frontiers are tiny and nothing else runs beside them, while the
   // full passes overlap the solve on the second stream, where a cooperative launch would have to wait for room)
-  if (incremental && c->trav_coop > 0 && c->B <= c->trav_coop && !c->ktiming) {
+  if (!query && incremental && c->trav_coop > 0 && c->B <= c->trav_coop && !c->ktiming) {
     int ndepth = c->bvh_height + 1, nnode = c->nnode;
     long long capf = c->cap_front, capl = c->cap_leaf;
     const int* nodes = c->nodes; const double* boxes = c->boxes; PairEnt* fa = c->frontA; PairEnt* fb = c->frontB;
@@ -654,7 +890,8 @@ static int traverse_and_test(Ctx* c, const double* xyz, const double* uvw, doubl
     CG_LAUNCH_CHECK(c);
     dim3 g2(148 * 4, c->B);
     k_narrow<<<g2, 128, 0, KS(c, "k_narrow")>>>(ccd, c->nnode, c->np, (const int4*)c->node_tri, c->boxes, xyz, uvw, dt, delta, c->leaf,
-                                        c->cap_leaf, c->cand, c->cap_leaf * 2, c->raw, c->cap_raw, c->cnt);
+                                        c->cap_leaf, c->cand, c->cap_leaf * 2, c->raw, c->cap_raw, c->cnt, c->nodes, c->pre, c->npath,
+                                        c->ndepth);
     CG_LAUNCH_CHECK(c);
   }
   return CLOTHGPU_OK;

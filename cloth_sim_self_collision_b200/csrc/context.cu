@@ -80,6 +80,7 @@ static int alloc_queues(Ctx* c) {
 int grow_queues(Ctx* c, int bits) {
   CG_CUDA(cudaStreamSynchronize(c->stream));
   const long long hard = 1LL << 28;
+  if (!(bits & 15)) return CLOTHGPU_OK;  // bit 4 (k_query's per-leaf frontier): nothing to grow, the retry is a full pass
   if (bits & 1) c->cap_front *= 2;
   if (bits & 2) c->cap_leaf *= 2;
   if (bits & 4) c->cap_raw *= 2;
@@ -326,6 +327,7 @@ static int build_bvh(Ctx* c, const int* nodes, const int* tri) {
   // preorder rank in the order of the self traversal: self(n) visits n, then self(child0), self(child1)
   // (bvh_aabb.cpp:540-557); explicit stack, the trees are ~20 deep but the recursion is not needed
   std::vector<uint32_t> pre(nn, 0);
+  std::vector<unsigned long long> npath(nn, 0ULL);
   std::vector<int> depth(nn, 0), internal;
   std::vector<int> stack;
   stack.push_back(0);
@@ -348,6 +350,8 @@ static int build_bvh(Ctx* c, const int* nodes, const int* tri) {
     if (nodes[c0 * 3] != i || nodes[c1 * 3] != i) { set_error("BVH parent links are inconsistent"); return CLOTHGPU_ERR_ARG; }
     internal.push_back(i);
     depth[c0] = depth[c1] = depth[i] + 1;
+    npath[c0] = npath[i];
+    npath[c1] = npath[i] | (1ULL << (63 - depth[i]));
     stack.push_back(c1);
     stack.push_back(c0);
   }
@@ -369,6 +373,8 @@ static int build_bvh(Ctx* c, const int* nodes, const int* tri) {
     CG_CHECK(dev_upload(&c->node_tri, nt));
   }
   CG_CHECK(dev_upload(&c->pre, pre));
+  CG_CHECK(dev_upload(&c->npath, npath));
+  CG_CHECK(dev_upload(&c->ndepth, depth));
   CG_CHECK(dev_upload(&c->internal_list, internal));
   return CLOTHGPU_OK;
 }
@@ -445,6 +451,14 @@ static int create_impl(Ctx* c, int nscene, int np, int ntri, int nquad, const in
     CG_CHECK(dev_zeros(&c->uvw_snap, B * c->ndof));
     CG_CHECK(dev_zeros(&c->vdirty, B * np));
     CG_CHECK(dev_zeros(&c->ndirty, B * nnode));
+    CG_CHECK(dev_zeros(&c->refit_nchild, B * nnode));
+    CG_CHECK(dev_zeros(&c->dirty_list, B * nnode));
+    {
+      const char* e1 = getenv("CLOTHGPU_INC_REFIT");
+      c->inc_refit = !(e1 && atoi(e1) == 0);
+      const char* e2 = getenv("CLOTHGPU_QUERY_TRAVERSAL");
+      c->query_trav = !(e2 && atoi(e2) == 0);
+    }
     {
       const char* inc = getenv("CLOTHGPU_INCREMENTAL");
       c->incremental_ccd = !(inc && atoi(inc) == 0);
@@ -553,7 +567,7 @@ void clothgpu_destroy(clothgpu_ctx* c) {
                   c->lev_f_rows, c->lev_b_ptr, c->lev_b_rows, c->op_ptr, c->ops, c->nodes, c->node_tri, c->pre, c->internal_list,
                   c->edge_index, c->edge_array, c->xyz, c->uvw, c->xyz_prev, c->uvw0, c->valDia, c->valCrs, c->iluDia,
                   c->iluCrs, c->vec_r, c->vec_x, c->vec_p, c->vec_z, c->tri_dW, c->tri_ddW, c->quad_dW, c->col_table,
-                  c->gravity, c->boxes, c->refit_flag, c->uvw_snap, c->vdirty, c->ndirty, c->scal, c->partials, c->xd_tsum, c->xd_stat, c->cnt, c->zone, c->zone_label,
+                  c->gravity, c->boxes, c->refit_flag, c->uvw_snap, c->vdirty, c->ndirty, c->refit_nchild, c->dirty_list, c->npath, c->ndepth, c->scal, c->partials, c->xd_tsum, c->xd_stat, c->cnt, c->zone, c->zone_label,
                   c->scratch, c->sort_keys, c->sort_keys2, c->sort_vals, c->sort_vals2};
   for (void* p : ptrs) cudaFree(p);
   cudaFree(c->tri_dbg_buf);

@@ -105,6 +105,7 @@ enum {
   CNT_CAND = 11,     // narrow-phase candidates (leaf pair, test slot) that survived the cheap culls
   CNT_RAWPREV = 12,  // raw contact elements of the previous detection pass (incremental CCD passes)
   CNT_GBAR = 13,     // arrival counter of the level barrier of the fused traversal kernel
+  CNT_NDIRTY = 15,   // dirty leaves of the current incremental pass (entries of dirty_list)
   CNT_IMP_SLOW = 14, // impulse elements whose fast arithmetic could not be certified (cumulative, diagnostic)
   CNT_FRONT = 16     // frontier sizes per traversal depth: CNT_FRONT + depth  (depth < 72)
 };
@@ -180,6 +181,12 @@ struct Ctx {
   // incremental CCD detection: velocities the last CCD boxes were built from, changed vertices / BVH nodes
   double* uvw_snap = nullptr;
   int *vdirty = nullptr, *ndirty = nullptr;
+  int* dirty_list = nullptr;            // incremental refit: the dirty leaf nodes (CNT_NDIRTY entries per scene)
+  int* refit_nchild = nullptr;          // incremental refit: number of dirty children per node
+  unsigned long long* npath = nullptr;  // per node: child choices from the root, left aligned (bit 63 - d = choice at depth d)
+  int* ndepth = nullptr;                // per node: depth
+  bool inc_refit = true;                // CLOTHGPU_INC_REFIT=0: incremental passes refit the whole tree
+  bool query_trav = true;               // CLOTHGPU_QUERY_TRAVERSAL=0: incremental passes use the frontier traversal
   bool incremental_ccd = true;  // CLOTHGPU_INCREMENTAL=0 re-runs every pass in full
   int imp_threads = 256;        // CLOTHGPU_IMP_THREADS: threads of the data-flow impulse kernel
   int imp_sleep_ns = 100;       // CLOTHGPU_IMP_SLEEP: nanoseconds between two polls of a predecessor's flag
