@@ -50,6 +50,9 @@ __device__ __forceinline__ void upd3s(double* v, int i, V3 old, V3 n, double a) 
   v[i * 3 + 1] = old.y + n.y * a;
   v[i * 3 + 2] = old.z + n.z * a;
 }
+__device__ __forceinline__ V3 upd3v(V3 old, V3 n, double a, double b) { return v3(old.x + n.x * a * b, old.y + n.y * a * b, old.z + n.z * a * b); }
+__device__ __forceinline__ V3 upd3sv(V3 old, V3 n, double a) { return v3(old.x + n.x * a, old.y + n.y * a, old.z + n.z * a); }
+__device__ __forceinline__ void st3(double* v, int i, V3 a) { v[i * 3 + 0] = a.x; v[i * 3 + 1] = a.y; v[i * 3 + 2] = a.z; }
 __device__ __forceinline__ void add3s(double* v, int i, V3 n, double a) {
   v[i * 3 + 0] += n.x * a;
   v[i * 3 + 1] += n.y * a;
@@ -108,27 +111,19 @@ __device__ __forceinline__ void impulse_prx_geom_more(PrxGeom& G, double stiffne
   else G.den = G.wa * G.wa + (1 - G.wa) * (1 - G.wa) + G.wb * G.wb + (1 - G.wb) * (1 - G.wb);
   G.yden = rcp_newton(G.den);
 }
-#ifdef IMP_TRACE
-__device__ long long g_imp_stamp[4];  // thread-private use is enough for the averages: written by the chain's current lane
-#define IMP_STAMP(I_, DEP_) do { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) : "d"(DEP_) : "memory"); tr_stamp[I_] = t_; } while (0)
-#else
-#define IMP_STAMP(I_, DEP_) do { } while (0)
-#endif
-// impulse_prx_apply with the two divisions of the chain (2 imp / den, / mass) taken from early reciprocals; falls back
-// to the plain divisions when a quotient cannot be certified.  Returns false if the reference path had to be used.
-__device__ __forceinline__ bool impulse_prx_apply_fast(const int* n, const PrxGeom& G, double* uvw, const ImpConst& K
-#ifdef IMP_TRACE
-                                                       , long long* tr_stamp
-#endif
-) {
-  if (!G.ok) return true;
-  const V3 v0 = ld3(uvw, n[0]), v1 = ld3(uvw, n[1]), v2 = ld3(uvw, n[2]), v3v = ld3(uvw, n[3]);
-  IMP_STAMP(0, v0.x + v1.x + v2.x + v3v.x + v0.y + v1.y + v2.y + v3v.y + v0.z + v1.z + v2.z + v3v.z);
+// impulse_prx_apply on velocities held in registers, with the two divisions of the chain (2 imp / den, / mass) taken
+// from early reciprocals; a quotient that cannot be certified is recomputed with the plain divisions (certified =
+// false).  v[0..3] in: the current velocities of the element's vertices, out: the updated ones.  Returns true if the
+// element changes the velocities.
+__device__ __forceinline__ bool impulse_prx_apply_fast_v(const PrxGeom& G, V3* v, const ImpConst& K, bool& certified) {
+  certified = true;
+  if (!G.ok) return false;
+  const V3 v0 = v[0], v1 = v[1], v2 = v[2], v3v = v[3];
   const V3 norm = G.norm;
   double rel_v;
   if (G.fv) rel_v = dot(((v3v - G.wa * v0) - G.wb * v1) - G.wc * v2, norm);
   else rel_v = dot((((1 - G.wb) * v2 + G.wb * v3v) - (1 - G.wa) * v0) - G.wa * v1, norm);
-  if (rel_v > G.thr) return true;
+  if (rel_v > G.thr) return false;
   const double imp_ie = K.mass * (G.thr - rel_v);
   const double imp_min = (G.imp_el < imp_ie) ? G.imp_el : imp_ie;
   bool ok = true;
@@ -137,21 +132,32 @@ __device__ __forceinline__ bool impulse_prx_apply_fast(const int* n, const PrxGe
   if (!ok) {
     imp_mod = 2 * imp_min / G.den;
     imp_mod /= K.mass;
+    certified = false;
   }
   imp_mod *= 0.25;
-  IMP_STAMP(1, imp_mod);
   if (G.fv) {
-    upd3(uvw, n[0], v0, -norm, imp_mod, G.wa);
-    upd3(uvw, n[1], v1, -norm, imp_mod, G.wb);
-    upd3(uvw, n[2], v2, -norm, imp_mod, G.wc);
-    upd3s(uvw, n[3], v3v, norm, imp_mod);
+    v[0] = upd3v(v0, -norm, imp_mod, G.wa);
+    v[1] = upd3v(v1, -norm, imp_mod, G.wb);
+    v[2] = upd3v(v2, -norm, imp_mod, G.wc);
+    v[3] = upd3sv(v3v, norm, imp_mod);
   } else {
-    upd3(uvw, n[0], v0, -norm, imp_mod, 1 - G.wa);
-    upd3(uvw, n[1], v1, -norm, imp_mod, G.wa);
-    upd3(uvw, n[2], v2, norm, imp_mod, 1 - G.wb);
-    upd3(uvw, n[3], v3v, norm, imp_mod, G.wb);
+    v[0] = upd3v(v0, -norm, imp_mod, 1 - G.wa);
+    v[1] = upd3v(v1, -norm, imp_mod, G.wa);
+    v[2] = upd3v(v2, norm, imp_mod, 1 - G.wb);
+    v[3] = upd3v(v3v, norm, imp_mod, G.wb);
   }
-  return ok;
+  return true;
+}
+// the same on velocities in global memory.  Returns false if the plain divisions had to be used.
+__device__ __forceinline__ bool impulse_prx_apply_fast(const int* n, const PrxGeom& G, double* uvw, const ImpConst& K) {
+  if (!G.ok) return true;
+  V3 v[4] = {ld3(uvw, n[0]), ld3(uvw, n[1]), ld3(uvw, n[2]), ld3(uvw, n[3])};
+  bool certified;
+  if (impulse_prx_apply_fast_v(G, v, K, certified)) {
+#pragma unroll
+    for (int a = 0; a < 4; a++) st3(uvw, n[a], v[a]);
+  }
+  return certified;
 }
 __device__ __forceinline__ void impulse_prx_apply(const int* n, const PrxGeom& G, double* uvw, double stiffness, double dt,
                                                   double mass) {
@@ -259,14 +265,14 @@ __device__ __forceinline__ void impulse_ccd_apply(const int* n, V3 p0, V3 p1, V3
 // roots / quotients of the chain are replaced by their certified forms and the two distance gates by comparisons of
 // the squared distance.  Returns 0: certified, nothing written; 1: certified, velocities written; 2: not certified,
 // nothing written -- the caller runs impulse_ccd_apply.
-__device__ __forceinline__ int impulse_ccd_fast(const int* n, V3 p0, V3 p1, V3 p2, V3 p3, double* uvw, const ImpConst& K) {
+__device__ __forceinline__ int impulse_ccd_fast_v(int is_fv, V3 p0, V3 p1, V3 p2, V3 p3, V3* v, const ImpConst& K) {
   bool ok = true;
-  const V3 v0 = ld3(uvw, n[0]), v1 = ld3(uvw, n[1]), v2 = ld3(uvw, n[2]), v3v = ld3(uvw, n[3]);
+  const V3 v0 = v[0], v1 = v[1], v2 = v[2], v3v = v[3];
   const double t = coplanar_time_cert(p0, p1, p2, p3, p0 + v0, p1 + v1, p2 + v2, p3 + v3v, ok);
   if (t < 0 || t > 1) return ok ? 0 : 2;
   const V3 p0m = p0 + t * v0, p1m = p1 + t * v1, p2m = p2 + t * v2, p3m = p3 + t * v3v;
   const double mass = K.mass;
-  if (n[4]) {
+  if (is_fv) {
     double w0, w1;
     {  // DistanceFaceVertex (dev_math.cuh: dist_face_vertex), distance gate on the square
       const V3 v20 = p0m - p2m, v21 = p1m - p2m;
@@ -296,10 +302,10 @@ __device__ __forceinline__ int impulse_ccd_fast(const int* n, V3 p0, V3 p1, V3 p
     imp_mod = div_cert(imp_mod, mass, K.inv_mass, ok);
     imp_mod *= 0.1;
     if (!ok) return 2;
-    upd3(uvw, n[0], v0, -norm, imp_mod, w0);
-    upd3(uvw, n[1], v1, -norm, imp_mod, w1);
-    upd3(uvw, n[2], v2, -norm, imp_mod, w2);
-    upd3s(uvw, n[3], v3v, norm, imp_mod);
+    v[0] = upd3v(v0, -norm, imp_mod, w0);
+    v[1] = upd3v(v1, -norm, imp_mod, w1);
+    v[2] = upd3v(v2, -norm, imp_mod, w2);
+    v[3] = upd3sv(v3v, norm, imp_mod);
   } else {
     double w01, w23;
     {  // DistanceEdgeEdge (dev_math.cuh: dist_edge_edge); the (nearly) parallel configuration goes to the reference path
@@ -332,12 +338,23 @@ __device__ __forceinline__ int impulse_ccd_fast(const int* n, V3 p0, V3 p1, V3 p
     imp_mod = div_cert(imp_mod, mass, K.inv_mass, ok);
     imp_mod *= 0.1;
     if (!ok) return 2;
-    upd3(uvw, n[0], v0, -norm, imp_mod, 1 - w01);
-    upd3(uvw, n[1], v1, -norm, imp_mod, w01);
-    upd3(uvw, n[2], v2, norm, imp_mod, 1 - w23);
-    upd3(uvw, n[3], v3v, norm, imp_mod, w23);
+    v[0] = upd3v(v0, -norm, imp_mod, 1 - w01);
+    v[1] = upd3v(v1, -norm, imp_mod, w01);
+    v[2] = upd3v(v2, norm, imp_mod, 1 - w23);
+    v[3] = upd3v(v3v, norm, imp_mod, w23);
   }
   return 1;
+}
+
+// the same on velocities in global memory
+__device__ __forceinline__ int impulse_ccd_fast(const int* n, V3 p0, V3 p1, V3 p2, V3 p3, double* uvw, const ImpConst& K) {
+  V3 v[4] = {ld3(uvw, n[0]), ld3(uvw, n[1]), ld3(uvw, n[2]), ld3(uvw, n[3])};
+  const int how = impulse_ccd_fast_v(n[4], p0, p1, p2, p3, v, K);
+  if (how == 1) {
+#pragma unroll
+    for (int a = 0; a < 4; a++) st3(uvw, n[a], v[a]);
+  }
+  return how;
 }
 
 // (vertex, element*4+corner) pairs in element order
@@ -348,11 +365,12 @@ __global__ void k_imp_pairs(int ne, const int* __restrict__ elems, unsigned* __r
   keys[i] = (unsigned)elems[k * 5 + a];
   vals[i] = i;
 }
-// predecessor of (element, corner): the previous element touching the same vertex, or -1
+// predecessor of (element, corner): the previous element touching the same vertex and the corner the vertex has
+// there, as element * 4 + corner, or -1
 __global__ void k_imp_pred(int n4, const unsigned* __restrict__ keys, const int* __restrict__ vals, int* __restrict__ pred) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
-  pred[vals[i]] = (i > 0 && keys[i - 1] == keys[i]) ? (vals[i - 1] >> 2) : -1;
+  pred[vals[i]] = (i > 0 && keys[i - 1] == keys[i]) ? vals[i - 1] : -1;
 }
 
 // one CTA per scene: level the dependency DAG, bucket the elements by level, apply level after level
@@ -388,7 +406,7 @@ __global__ void __launch_bounds__(1024) k_imp_run(int ccd, int np, long long cap
 #pragma unroll
       for (int a = 0; a < 4; a++) {
         const int pk = pred[k * 4 + a];
-        if (pk >= 0) l = max(l, ((volatile int*)level)[pk] + 1);
+        if (pk >= 0) l = max(l, ((volatile int*)level)[pk >> 2] + 1);
       }
       if (l > level[k]) { level[k] = l; sh_changed = 1; }
     }
@@ -474,7 +492,7 @@ __global__ void __launch_bounds__(256) k_imp_flow(int ccd, int np, long long cap
     // top stall of this kernel) and slows the one lane of the warp that is working on the chain.  Measured: 0 ns
     // 30.4 ms, 20..200 ns 29.6-29.8 ms, 500 ns 30.8 ms, 1000 ns 33.3 ms per step in the dense window
     const unsigned sleep_ns = (unsigned)K.sleep_ns;
-#define IMP_WAIT(P_) if ((P_) >= 0) while (!done[(P_)]) { if (sleep_ns > 0) __nanosleep(sleep_ns); }
+#define IMP_WAIT(P_) if ((P_) >= 0) while (!done[(P_) >> 2]) { if (sleep_ns > 0) __nanosleep(sleep_ns); }
     IMP_WAIT(p.x) IMP_WAIT(p.y) IMP_WAIT(p.z) IMP_WAIT(p.w)
 #undef IMP_WAIT
     __threadfence_block();
@@ -494,14 +512,7 @@ __global__ void __launch_bounds__(256) k_imp_flow(int ccd, int np, long long cap
         impulse_ccd_apply(n, q0, q1, q2, q3, uvw, delta, dt, mass);
       }
     } else if (K.fast) {
-#ifdef IMP_TRACE
-      long long tr_stamp[2] = {tr0, tr0};
-      if (!impulse_prx_apply_fast(n, G, uvw, K, tr_stamp)) atomicAdd(&c[CNT_IMP_SLOW], 1);
-      if (s == 0) { atomicAdd((unsigned long long*)&g_imp_stamp[0], (unsigned long long)(tr_stamp[0] - tr0));
-                    atomicAdd((unsigned long long*)&g_imp_stamp[1], (unsigned long long)(tr_stamp[1] - tr0)); }
-#else
       if (!impulse_prx_apply_fast(n, G, uvw, K)) atomicAdd(&c[CNT_IMP_SLOW], 1);
-#endif
     } else {
       impulse_prx_apply(n, G, uvw, stiffness, dt, mass);
     }
@@ -596,14 +607,10 @@ int launch_impulse(Ctx* c, const double* xyz, double* uvw, double delta, double 
         comp += (double)(tr[k * 3 + 1] - tr[k * 3 + 0]);
         how[tr[k * 3 + 2] & 3]++;
         long long last = -1;
-        for (int a = 0; a < 4; a++) if (pred[k * 4 + a] >= 0) last = std::max(last, tr[(size_t)pred[k * 4 + a] * 3 + 1]);
+        for (int a = 0; a < 4; a++) if (pred[k * 4 + a] >= 0) last = std::max(last, tr[(size_t)(pred[k * 4 + a] >> 2) * 3 + 1]);
         if (last >= 0) { hand += (double)(tr[k * 3 + 0] - last); nh++; }
         tmin = std::min(tmin, tr[k * 3 + 0]); tmax = std::max(tmax, tr[k * 3 + 1]);
       }
-      long long stamp[4] = {0, 0, 0, 0}, zero[4] = {0, 0, 0, 0};
-      CG_CUDA(cudaMemcpyFromSymbol(stamp, g_imp_stamp, sizeof(stamp)));
-      CG_CUDA(cudaMemcpyToSymbol(g_imp_stamp, zero, sizeof(zero)));
-      if (!ccd && ne) fprintf(stderr, "imptrace prx: loads arrive +%.0f, arithmetic done +%.0f (cycles after the wait)\n", (double)stamp[0] / ne, (double)stamp[1] / ne);
       fprintf(stderr, "imptrace ccd=%d ne=%d span=%lld cyc  compute/elem=%.0f  handoff/elem=%.0f (n=%lld)  nowrite=%lld write=%lld slow=%lld prx=%lld\n",
               ccd, ne, ne ? tmax - tmin : 0, ne ? comp / ne : 0.0, nh ? hand / nh : 0.0, nh, how[0], how[1], how[2], how[3]);
     }
