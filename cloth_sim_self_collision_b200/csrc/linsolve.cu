@@ -5,22 +5,16 @@
 // ForwardSubstitution / BackwardSubstitution (ilu_sparse.cpp:352-384, 507-569, 185-215, 295-324) and Solve_PCG
 // (:628-709).
 //
-// Parity: SpMV, the factorisation and the triangular solves keep the reference's per-row operation order, so
-// they are bit-identical to it (compiled with -fmad=false).  Dot products use a fixed-shape tree (deterministic,
-// but not the reference's serial left-to-right order): PCG iterates agree to rounding, not bit for bit.
+// Parity: SpMV, the factorisation and the triangular solves keep the reference's per-row operation order and the
+// dot products return the value of the reference's serial left-to-right loop (k_xdot_*, below), so PCG / CG iterates
+// and iteration counts are bit-identical to it (compiled with -fmad=false).  The fast build (CLOTHGPU_FAST_MODE) uses
+// a fixed-shape tree for the dot products instead.
 //
 // The triangular solves and the factorisation are dependency chains over the rows (1021 levels on a 256^2 grid in
-// the reference's natural ordering, which parity forces us to keep): one CTA per scene walks the levels with a
-// block barrier per level; rows of a level are independent.  Batches of scenes run one CTA each, concurrently.
-#include <climits>
-#include <cstdio>
-#include <cstdlib>
-
-#include "ctx.h"
-
-namespace cg {
-
-
+// the reference's natural ordering, which parity forces us to keep).  The production path is the strip-pipelined
+// wavefront of trisolve.cu / ilufactor.cu; the level-scheduled kernels in this file (one CTA per scene, a block
+// barrier per level) are the fallback for patterns whose plans do not fit shared memory and the CLOTHGPU_TRISOLVE=levels
+// measurement switch.
 // ------------------------------------------------------------------------------------------------ SpMV
 // one thread per (row, component): y_r = beta*y_r + alpha * sum_j (a_r0 x0 + a_r1 x1 + a_r2 x2), off-diagonal blocks in
 // crs order, diagonal last.  If partials != nullptr the block also reduces x.y (fused p.Ap of PCG).
