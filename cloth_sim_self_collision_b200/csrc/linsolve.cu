@@ -15,6 +15,15 @@
 // wavefront of trisolve.cu / ilufactor.cu; the level-scheduled kernels in this file (one CTA per scene, a block
 // barrier per level) are the fallback for patterns whose plans do not fit shared memory and the CLOTHGPU_TRISOLVE=levels
 // measurement switch.
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+
+#include "ctx.h"
+
+namespace cg {
+
+
 // ------------------------------------------------------------------------------------------------ SpMV
 // one thread per (row, component): y_r = beta*y_r + alpha * sum_j (a_r0 x0 + a_r1 x1 + a_r2 x2), off-diagonal blocks in
 // crs order, diagonal last.  If partials != nullptr the block also reduces x.y (fused p.Ap of PCG).
