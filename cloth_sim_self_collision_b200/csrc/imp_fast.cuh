@@ -101,7 +101,8 @@ struct ImpConst {
 };
 
 // FindCoplanerInterp (bvh_aabb.cpp:598-662) as in coplanar_time_inl<true>; the roots of the derivative come from the
-// certified square root and quotients (the reciprocal of 3 k3 is formed while the root is computed).
+// certified square root and quotients (the reciprocal of 3 k3 is formed while the root is computed).  The branch
+// ladder only selects the bracket; the bisection runs once at the end (one copy of its code instead of nine).
 static __device__ __forceinline__ double coplanar_time_cert(V3 s0, V3 s1, V3 s2, V3 s3, V3 e0, V3 e1, V3 e2, V3 e3, bool& ok) {
   const V3 x1 = s1 - s0, x2 = s2 - s0, x3 = s3 - s0;
   const V3 v1 = (e1 - e0) - x1, v2 = (e2 - e0) - x2, v3v = (e3 - e0) - x3;
@@ -112,15 +113,18 @@ static __device__ __forceinline__ double coplanar_time_cert(V3 s0, V3 s1, V3 s2,
   const double r0 = -0.0, r1 = +1.0;
   const double f0 = cubic(r0, k0, k1, k2, k3), f1 = cubic(r1, k0, k1, k2, k3);
   const double det = k2 * k2 - 3 * k1 * k3;
+  double ba = 0, bb = 0, bf = 0;  // bracket [ba, bb] and the value at its left end
+  bool found = false;
+#define CG_BRACKET(A_, B_, F_) do { ba = (A_); bb = (B_); bf = (F_); found = true; } while (0)
   if (fabs(k3) < 1.0e-10 && fabs(k2) > 1.0e-10) {
     const double r2 = -k1 / (2 * k2);
     const double f2 = cubic(r2, k0, k1, k2, k3);
     if (r2 > 0 && r2 < 1) {
-      if (f0 * f2 < 0) return cubic_root_spec(r0, r2, f0, k0, k1, k2, k3);
-      else if (f2 * f1 < 0) return cubic_root_spec(r2, r1, f2, k0, k1, k2, k3);
+      if (f0 * f2 < 0) CG_BRACKET(r0, r2, f0);
+      else if (f2 * f1 < 0) CG_BRACKET(r2, r1, f2);
     }
   }
-  if (det > 0 && fabs(k3) > 1.0e-10) {
+  if (!found && det > 0 && fabs(k3) > 1.0e-10) {
     const double b3 = 3 * k3;
     const double y3 = rcp_newton(b3);
     double hh;
@@ -128,21 +132,27 @@ static __device__ __forceinline__ double coplanar_time_cert(V3 s0, V3 s1, V3 s2,
     const double r3 = div_cert(-k2 - sq, b3, y3, ok);
     const double f3 = cubic(r3, k0, k1, k2, k3);
     if (r3 > 0 && r3 < 1) {
-      if (f0 * f3 < 0) return cubic_root_spec(r0, r3, f0, k0, k1, k2, k3);
-      else if (f3 * f1 < 0) return cubic_root_spec(r3, r1, f3, k0, k1, k2, k3);
+      if (f0 * f3 < 0) CG_BRACKET(r0, r3, f0);
+      else if (f3 * f1 < 0) CG_BRACKET(r3, r1, f3);
     }
-    const double r4 = div_cert(-k2 + sq, b3, y3, ok);
-    const double f4 = cubic(r4, k0, k1, k2, k3);
-    if (r3 > 0 && r3 < 1 && r4 > 0 && r4 < 1) {
-      if (f3 * f4 < 0) return cubic_root_spec(r3, r4, f3, k0, k1, k2, k3);
-    }
-    if (r4 > 0 && r4 < 1) {
-      if (f0 * f4 < 0) return cubic_root_spec(r0, r4, f0, k0, k1, k2, k3);
-      else if (f4 * f1 < 0) return cubic_root_spec(r4, r1, f4, k0, k1, k2, k3);
+    if (!found) {
+      const double r4 = div_cert(-k2 + sq, b3, y3, ok);
+      const double f4 = cubic(r4, k0, k1, k2, k3);
+      if (r3 > 0 && r3 < 1 && r4 > 0 && r4 < 1) {
+        if (f3 * f4 < 0) CG_BRACKET(r3, r4, f3);
+      }
+      if (!found && r4 > 0 && r4 < 1) {
+        if (f0 * f4 < 0) CG_BRACKET(r0, r4, f0);
+        else if (f4 * f1 < 0) CG_BRACKET(r4, r1, f4);
+      }
     }
   }
-  if (f0 * f1 > 0) return -1;
-  return cubic_root_spec(r0, r1, f0, k0, k1, k2, k3);
+  if (!found) {
+    if (f0 * f1 > 0) return -1;
+    CG_BRACKET(r0, r1, f0);
+  }
+#undef CG_BRACKET
+  return cubic_root_spec(ba, bb, bf, k0, k1, k2, k3);
 }
 
 }  // namespace cg
