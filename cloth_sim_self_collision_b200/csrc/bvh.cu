@@ -792,6 +792,91 @@ __global__ void k_compact_elems(int n, const RawElem* __restrict__ raw, const in
   if (i == n - 1) cnt[CNT_ELEM] = pos[i] + flag[i];
 }
 
+// The canonical set of a SMALL raw list (most incremental passes: a few hundred to a few thousand raw elements) in one
+// launch for all scenes: one CTA per scene sorts its list in shared memory (bitonic network on the 40-byte records,
+// same comparison as the library sort), marks the first record of every key, scans and compacts -- instead of a
+// library merge sort, a flag kernel, a library scan and a compaction kernel per scene.  The sorted list is written
+// back (it is the "previous" list of the next incremental pass).  Scenes with more than CANON_SMALL raw elements are
+// left to the library path.
+enum { CANON_SMALL = 4096, CANON_T = 1024 };
+__global__ void __launch_bounds__(CANON_T) k_canon_small(int npow2, long long cap_raw, long long cap_elem, RawElem* __restrict__ raw_all,
+                                                          int* __restrict__ elems_all, int* cnt) {
+  extern __shared__ __align__(16) unsigned char canon_sm[];
+  RawElem* sm = reinterpret_cast<RawElem*>(canon_sm);
+  __shared__ int wsum[CANON_T / 32];
+  __shared__ int carry;
+  const int s = blockIdx.x;
+  int* c = cnt + s * NCNT;
+  if (!c[CNT_ACTIVE]) return;
+  const int n = c[CNT_RAW];
+  if (n > CANON_SMALL || n > npow2) return;  // the library path handles this scene
+  if (n == 0) { if (threadIdx.x == 0) c[CNT_ELEM] = 0; return; }
+  RawElem* raw = raw_all + (size_t)s * cap_raw;
+  int* elems = elems_all + (size_t)s * cap_elem * 5;
+  int N = 1;
+  while (N < n) N <<= 1;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    if (i < n) sm[i] = raw[i];
+    else { RawElem r; r.n[0] = r.n[1] = r.n[2] = r.n[3] = INT_MAX; r.pre = 0xffffffffu; r.slot = 0xffffffffu; r.path_hi = ~0ULL; r.path_lo = ~0ULL; sm[i] = r; }
+  }
+  __syncthreads();
+  const RawLess less;
+  for (int k = 2; k <= N; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const RawElem a = sm[i], b = sm[l];
+          const bool up = (i & k) == 0;
+          if (up ? less(b, a) : less(a, b)) { sm[i] = b; sm[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) raw[i] = sm[i];
+  // first record of every key -> compact (std::set keeps the first inserted of equal keys: smallest DFS rank)
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    int f = 0;
+    if (i < n) {
+      f = 1;
+      if (i > 0) {
+        const RawElem& a = sm[i - 1];
+        const RawElem& b = sm[i];
+        f = (a.n[0] != b.n[0] || a.n[1] != b.n[1] || a.n[2] != b.n[2] || a.n[3] != b.n[3]) ? 1 : 0;
+      }
+    }
+    int incl = f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; w++) woff += wsum[w];
+    const int pos = carry + woff + incl - f;
+    if (f) {
+      if (pos < cap_elem) {
+        const RawElem& r = sm[i];
+        elems[pos * 5 + 0] = r.n[0]; elems[pos * 5 + 1] = r.n[1]; elems[pos * 5 + 2] = r.n[2]; elems[pos * 5 + 3] = r.n[3];
+        elems[pos * 5 + 4] = r.slot < 6 ? 1 : 0;
+      } else {
+        atomicOr(&c[CNT_OVERFLOW], 8);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = pos + f;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) c[CNT_ELEM] = carry;
+}
+
 __global__ void k_set_active(int* cnt, int v) { cnt[blockIdx.x * NCNT + CNT_ACTIVE] = v; }
 
 // scenes whose fused traversal (one CTA per SM and scene) is co-resident: resident CTAs of k_trav_all per SM
@@ -948,9 +1033,28 @@ int run_contacts(Ctx* c, const double* xyz, const double* uvw, double dt, double
     CG_CHECK(grow_queues(c, bits));
   }
   phase_begin(c, 5);
-  for (int s = 0; s < c->B; s++) {
-    if (!c->h_cnt[s * NCNT + CNT_ACTIVE]) continue;
-    CG_CHECK(canonical_set(c, s, c->h_cnt[s * NCNT + CNT_RAW]));
+  {
+    // small raw lists: one launch for all scenes; anything larger goes through the library sort, scene by scene
+    int nsmall = 0, nmax_small = 0;
+    for (int s = 0; s < c->B; s++) {
+      if (!c->h_cnt[s * NCNT + CNT_ACTIVE]) continue;
+      const int nraw = c->h_cnt[s * NCNT + CNT_RAW];
+      if (c->canon_small && nraw <= CANON_SMALL) { nsmall++; nmax_small = std::max(nmax_small, nraw); }
+    }
+    if (nsmall > 0) {
+      int npow2 = 32;
+      while (npow2 < nmax_small) npow2 <<= 1;
+      const int smem = npow2 * (int)sizeof(RawElem);
+      CG_CUDA(cudaFuncSetAttribute(k_canon_small, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(smem, 48 * 1024)));
+      k_canon_small<<<c->B, CANON_T, smem, KS(c, "k_canon_small")>>>(npow2, c->cap_raw, c->cap_elem, c->raw, c->elems, c->cnt);
+      CG_LAUNCH_CHECK(c);
+    }
+    for (int s = 0; s < c->B; s++) {
+      if (!c->h_cnt[s * NCNT + CNT_ACTIVE]) continue;
+      const int nraw = c->h_cnt[s * NCNT + CNT_RAW];
+      if (c->canon_small && nraw <= CANON_SMALL) continue;
+      CG_CHECK(canonical_set(c, s, nraw));
+    }
   }
   CG_CHECK(fetch_counters(c));
   phase_end(c, 5);
