@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(QRY_WARPS * 32) k_query(int nnode, const int* 
                                                            const unsigned long long* __restrict__ npath,
                                                            const int* __restrict__ ndirty,
                                                            const int* __restrict__ dirty_list, PairEnt* __restrict__ leaf,
-                                                           long long cap_leaf, int* cnt) {
+                                                           long long cap_leaf, int* cnt, int qcap) {
   // one warp per dirty leaf, breadth first: the lanes test the children of up to 32 frontier nodes at once, so a query
   // costs one round of dependent loads per tree level instead of one per visited node
   __shared__ int q[QRY_WARPS][2][QRY_CAP];
@@ -454,12 +454,12 @@ __global__ void __launch_bounds__(QRY_WARPS * 32) k_query(int nnode, const int* 
 #pragma unroll
         for (int k = 0; k < 2; k++) {
           if (hit[k] && !isleaf[k]) {
-            if (pos < QRY_CAP) q[warp][cur ^ 1][pos] = ch[k];
+            if (pos < qcap) q[warp][cur ^ 1][pos] = ch[k];
             pos++;
           }
         }
       }
-      if (nnext > QRY_CAP) {  // a frontier wider than the queue: the host repeats the pass with the frontier traversal
+      if (nnext > qcap) {  // a frontier wider than the queue: the host repeats the pass with the frontier traversal
         if (lane == 0) atomicOr(&c[CNT_OVERFLOW], 16);
         nnext = 0;
       }
@@ -798,7 +798,7 @@ __global__ void k_compact_elems(int n, const RawElem* __restrict__ raw, const in
 // library merge sort, a flag kernel, a library scan and a compaction kernel per scene.  The sorted list is written
 // back (it is the "previous" list of the next incremental pass).  Scenes with more than CANON_SMALL raw elements are
 // left to the library path.
-enum { CANON_SMALL = 4096, CANON_T = 1024 };
+enum { CANON_SMALL = 2048, CANON_T = 1024 };  // (a 4096-record list takes 176 us here: no faster than the library path)
 __global__ void __launch_bounds__(CANON_T) k_canon_small(int npow2, long long cap_raw, long long cap_elem, RawElem* __restrict__ raw_all,
                                                           int* __restrict__ elems_all, int* cnt) {
   extern __shared__ __align__(16) unsigned char canon_sm[];
@@ -933,7 +933,7 @@ static int traverse_and_test(Ctx* c, const double* xyz, const double* uvw, doubl
   if (query) {
     dim3 g(std::max(8, 148 * 8 / c->B), c->B);
     k_query<<<g, QRY_WARPS * 32, 0, KS(c, "k_query")>>>(c->nnode, c->nodes, c->boxes, c->npath, nd, c->dirty_list, c->leaf, c->cap_leaf,
-                                                c->cnt);
+                                                c->cnt, std::min((int)QRY_CAP, c->query_cap));
     CG_LAUNCH_CHECK(c);
   } else {
     dim3 g(div_up(c->ninternal, 256), c->B);

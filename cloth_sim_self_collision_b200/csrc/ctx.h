@@ -186,6 +186,7 @@ struct Ctx {
   unsigned long long* npath = nullptr;  // per node: child choices from the root, left aligned (bit 63 - d = choice at depth d)
   int* ndepth = nullptr;                // per node: depth
   bool inc_refit = true;                // CLOTHGPU_INC_REFIT=0: incremental passes refit the whole tree
+  int query_cap = 256;                  // CLOTHGPU_QUERY_CAP: per-leaf frontier capacity of k_query (tests force the overflow path)
   bool canon_small = true;              // CLOTHGPU_CANON_SMALL=0: every raw list goes through the library sort
   bool query_trav = true;               // CLOTHGPU_QUERY_TRAVERSAL=0: incremental passes use the frontier traversal
   bool incremental_ccd = true;  // CLOTHGPU_INCREMENTAL=0 re-runs every pass in full
