@@ -11,8 +11,21 @@
 namespace cg {
 
 
+// the active flags of up to 64 scenes travel as a kernel argument: no staging buffer, no host synchronisation
+__global__ void k_set_active_mask(int B, int* cnt, unsigned long long mask) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < B) cnt[s * NCNT + CNT_ACTIVE] = (int)((mask >> s) & 1ULL);
+}
+
 int set_active(Ctx* c, const int* active) {
   for (int s = 0; s < c->B; s++) c->h_cnt[s * NCNT + CNT_ACTIVE] = active ? (active[s] != 0) : 1;
+  if (c->B <= 64) {
+    unsigned long long mask = 0;
+    for (int s = 0; s < c->B; s++) mask |= (unsigned long long)(c->h_cnt[s * NCNT + CNT_ACTIVE] != 0) << s;
+    k_set_active_mask<<<1, 64, 0, KS(c, "k_set_active_mask")>>>(c->B, c->cnt, mask);
+    CG_LAUNCH_CHECK(c);
+    return CLOTHGPU_OK;
+  }
   CG_CUDA(cudaMemcpy2DAsync(c->cnt + CNT_ACTIVE, sizeof(int) * NCNT, c->h_cnt + CNT_ACTIVE, sizeof(int) * NCNT,
                             sizeof(int), c->B, cudaMemcpyHostToDevice, c->stream));
   // h_cnt is reused by the next counter fetch: the upload must have left the host buffer before that

@@ -1024,39 +1024,35 @@ int run_contacts(Ctx* c, const double* xyz, const double* uvw, double dt, double
     phase_begin(c, 4);
     // a retry after a queue overflow is always a full pass (the previous raw list does not survive the regrowth)
     if (!(prelaunched && attempt == 0)) CG_CHECK(traverse_and_test(c, xyz, uvw, dt, delta, ccd, incremental && attempt == 0));
+    // small raw lists (most incremental passes) are sorted / compacted right away, one launch for all scenes, before
+    // the counters come back: such a pass costs one host round trip, not two.  The kernel skips scenes whose list is
+    // longer than CANON_SMALL; those go through the library sort below.
+    if (c->canon_small) {
+      const int smem = CANON_SMALL * (int)sizeof(RawElem);
+      CG_CUDA(cudaFuncSetAttribute(k_canon_small, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(smem, 48 * 1024)));
+      k_canon_small<<<c->B, CANON_T, smem, KS(c, "k_canon_small")>>>(CANON_SMALL, c->cap_raw, c->cap_elem, c->raw, c->elems, c->cnt);
+      CG_LAUNCH_CHECK(c);
+    }
     CG_CHECK(fetch_counters(c));
     phase_end(c, 4);
     int bits = 0;
     for (int s = 0; s < c->B; s++) bits |= c->h_cnt[s * NCNT + CNT_OVERFLOW];
-    if (bits == 0) break;
+    if ((bits & ~8) == 0) break;  // (bit 3, the element buffer, is reported below)
     if (attempt >= 12) { set_error("contact work queues keep overflowing"); return CLOTHGPU_ERR_CAPACITY; }
     CG_CHECK(grow_queues(c, bits));
   }
   phase_begin(c, 5);
   {
-    // small raw lists: one launch for all scenes; anything larger goes through the library sort, scene by scene
-    int nsmall = 0, nmax_small = 0;
-    for (int s = 0; s < c->B; s++) {
-      if (!c->h_cnt[s * NCNT + CNT_ACTIVE]) continue;
-      const int nraw = c->h_cnt[s * NCNT + CNT_RAW];
-      if (c->canon_small && nraw <= CANON_SMALL) { nsmall++; nmax_small = std::max(nmax_small, nraw); }
-    }
-    if (nsmall > 0) {
-      int npow2 = 32;
-      while (npow2 < nmax_small) npow2 <<= 1;
-      const int smem = npow2 * (int)sizeof(RawElem);
-      CG_CUDA(cudaFuncSetAttribute(k_canon_small, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(smem, 48 * 1024)));
-      k_canon_small<<<c->B, CANON_T, smem, KS(c, "k_canon_small")>>>(npow2, c->cap_raw, c->cap_elem, c->raw, c->elems, c->cnt);
-      CG_LAUNCH_CHECK(c);
-    }
+    bool any_large = false;
     for (int s = 0; s < c->B; s++) {
       if (!c->h_cnt[s * NCNT + CNT_ACTIVE]) continue;
       const int nraw = c->h_cnt[s * NCNT + CNT_RAW];
       if (c->canon_small && nraw <= CANON_SMALL) continue;
       CG_CHECK(canonical_set(c, s, nraw));
+      any_large = true;
     }
+    if (any_large) CG_CHECK(fetch_counters(c));
   }
-  CG_CHECK(fetch_counters(c));
   phase_end(c, 5);
   for (int s = 0; s < c->B; s++) {
     if (c->h_cnt[s * NCNT + CNT_OVERFLOW] & 8) { set_error("contact element buffer overflow"); return CLOTHGPU_ERR_CAPACITY; }

@@ -451,6 +451,12 @@ __global__ void __launch_bounds__(1024) k_imp_run(int ccd, int np, long long cap
 // clock when it was done, outcome}; launch_impulse prints a summary to stderr
 __device__ long long* g_imp_trace;
 #endif
+// release / acquire around the "done" flags of k_imp_flow (IMP_FENCE_SC: the sequentially consistent __threadfence_block)
+#ifdef IMP_FENCE_SC
+#define IMP_FENCE() __threadfence_block()
+#else
+#define IMP_FENCE() asm volatile("fence.acq_rel.cta;" ::: "memory")
+#endif
 __global__ void __launch_bounds__(256) k_imp_flow(int ccd, int np, long long cap_elem, const int* __restrict__ elems_all,
                                                     const int* __restrict__ pred_all, const double* __restrict__ xyz_all,
                                                     double* uvw_all, const ImpConst K, int* cnt) {
@@ -495,7 +501,7 @@ __global__ void __launch_bounds__(256) k_imp_flow(int ccd, int np, long long cap
 #define IMP_WAIT(P_) if ((P_) >= 0) while (!done[(P_) >> 2]) { if (sleep_ns > 0) __nanosleep(sleep_ns); }
     IMP_WAIT(p.x) IMP_WAIT(p.y) IMP_WAIT(p.z) IMP_WAIT(p.w)
 #undef IMP_WAIT
-    __threadfence_block();
+    IMP_FENCE();
 #ifdef IMP_TRACE
     const long long tr0 = clock64();
     int tr_how = 3;
@@ -516,7 +522,7 @@ __global__ void __launch_bounds__(256) k_imp_flow(int ccd, int np, long long cap
     } else {
       impulse_prx_apply(n, G, uvw, stiffness, dt, mass);
     }
-    __threadfence_block();
+    IMP_FENCE();
     done[k] = 1;
 #ifdef IMP_TRACE
     if (s == 0) { g_imp_trace[k * 3 + 0] = tr0; g_imp_trace[k * 3 + 1] = clock64(); g_imp_trace[k * 3 + 2] = tr_how; }
