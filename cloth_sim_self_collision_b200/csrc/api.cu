@@ -126,6 +126,8 @@ int run_resolve(Ctx* c, const clothgpu_params& p, int* applied, int* stats, bool
     if (stats) {
       stats[s * CLOTHGPU_NSTATS + 4] = app[s];
       stats[s * CLOTHGPU_NSTATS + 7] = c->h_cnt[s * NCNT + CNT_IMP_SLOW];  // as of the last counter fetch
+      stats[s * CLOTHGPU_NSTATS + 14] = c->h_cnt[s * NCNT + CNT_RANK_BAD];
+      stats[s * CLOTHGPU_NSTATS + 15] = c->h_cnt[s * NCNT + CNT_RANK_BAD + 1];
     }
   }
   return CLOTHGPU_OK;

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) k_refit_inc(int nnode, int np, const int*
 // ------------------------------------------------------------------------------------------------ traversal
 __global__ void k_trav_reset(int* cnt) {
   int* c = cnt + blockIdx.x * NCNT;
-  for (int k = threadIdx.x; k < NCNT - CNT_FRONT; k += blockDim.x) c[CNT_FRONT + k] = 0;
+  for (int k = threadIdx.x; k < CNT_RANK_BAD - CNT_FRONT; k += blockDim.x) c[CNT_FRONT + k] = 0;
   if (threadIdx.x == 0) {
     c[CNT_RAWPREV] = c[CNT_RAW];  // raw elements of the previous detection (now in the other raw buffer)
     c[CNT_LEAF] = 0; c[CNT_RAW] = 0; c[CNT_ELEM] = 0; c[CNT_OVERFLOW] = 0; c[CNT_CAND] = 0; c[CNT_GBAR] = 0;
@@ -671,7 +671,7 @@ __global__ void __launch_bounds__(128, NARROW_B) k_narrow(int ccd, int nnode, in
                                                  RawElem* __restrict__ raw, long long cap_raw, int* cnt,
                                                  const int* __restrict__ nodes, const uint32_t* __restrict__ pre,
                                                  const unsigned long long* __restrict__ npath,
-                                                 const int* __restrict__ ndepth) {
+                                                 const int* __restrict__ ndepth, int rank_check) {
   const int s = blockIdx.y;
   int* c = cnt + s * NCNT;
   if (!c[CNT_ACTIVE]) return;
@@ -699,7 +699,17 @@ __global__ void __launch_bounds__(128, NARROW_B) k_narrow(int ccd, int nnode, in
       if (slot < 6) canon_fv(S.n[0], S.n[1], S.n[2], S.n[3], key);
       else canon_ee(S.n[0], S.n[1], S.n[2], S.n[3], key);
       PairEnt e = lf[cs.w];  // the pair's DFS rank is only needed for the (rare) hits
-      if (e.pre == 0xffffffffu) pair_rank(e.i0, e.i1, nodes, pre, npath, ndepth, e);
+      if (e.pre == 0xffffffffu) {
+        pair_rank(e.i0, e.i1, nodes, pre, npath, ndepth, e);
+      } else if (rank_check) {
+        // CLOTHGPU_RANK_CHECK=1 (tests): a pair of the frontier traversal carries its rank; the reconstruction from the
+        // root paths and the orientation rule of k_query must give the same
+        PairEnt e2 = e;
+        pair_rank(e.i0, e.i1, nodes, pre, npath, ndepth, e2);
+        if (e2.pre != e.pre || e2.path_hi != e.path_hi || e2.path_lo != e.path_lo || !(npath[e.i0] < npath[e.i1]))
+          atomicAdd(&c[CNT_RANK_BAD], 1);
+        atomicAdd(&c[CNT_RANK_BAD + 1], 1);
+      }
       emit(e, slot, key, rw, cap_raw, c);
     }
   }
@@ -976,7 +986,7 @@ static int traverse_and_test(Ctx* c, const double* xyz, const double* uvw, doubl
     dim3 g2(148 * 4, c->B);
     k_narrow<<<g2, 128, 0, KS(c, "k_narrow")>>>(ccd, c->nnode, c->np, (const int4*)c->node_tri, c->boxes, xyz, uvw, dt, delta, c->leaf,
                                         c->cap_leaf, c->cand, c->cap_leaf * 2, c->raw, c->cap_raw, c->cnt, c->nodes, c->pre, c->npath,
-                                        c->ndepth);
+                                        c->ndepth, c->rank_check ? 1 : 0);
     CG_LAUNCH_CHECK(c);
   }
   return CLOTHGPU_OK;

@@ -107,7 +107,8 @@ enum {
   CNT_GBAR = 13,     // arrival counter of the level barrier of the fused traversal kernel
   CNT_NDIRTY = 15,   // dirty leaves of the current incremental pass (entries of dirty_list)
   CNT_IMP_SLOW = 14, // impulse elements whose fast arithmetic could not be certified (cumulative, diagnostic)
-  CNT_FRONT = 16     // frontier sizes per traversal depth: CNT_FRONT + depth  (depth < 72)
+  CNT_FRONT = 16,    // frontier sizes per traversal depth: CNT_FRONT + depth  (depth < 72)
+  CNT_RANK_BAD = 90  // CLOTHGPU_RANK_CHECK: [0] narrow-phase hits whose rebuilt DFS rank differs from the carried one, [1] hits checked (cumulative)
 };
 // per-scene device scalars (doubles): layout of scal[]
 enum { SC_INV_SQ0 = 0, SC_RPR = 1, SC_PAP = 2, SC_SQ = 3, SC_ALPHA = 4, SC_BETA = 5, SC_CONV = 6, SC_TOL2 = 7,
@@ -186,6 +187,7 @@ struct Ctx {
   unsigned long long* npath = nullptr;  // per node: child choices from the root, left aligned (bit 63 - d = choice at depth d)
   int* ndepth = nullptr;                // per node: depth
   bool inc_refit = true;                // CLOTHGPU_INC_REFIT=0: incremental passes refit the whole tree
+  bool rank_check = false;              // CLOTHGPU_RANK_CHECK=1: k_narrow cross-checks pair_rank against the ranks the frontier traversal carries
   int query_cap = 256;                  // CLOTHGPU_QUERY_CAP: per-leaf frontier capacity of k_query (tests force the overflow path)
   bool canon_small = true;              // CLOTHGPU_CANON_SMALL=0: every raw list goes through the library sort
   bool query_trav = true;               // CLOTHGPU_QUERY_TRAVERSAL=0: incremental passes use the frontier traversal

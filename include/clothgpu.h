@@ -104,6 +104,8 @@ enum { CLOTHGPU_NSTATS = 256 };
  * [4]=is_impulse_applied, [5]=last "NNode In RIZ", [6]=1 if the RIZ loop ended with "Resolved All Collisions",
  * [7]=diagnostic, not a reference quantity: impulse elements (cumulative over the context's life) whose certified
  *     fast arithmetic had to fall back to the plain IEEE operations (same result either way),
+ * [14],[15]=diagnostic (CLOTHGPU_RANK_CHECK=1): narrow-phase hits whose depth-first rank rebuilt from the root paths
+ *     differs from the rank the frontier traversal carries (must be 0) / hits checked, cumulative,
  * [8..13)=CCD elems per impulse pass, [16..116)=CCD elems per RIZ round, [128..228)="NNode In RIZ" per RIZ round */
 
 /* ------------------------------------------------------------------------------------------------ life cycle */

@@ -895,3 +895,23 @@ def test_certified_fast_arithmetic_selftest():
     print("certified math: mismatches / uncertified per test:", o.tolist())
     assert (o[:, 0] == 0).all(), o
     assert (o[:, 1] < 0.01 * n).all(), o
+
+
+def test_pair_rank_reconstruction_matches_the_traversal(oracle, monkeypatch):
+    """The leaf-query traversal of the incremental CCD passes (k_query) does not carry the depth-first rank of a leaf
+    pair; the narrow phase rebuilds it from the two root-to-leaf paths (pair_rank).  The rank only decides FV / EE key
+    collisions, which trajectories rarely contain, so it is checked directly: with CLOTHGPU_RANK_CHECK=1 every
+    narrow-phase hit of the full (frontier) passes is re-ranked and compared with the rank the traversal carried,
+    together with the orientation rule of the query."""
+    monkeypatch.setenv("CLOTHGPU_RANK_CHECK", "1")
+    sc = _scene_with_bvh(oracle, 31, 40)
+    p = T.params_for(sc, S.SELF_CONTACT)
+    x0, v0 = T.folded_state(sc, gap=0.006, vel=5.0)
+    g = G.ClothGPU(sc)
+    g.upload_state(x0, v0)
+    st = None
+    for _ in range(4):
+        st = g.step_self_contact(p, 1)[0]
+    g.close()
+    assert st[15] > 1000, "the scene must produce narrow-phase hits to check (%d)" % st[15]
+    assert st[14] == 0, "pair_rank disagrees with the traversal on %d of %d hits" % (st[14], st[15])
