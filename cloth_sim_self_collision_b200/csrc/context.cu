@@ -456,6 +456,8 @@ static int create_impl(Ctx* c, int nscene, int np, int ntri, int nquad, const in
     {
       const char* e1 = getenv("CLOTHGPU_INC_REFIT");
       c->inc_refit = !(e1 && atoi(e1) == 0);
+      const char* e6 = getenv("CLOTHGPU_RIZ_FUSED");
+      c->riz_fused = !(e6 && atoi(e6) == 0);
       const char* e5 = getenv("CLOTHGPU_RANK_CHECK");
       c->rank_check = e5 && atoi(e5) != 0;
       const char* e4 = getenv("CLOTHGPU_QUERY_CAP");

@@ -709,17 +709,9 @@ __global__ void k_riz_keys(int np, const int* __restrict__ label, unsigned* __re
 // ApplyRigidImpactZone, self_collision_cloth.cpp:298-348, one thread per zone (segment of the label-sorted vertex
 // list, ascending vertex id inside the segment = std::set<int> order).
 // Reference quirk (:327-329): the "inertia tensor" diagonal uses v.v (velocity) where q.q (position) is meant.
-__global__ void k_riz_apply(int np, const unsigned* __restrict__ keys, const int* __restrict__ vals,
-                            const double* __restrict__ xyz, const double* __restrict__ uvw0, double* __restrict__ uvw,
-                            int* cnt) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= np) return;
-  const unsigned key = keys[i];
-  if (key == 0x7fffffffu) return;
-  atomicAdd(&cnt[CNT_RIZ_NODES], 1);
-  if (i > 0 && keys[i - 1] == key) return;
-  int e = i;
-  while (e < np && keys[e] == key) e++;
+// one rigid impact zone: the members vals[i .. e) in ascending vertex id (ApplyRigidImpactZone, self_collision_cloth.cpp:298-348)
+__device__ __forceinline__ void riz_zone(int i, int e, const int* __restrict__ vals, const double* __restrict__ xyz,
+                                         const double* __restrict__ uvw0, double* __restrict__ uvw) {
   V3 gc = v3(0, 0, 0), av = v3(0, 0, 0);
   for (int j = i; j < e; j++) {
     gc = gc + ld3(xyz, vals[j]);
@@ -766,7 +758,83 @@ __global__ void k_riz_apply(int np, const unsigned* __restrict__ keys, const int
     uvw[v * 3 + 2] = av.z + rot.z;
   }
 }
+
+__global__ void k_riz_apply(int np, const unsigned* __restrict__ keys, const int* __restrict__ vals,
+                            const double* __restrict__ xyz, const double* __restrict__ uvw0, double* __restrict__ uvw,
+                            int* cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  const unsigned key = keys[i];
+  if (key == 0x7fffffffu) return;
+  atomicAdd(&cnt[CNT_RIZ_NODES], 1);
+  if (i > 0 && keys[i - 1] == key) return;
+  int e = i;
+  while (e < np && keys[e] == key) e++;
+  riz_zone(i, e, vals, xyz, uvw0, uvw);
+}
 __global__ void k_zero_cnt(int* cnt, int slot) { cnt[blockIdx.x * NCNT + slot] = 0; }
+
+// ApplyRigidImpactZone for all scenes in ONE launch (one CTA per scene) instead of, per scene, a key kernel, a library
+// radix sort of all np vertices and the zone kernel: the members (a few hundred vertices, typically) are collected,
+// sorted by (zone label, vertex id) with a bitonic network -- in shared memory up to RIZ_SMEM members, in a global
+// scratch array beyond -- and every zone is then reduced by one thread exactly as in k_riz_apply (riz_zone).
+enum { RIZ_T = 1024, RIZ_SMEM = 4096 };
+__global__ void __launch_bounds__(RIZ_T) k_riz_apply_all(int np, const int* __restrict__ label_all,
+                                                          const double* __restrict__ xyz_all, const double* __restrict__ uvw0_all,
+                                                          double* __restrict__ uvw_all, unsigned long long* __restrict__ gkeys_all,
+                                                          int* __restrict__ gvals_all, int* cnt) {
+  __shared__ unsigned long long skeys[RIZ_SMEM];
+  __shared__ int svals_n, s_total;
+  const int s = blockIdx.x;
+  int* c = cnt + s * NCNT;
+  if (!c[CNT_ACTIVE]) return;
+  const int* label = label_all + (size_t)s * np;
+  const double* xyz = xyz_all + (size_t)s * np * 3;
+  const double* uvw0 = uvw0_all + (size_t)s * np * 3;
+  double* uvw = uvw_all + (size_t)s * np * 3;
+  if (threadIdx.x == 0) { svals_n = 0; s_total = 0; }
+  __syncthreads();
+  int mine = 0;
+  for (int v = threadIdx.x; v < np; v += blockDim.x) mine += label[v] >= 0;
+  if (mine) atomicAdd(&s_total, mine);
+  __syncthreads();
+  const int n = s_total;
+  if (threadIdx.x == 0) c[CNT_RIZ_NODES] = n;
+  if (n == 0) return;
+  int N = 1;
+  while (N < n) N <<= 1;
+  unsigned long long* keys = (N <= RIZ_SMEM) ? skeys : gkeys_all + (size_t)s * 2 * np;  // (N < 2 np)
+  for (int v = threadIdx.x; v < np; v += blockDim.x) {
+    const int l = label[v];
+    if (l >= 0) keys[atomicAdd(&svals_n, 1)] = ((unsigned long long)(unsigned)l << 32) | (unsigned)v;
+  }
+  for (int i = n + threadIdx.x; i < N; i += blockDim.x) keys[i] = ~0ULL;
+  __syncthreads();
+  for (int k = 2; k <= N; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = keys[i], b = keys[l];
+          const bool up = (i & k) == 0;
+          if (up ? (b < a) : (a < b)) { keys[i] = b; keys[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // vertex ids in sorted order (the member list riz_zone walks); the keys stay for the zone boundaries
+  int* vals = gvals_all + (size_t)s * np;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) vals[i] = (int)(keys[i] & 0xffffffffULL);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned zl = (unsigned)(keys[i] >> 32);
+    if (i > 0 && (unsigned)(keys[i - 1] >> 32) == zl) continue;
+    int e = i;
+    while (e < n && (unsigned)(keys[e] >> 32) == zl) e++;
+    riz_zone(i, e, vals, xyz, uvw0, uvw);
+  }
+}
 
 int launch_riz_reset(Ctx* c) {
   CG_CUDA(cudaMemsetAsync(c->zone, 0xff, sizeof(int) * (size_t)c->B * c->np, c->stream));
@@ -787,6 +855,13 @@ int launch_riz_make(Ctx* c) {
 }
 
 int launch_riz_apply(Ctx* c, const double* xyz, double* uvw) {
+  if (c->riz_fused) {
+    // scratch per scene: 2 np keys (a power of two >= the member count) + np vertex ids
+    CG_CHECK(ensure_sort_capacity(c, 2LL * c->np * c->B));
+    k_riz_apply_all<<<c->B, RIZ_T, 0, KS(c, "k_riz_apply")>>>(c->np, c->zone_label, xyz, c->uvw0, uvw, c->sort_keys, c->sort_vals, c->cnt);
+    CG_LAUNCH_CHECK(c);
+    return CLOTHGPU_OK;
+  }
   k_zero_cnt<<<c->B, 1, 0, KS(c, "k_zero_cnt")>>>(c->cnt, CNT_RIZ_NODES);
   CG_LAUNCH_CHECK(c);
   CG_CHECK(ensure_sort_capacity(c, c->np));
