@@ -530,6 +530,159 @@ __global__ void __launch_bounds__(256) k_imp_flow(int ccd, int np, long long cap
   }
 }
 
+// Data-flow sweep with a velocity MAILBOX in shared memory.  In k_imp_flow an element hands its result to its successor
+// through global memory: twelve stores, a CTA fence behind them, a flag, and on the other side twelve loads that miss
+// L1 (the stores of another warp invalidate the lines): the ncu source view attributes 30 % of a proximity hop and 8 %
+// of a CCD hop to the first use of those loads.  Here every element leaves the velocities of its four vertices (changed
+// or not) in a ring slot in shared memory and sets bit 0 of its flag; only then does it write global memory, fence and
+// set bit 1.  A successor at most IMP_RING elements behind waits for bit 0 of its predecessors, reads the four slots
+// in one batch of loads and validates the slots' tags (re-read after the data: a slot recycled in the meantime sends
+// that corner to the global path, which waits for bit 1); anyone else waits for bit 1 and reads global memory.  An
+// element's slot is invalidated (tag = -1, fence) when its thread picks the element up, long before the data is
+// written, so publishing costs one fence with nothing but shared-memory stores in flight.  Same arithmetic, same order.
+enum { IMP_RING = 1024, IMP_SLOT = 13 };  // slot: 12 velocity components + tag (element index)
+__device__ __forceinline__ V3 ldcg3(const double* a, int i) { return v3(__ldcg(a + i * 3 + 0), __ldcg(a + i * 3 + 1), __ldcg(a + i * 3 + 2)); }
+// the reference arithmetic as a call: elements whose fast arithmetic could not be certified (rare) land here
+__device__ __noinline__ void impulse_ccd_slow(const int* n, const double* xyz, double* uvw, double delta, double dt, double mass) {
+  impulse_ccd_apply(n, ld3(xyz, n[0]), ld3(xyz, n[1]), ld3(xyz, n[2]), ld3(xyz, n[3]), uvw, delta, dt, mass);
+}
+template <int CCD>
+__global__ void __launch_bounds__(256) k_imp_flow_mb(int np, long long cap_elem, const int* __restrict__ elems_all,
+                                                       const int* __restrict__ pred_all, const double* __restrict__ xyz_all,
+                                                       double* uvw_all, const ImpConst K, int done_bytes, int* cnt) {
+  extern __shared__ __align__(16) unsigned char imp_sm[];
+  const double delta = K.delta, stiffness = K.stiffness, dt = K.dt, mass = K.mass;
+  const int s = blockIdx.x;
+  int* c = cnt + s * NCNT;
+  if (!c[CNT_ACTIVE]) return;
+  const int ne = c[CNT_ELEM];
+  if (ne == 0) return;
+  const int* elems = elems_all + (size_t)s * cap_elem * 5;
+  const int4* pred = reinterpret_cast<const int4*>(pred_all + (size_t)s * cap_elem * 4);
+  const double* xyz = xyz_all + (size_t)s * np * 3;
+  double* uvw = uvw_all + (size_t)s * np * 3;
+  volatile unsigned char* done = imp_sm;  // bit 0: mailbox slot written, bit 1: global memory written and fenced
+  volatile double* ring = reinterpret_cast<volatile double*>(imp_sm + done_bytes);
+  volatile long long* tags = reinterpret_cast<volatile long long*>(imp_sm + done_bytes);
+  for (int k = threadIdx.x; k < ne; k += blockDim.x) imp_sm[k] = 0;
+  for (int r = threadIdx.x; r < IMP_RING; r += blockDim.x) tags[r * IMP_SLOT + 12] = -1;
+  __syncthreads();
+  const int nwarp = blockDim.x >> 5;
+  if ((int)(threadIdx.x & 31) >= K.lanes) return;
+  const unsigned sleep_ns = (unsigned)K.sleep_ns;
+  const int slot0 = (threadIdx.x & 31) * nwarp + (threadIdx.x >> 5);
+  for (int k = slot0; k < ne; k += nwarp * K.lanes) {
+    const size_t myslot = (size_t)(k & (IMP_RING - 1)) * IMP_SLOT;
+    tags[myslot + 12] = -1;  // the slot's previous owner is IMP_RING elements back: its late readers take the global path
+    IMP_FENCE();
+    const int4 p4 = pred[k];
+    const int pr[4] = {p4.x, p4.y, p4.z, p4.w};
+    int n[5];
+#pragma unroll
+    for (int a = 0; a < 5; a++) n[a] = elems[(size_t)k * 5 + a];
+    PrxGeom G;
+    V3 q0 = v3(0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
+    if (!CCD) {  // velocity independent: in the shadow of the wait
+      impulse_prx_geom(n, xyz, delta, G);
+      impulse_prx_geom_more(G, stiffness, dt);
+    } else {
+      q0 = ld3(xyz, n[0]); q1 = ld3(xyz, n[1]); q2 = ld3(xyz, n[2]); q3 = ld3(xyz, n[3]);
+    }
+    V3 v[4];
+    // a vertex without predecessor keeps the velocity it had before the sweep: loaded ahead of the wait
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+      if (pr[a] < 0) v[a] = ldcg3(uvw, n[a]);
+#ifdef IMP_TRACE
+    long long tr_ready;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(tr_ready) : "d"(CCD ? q0.x + q1.x + q2.x + q3.x : G.p_depth + G.yden) : "memory");
+#endif
+    // wait: bit 0 of the predecessors within reach of the ring, bit 1 of the others
+    bool near[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      near[a] = pr[a] >= 0 && k - (pr[a] >> 2) < IMP_RING;
+      if (pr[a] >= 0) {
+        const int e = pr[a] >> 2;
+        const unsigned char bit = near[a] ? 1 : 2;
+        while (!(done[e] & bit)) { if (sleep_ns > 0) __nanosleep(sleep_ns); }
+      }
+    }
+    // one batch of loads: tag, three components, tag for every near corner
+    long long t1[4], t2[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const int e = near[a] ? (pr[a] >> 2) : 0, ce = near[a] ? (pr[a] & 3) : 0;
+      const size_t sl = (size_t)(e & (IMP_RING - 1)) * IMP_SLOT;
+      t1[a] = tags[sl + 12];
+      if (near[a]) v[a] = v3(ring[sl + ce * 3 + 0], ring[sl + ce * 3 + 1], ring[sl + ce * 3 + 2]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const int e = near[a] ? (pr[a] >> 2) : 0;
+      t2[a] = tags[(size_t)(e & (IMP_RING - 1)) * IMP_SLOT + 12];
+    }
+    unsigned need_global = 0;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      if (pr[a] < 0) continue;
+      const long long e = pr[a] >> 2;
+      if (!near[a] || t1[a] != e || t2[a] != e) need_global |= 1u << a;
+    }
+    if (need_global) {
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+        if ((need_global >> a & 1) && near[a]) while (!(done[pr[a] >> 2] & 2)) { if (sleep_ns > 0) __nanosleep(sleep_ns); }
+      IMP_FENCE();
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+        if (need_global >> a & 1) v[a] = ldcg3(uvw, n[a]);
+    }
+#ifdef IMP_TRACE
+    long long tr0;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(tr0) : "d"(v[0].x + v[1].x + v[2].x + v[3].x) : "memory");
+#endif
+    bool wrote;
+    if (CCD) {
+      int how = impulse_ccd_fast_v(n[4], q0, q1, q2, q3, v, K);
+      if (how == 2) {
+        // not certified: the reference arithmetic on global memory.  Every predecessor's global result must be there.
+        atomicAdd(&c[CNT_IMP_SLOW], 1);
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+          if (pr[a] >= 0) while (!(done[pr[a] >> 2] & 2)) { if (sleep_ns > 0) __nanosleep(sleep_ns); }
+        IMP_FENCE();
+        impulse_ccd_slow(n, xyz, uvw, delta, dt, mass);
+        IMP_FENCE();
+#pragma unroll
+        for (int a = 0; a < 4; a++) v[a] = ldcg3(uvw, n[a]);
+        how = 0;  // global memory is already up to date
+      }
+      wrote = how == 1;
+    } else {
+      bool certified;
+      wrote = impulse_prx_apply_fast_v(G, v, K, certified);
+      if (!certified) atomicAdd(&c[CNT_IMP_SLOW], 1);
+    }
+    // mailbox data, fence, tag, bit 0: the successor can go on
+#pragma unroll
+    for (int a = 0; a < 4; a++) { ring[myslot + a * 3 + 0] = v[a].x; ring[myslot + a * 3 + 1] = v[a].y; ring[myslot + a * 3 + 2] = v[a].z; }
+    IMP_FENCE();
+    tags[myslot + 12] = (long long)k;
+    done[k] = 1;
+#ifdef IMP_TRACE
+    if (s == 0) { g_imp_trace[k * 3 + 0] = tr0; g_imp_trace[k * 3 + 1] = clock64(); g_imp_trace[k * 3 + 2] = tr_ready; }
+#endif
+    // global memory and bit 1, off the chain's critical path
+    if (wrote) {
+#pragma unroll
+      for (int a = 0; a < 4; a++) st3(uvw, n[a], v[a]);
+    }
+    IMP_FENCE();
+    done[k] = 3;
+  }
+}
+
 // smallest x with sqrt(x) >= c / largest x with sqrt(x) <= c (the host sqrt is the correctly rounded IEEE operation)
 static double sqrt_ge_threshold(double c) {
   double x = c * c;
@@ -589,6 +742,55 @@ int launch_impulse(Ctx* c, const double* xyz, double* uvw, double delta, double 
     const int smem = (ne_max + 127) / 128 * 128;
     CG_CUDA(cudaFuncSetAttribute(k_imp_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(smem, 48 * 1024)));
     const int imp_threads = c->imp_threads;
+    {
+      const ImpConst K0 = make_imp_const(c, delta, stiffness, dt, mass);
+      const int done_bytes = (ne_max + 127) / 128 * 128;
+      const int smem_mb = done_bytes + IMP_RING * IMP_SLOT * 8;
+      if (K0.fast && c->imp_mailbox && smem_mb <= 227 * 1024) {
+#ifdef IMP_TRACE
+        static long long* tr_dev2 = nullptr;
+        if (!tr_dev2) {
+          CG_CUDA(cudaMalloc((void**)&tr_dev2, sizeof(long long) * 3 * (1 << 20)));
+          CG_CUDA(cudaMemcpyToSymbol(g_imp_trace, &tr_dev2, sizeof(tr_dev2)));
+        }
+#endif
+        if (ccd) {
+          CG_CUDA(cudaFuncSetAttribute(k_imp_flow_mb<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_mb));
+          k_imp_flow_mb<1><<<c->B, imp_threads, smem_mb, KS(c, "k_imp_flow")>>>(c->np, c->cap_elem, c->elems, c->imp_pred, xyz, uvw, K0,
+                                                                       done_bytes, c->cnt);
+        } else {
+          CG_CUDA(cudaFuncSetAttribute(k_imp_flow_mb<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_mb));
+          k_imp_flow_mb<0><<<c->B, imp_threads, smem_mb, KS(c, "k_imp_flow")>>>(c->np, c->cap_elem, c->elems, c->imp_pred, xyz, uvw, K0,
+                                                                       done_bytes, c->cnt);
+        }
+        CG_LAUNCH_CHECK(c);
+#ifdef IMP_TRACE
+        {
+          const int ne = std::min(c->h_cnt[CNT_ELEM], 1 << 20);
+          std::vector<long long> tr((size_t)ne * 3);
+          std::vector<int> pred((size_t)ne * 4);
+          CG_CUDA(cudaStreamSynchronize(c->stream));
+          CG_CUDA(cudaMemcpy(tr.data(), tr_dev2, sizeof(long long) * 3 * ne, cudaMemcpyDeviceToHost));
+          CG_CUDA(cudaMemcpy(pred.data(), c->imp_pred, sizeof(int) * 4 * ne, cudaMemcpyDeviceToHost));
+          double comp = 0, hand = 0, late = 0;
+          long long nh = 0, nlate = 0, tmin = LLONG_MAX, tmax = 0;
+          for (int k = 0; k < ne; k++) {
+            comp += (double)(tr[k * 3 + 1] - tr[k * 3 + 0]);
+            long long last = -1;
+            for (int a = 0; a < 4; a++) if (pred[k * 4 + a] >= 0) last = std::max(last, tr[(size_t)(pred[k * 4 + a] >> 2) * 3 + 1]);
+            if (last >= 0) {
+              hand += (double)(tr[k * 3 + 0] - last); nh++;
+              if (tr[k * 3 + 2] > last) { nlate++; late += (double)(tr[k * 3 + 2] - last); }
+            }
+            tmin = std::min(tmin, tr[k * 3 + 0]); tmax = std::max(tmax, tr[k * 3 + 1]);
+          }
+          fprintf(stderr, "imptrace MAILBOX ccd=%d ne=%d span=%lld cyc  compute/elem=%.0f  handoff/elem=%.0f (n=%lld)  late starters %lld (mean lateness %.0f)\n", ccd, ne,
+                  ne ? tmax - tmin : 0, ne ? comp / ne : 0.0, nh ? hand / nh : 0.0, nh, nlate, nlate ? late / nlate : 0.0);
+        }
+#endif
+        return CLOTHGPU_OK;
+      }
+    }
 #ifdef IMP_TRACE
     static long long* tr_dev = nullptr;
     const int tr_cap = 1 << 20;

@@ -67,3 +67,27 @@ for it in range(5):
     if len(e) == 0:
         break
     uvw = analyse("ccd %d" % it, e, uvw, lambda u, el: lib.impulse_ccd(u, cl, k, dt, m, x_prev, el))
+
+
+def distances(name, elems):
+    """distribution of the distance (in elements) to the predecessor on each vertex"""
+    last = {}
+    far = {256: 0, 1024: 0, 4096: 0, 16384: 0}
+    anyfar = {256: 0, 1024: 0, 4096: 0, 16384: 0}
+    for k, row in enumerate(elems):
+        dmax = 0
+        for vv in row[:4]:
+            vv = int(vv)
+            if vv in last:
+                dmax = max(dmax, k - last[vv])
+            last[vv] = k
+        for t in far:
+            if dmax >= t:
+                anyfar[t] += 1
+    print("%s: %d elements; elements whose farthest predecessor is >= 256 / 1024 / 4096 / 16384 back: %s" %
+          (name, len(elems), [anyfar[t] for t in (256, 1024, 4096, 16384)]), flush=True)
+
+
+if os.environ.get("PROBE_DIST"):
+    boxes = lib.refit_prx(sc, x_prev, cl)
+    distances("prox", lib.contacts_prx(sc, boxes, x_prev, cl))
