@@ -479,10 +479,6 @@ static int create_impl(Ctx* c, int nscene, int np, int ntri, int nquad, const in
       c->trav_sms = pr.multiProcessorCount;
       const char* it = getenv("CLOTHGPU_IMP_THREADS");
       if (it) c->imp_threads = std::min(1024, std::max(32, atoi(it) / 32 * 32));
-      const char* iwk = getenv("CLOTHGPU_IMP_WALK");
-      if (iwk) c->imp_walk = atoi(iwk) != 0;
-      const char* imb = getenv("CLOTHGPU_IMP_MAILBOX");
-      if (imb) c->imp_mailbox = atoi(imb) != 0;
       const char* isl = getenv("CLOTHGPU_IMP_SLEEP");
       if (isl) c->imp_sleep_ns = std::min(100000, std::max(0, atoi(isl)));
       const char* il = getenv("CLOTHGPU_IMP_LANES");

@@ -196,8 +196,6 @@ struct Ctx {
   int imp_threads = 256;        // CLOTHGPU_IMP_THREADS: threads of the data-flow impulse kernel
   int imp_sleep_ns = 100;       // CLOTHGPU_IMP_SLEEP: nanoseconds between two polls of a predecessor's flag
   int imp_lanes = 32;           // CLOTHGPU_IMP_LANES: working lanes per warp of the data-flow impulse kernel
-  bool imp_walk = true;         // CLOTHGPU_IMP_WALK=0: data-flow impulse kernels (k_imp_flow / k_imp_flow_mb) instead of the single walker
-  bool imp_mailbox = false;     // CLOTHGPU_IMP_MAILBOX=1: impulses hand their results over through a shared-memory ring (k_imp_flow_mb)
   bool imp_fast = true;         // CLOTHGPU_IMP_FAST=0: impulses with the plain IEEE divisions / square roots only (imp_fast.cuh)
   int trav_coop = 0;            // max scenes for which the fused (cooperative) traversal is co-resident; 0 = off
   int trav_sms = 148;

@@ -530,306 +530,6 @@ __global__ void __launch_bounds__(256) k_imp_flow(int ccd, int np, long long cap
   }
 }
 
-// Data-flow sweep with a velocity MAILBOX in shared memory.  In k_imp_flow an element hands its result to its successor
-// through global memory: twelve stores, a CTA fence behind them, a flag, and on the other side twelve loads that miss
-// L1 (the stores of another warp invalidate the lines): the ncu source view attributes 30 % of a proximity hop and 8 %
-// of a CCD hop to the first use of those loads.  Here every element leaves the velocities of its four vertices (changed
-// or not) in a ring slot in shared memory and sets bit 0 of its flag; only then does it write global memory, fence and
-// set bit 1.  A successor at most IMP_RING elements behind waits for bit 0 of its predecessors, reads the four slots
-// in one batch of loads and validates the slots' tags (re-read after the data: a slot recycled in the meantime sends
-// that corner to the global path, which waits for bit 1); anyone else waits for bit 1 and reads global memory.  An
-// element's slot is invalidated (tag = -1, fence) when its thread picks the element up, long before the data is
-// written, so publishing costs one fence with nothing but shared-memory stores in flight.  Same arithmetic, same order.
-enum { IMP_RING = 1024, IMP_SLOT = 13 };  // slot: 12 velocity components + tag (element index)
-__device__ __forceinline__ V3 ldcg3(const double* a, int i) { return v3(__ldcg(a + i * 3 + 0), __ldcg(a + i * 3 + 1), __ldcg(a + i * 3 + 2)); }
-// the reference arithmetic as a call: elements whose fast arithmetic could not be certified (rare) land here
-__device__ __noinline__ void impulse_ccd_slow(const int* n, const double* xyz, double* uvw, double delta, double dt, double mass) {
-  impulse_ccd_apply(n, ld3(xyz, n[0]), ld3(xyz, n[1]), ld3(xyz, n[2]), ld3(xyz, n[3]), uvw, delta, dt, mass);
-}
-template <int CCD>
-__global__ void __launch_bounds__(256) k_imp_flow_mb(int np, long long cap_elem, const int* __restrict__ elems_all,
-                                                       const int* __restrict__ pred_all, const double* __restrict__ xyz_all,
-                                                       double* uvw_all, const ImpConst K, int done_bytes, int* cnt) {
-  extern __shared__ __align__(16) unsigned char imp_sm[];
-  const double delta = K.delta, stiffness = K.stiffness, dt = K.dt, mass = K.mass;
-  const int s = blockIdx.x;
-  int* c = cnt + s * NCNT;
-  if (!c[CNT_ACTIVE]) return;
-  const int ne = c[CNT_ELEM];
-  if (ne == 0) return;
-  const int* elems = elems_all + (size_t)s * cap_elem * 5;
-  const int4* pred = reinterpret_cast<const int4*>(pred_all + (size_t)s * cap_elem * 4);
-  const double* xyz = xyz_all + (size_t)s * np * 3;
-  double* uvw = uvw_all + (size_t)s * np * 3;
-  volatile unsigned char* done = imp_sm;  // bit 0: mailbox slot written, bit 1: global memory written and fenced
-  volatile double* ring = reinterpret_cast<volatile double*>(imp_sm + done_bytes);
-  volatile long long* tags = reinterpret_cast<volatile long long*>(imp_sm + done_bytes);
-  for (int k = threadIdx.x; k < ne; k += blockDim.x) imp_sm[k] = 0;
-  for (int r = threadIdx.x; r < IMP_RING; r += blockDim.x) tags[r * IMP_SLOT + 12] = -1;
-  __syncthreads();
-  const int nwarp = blockDim.x >> 5;
-  if ((int)(threadIdx.x & 31) >= K.lanes) return;
-  const unsigned sleep_ns = (unsigned)K.sleep_ns;
-  const int slot0 = (threadIdx.x & 31) * nwarp + (threadIdx.x >> 5);
-  for (int k = slot0; k < ne; k += nwarp * K.lanes) {
-    const size_t myslot = (size_t)(k & (IMP_RING - 1)) * IMP_SLOT;
-    tags[myslot + 12] = -1;  // the slot's previous owner is IMP_RING elements back: its late readers take the global path
-    IMP_FENCE();
-    const int4 p4 = pred[k];
-    const int pr[4] = {p4.x, p4.y, p4.z, p4.w};
-    int n[5];
-#pragma unroll
-    for (int a = 0; a < 5; a++) n[a] = elems[(size_t)k * 5 + a];
-    PrxGeom G;
-    V3 q0 = v3(0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
-    if (!CCD) {  // velocity independent: in the shadow of the wait
-      impulse_prx_geom(n, xyz, delta, G);
-      impulse_prx_geom_more(G, stiffness, dt);
-    } else {
-      q0 = ld3(xyz, n[0]); q1 = ld3(xyz, n[1]); q2 = ld3(xyz, n[2]); q3 = ld3(xyz, n[3]);
-    }
-    V3 v[4];
-    // a vertex without predecessor keeps the velocity it had before the sweep: loaded ahead of the wait
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-      if (pr[a] < 0) v[a] = ldcg3(uvw, n[a]);
-#ifdef IMP_TRACE
-    long long tr_ready;
-    asm volatile("mov.u64 %0, %%clock64;" : "=l"(tr_ready) : "d"(CCD ? q0.x + q1.x + q2.x + q3.x : G.p_depth + G.yden) : "memory");
-#endif
-    // wait: bit 0 of the predecessors within reach of the ring, bit 1 of the others
-    bool near[4];
-#pragma unroll
-    for (int a = 0; a < 4; a++) {
-      near[a] = pr[a] >= 0 && k - (pr[a] >> 2) < IMP_RING;
-      if (pr[a] >= 0) {
-        const int e = pr[a] >> 2;
-        const unsigned char bit = near[a] ? 1 : 2;
-        while (!(done[e] & bit)) { if (sleep_ns > 0) __nanosleep(sleep_ns); }
-      }
-    }
-    // one batch of loads: tag, three components, tag for every near corner
-    long long t1[4], t2[4];
-#pragma unroll
-    for (int a = 0; a < 4; a++) {
-      const int e = near[a] ? (pr[a] >> 2) : 0, ce = near[a] ? (pr[a] & 3) : 0;
-      const size_t sl = (size_t)(e & (IMP_RING - 1)) * IMP_SLOT;
-      t1[a] = tags[sl + 12];
-      if (near[a]) v[a] = v3(ring[sl + ce * 3 + 0], ring[sl + ce * 3 + 1], ring[sl + ce * 3 + 2]);
-    }
-#pragma unroll
-    for (int a = 0; a < 4; a++) {
-      const int e = near[a] ? (pr[a] >> 2) : 0;
-      t2[a] = tags[(size_t)(e & (IMP_RING - 1)) * IMP_SLOT + 12];
-    }
-    unsigned need_global = 0;
-#pragma unroll
-    for (int a = 0; a < 4; a++) {
-      if (pr[a] < 0) continue;
-      const long long e = pr[a] >> 2;
-      if (!near[a] || t1[a] != e || t2[a] != e) need_global |= 1u << a;
-    }
-    if (need_global) {
-#pragma unroll
-      for (int a = 0; a < 4; a++)
-        if ((need_global >> a & 1) && near[a]) while (!(done[pr[a] >> 2] & 2)) { if (sleep_ns > 0) __nanosleep(sleep_ns); }
-      IMP_FENCE();
-#pragma unroll
-      for (int a = 0; a < 4; a++)
-        if (need_global >> a & 1) v[a] = ldcg3(uvw, n[a]);
-    }
-#ifdef IMP_TRACE
-    long long tr0;
-    asm volatile("mov.u64 %0, %%clock64;" : "=l"(tr0) : "d"(v[0].x + v[1].x + v[2].x + v[3].x) : "memory");
-#endif
-    bool wrote;
-    if (CCD) {
-      int how = impulse_ccd_fast_v(n[4], q0, q1, q2, q3, v, K);
-      if (how == 2) {
-        // not certified: the reference arithmetic on global memory.  Every predecessor's global result must be there.
-        atomicAdd(&c[CNT_IMP_SLOW], 1);
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-          if (pr[a] >= 0) while (!(done[pr[a] >> 2] & 2)) { if (sleep_ns > 0) __nanosleep(sleep_ns); }
-        IMP_FENCE();
-        impulse_ccd_slow(n, xyz, uvw, delta, dt, mass);
-        IMP_FENCE();
-#pragma unroll
-        for (int a = 0; a < 4; a++) v[a] = ldcg3(uvw, n[a]);
-        how = 0;  // global memory is already up to date
-      }
-      wrote = how == 1;
-    } else {
-      bool certified;
-      wrote = impulse_prx_apply_fast_v(G, v, K, certified);
-      if (!certified) atomicAdd(&c[CNT_IMP_SLOW], 1);
-    }
-    // mailbox data, fence, tag, bit 0: the successor can go on
-#pragma unroll
-    for (int a = 0; a < 4; a++) { ring[myslot + a * 3 + 0] = v[a].x; ring[myslot + a * 3 + 1] = v[a].y; ring[myslot + a * 3 + 2] = v[a].z; }
-    IMP_FENCE();
-    tags[myslot + 12] = (long long)k;
-    done[k] = 1;
-#ifdef IMP_TRACE
-    if (s == 0) { g_imp_trace[k * 3 + 0] = tr0; g_imp_trace[k * 3 + 1] = clock64(); g_imp_trace[k * 3 + 2] = tr_ready; }
-#endif
-    // global memory and bit 1, off the chain's critical path
-    if (wrote) {
-#pragma unroll
-      for (int a = 0; a < 4; a++) st3(uvw, n[a], v[a]);
-    }
-    IMP_FENCE();
-    done[k] = 3;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Single-walker sweep (the default).  The dependency chain of a sweep holds 85-93 % of its elements, and in the
-// data-flow kernels every hop of that chain pays a hand-over between two threads: flag, fence, polls and a round of
-// loads that miss L1 -- about 1000 of the 1800 cycles of a proximity hop and of the 4200 cycles of a CCD hop (per-hop
-// trace, tools/build_variant.sh trace).  So the chain is not distributed at all: ONE thread (the walker) applies the
-// elements in the reference's own serial order, and the other 224 threads of the CTA are its helpers.  They run ahead
-// and leave everything that does not depend on the velocities -- indices, positions, closest-point weights, normal,
-// penetration depth, the early reciprocal -- in a ring in shared memory.  The walker keeps the velocities it touches
-// in a direct-mapped, write-through cache in shared memory (consecutive elements share vertices), so a hop consists of
-// shared-memory loads and the element's own arithmetic: no flag, no fence, no global load on the chain.  Results go
-// to global memory by plain stores (the cache is write-through), so the uncertified fallback (the reference
-// arithmetic on global memory) and the next kernel see them.  Bit-identical by construction: this IS the serial loop.
-enum { IMPW_RING = 256, IMPW_D = 16, IMPW_I = 8, IMPW_NV = 2048, IMPW_HELPER0 = 32 };
-__device__ __forceinline__ V3 impw_get(volatile int* ctag, volatile double* cval, const double* uvw, int v) {
-  const int idx = v & (IMPW_NV - 1);
-  if (ctag[idx] == v) return v3(cval[idx * 3 + 0], cval[idx * 3 + 1], cval[idx * 3 + 2]);
-  const V3 r = ld3(uvw, v);  // (an evicted value went to global memory by this thread's own store: program order)
-  ctag[idx] = v;
-  cval[idx * 3 + 0] = r.x; cval[idx * 3 + 1] = r.y; cval[idx * 3 + 2] = r.z;
-  return r;
-}
-__device__ __forceinline__ void impw_put(volatile int* ctag, volatile double* cval, double* uvw, int v, V3 a) {
-  const int idx = v & (IMPW_NV - 1);
-  ctag[idx] = v;
-  cval[idx * 3 + 0] = a.x; cval[idx * 3 + 1] = a.y; cval[idx * 3 + 2] = a.z;
-  st3(uvw, v, a);
-}
-// the reference arithmetic as a call: elements whose fast arithmetic could not be certified (rare) land here
-__device__ __noinline__ void impulse_ccd_slow_call(const int* n, const double* xyz, double* uvw, double delta, double dt, double mass) {
-  impulse_ccd_apply(n, ld3(xyz, n[0]), ld3(xyz, n[1]), ld3(xyz, n[2]), ld3(xyz, n[3]), uvw, delta, dt, mass);
-}
-template <int CCD>
-__global__ void __launch_bounds__(256) k_imp_walk(int np, long long cap_elem, const int* __restrict__ elems_all,
-                                                    const double* __restrict__ xyz_all, double* uvw_all, const ImpConst K,
-                                                    int* cnt) {
-  extern __shared__ __align__(16) unsigned char impw_sm[];
-  volatile double* ring_d = reinterpret_cast<volatile double*>(impw_sm);                     // [IMPW_RING][IMPW_D]
-  volatile double* cval = ring_d + IMPW_RING * IMPW_D;                                       // [IMPW_NV][3]
-  volatile int* ring_i = reinterpret_cast<volatile int*>(cval + IMPW_NV * 3);                // [IMPW_RING][IMPW_I]
-  volatile int* ready = ring_i + IMPW_RING * IMPW_I;                                         // [IMPW_RING]: element + 1
-  volatile int* ctag = ready + IMPW_RING;                                                    // [IMPW_NV]
-  volatile int* walked = ctag + IMPW_NV;                                                     // elements consumed by the walker
-  const double delta = K.delta, stiffness = K.stiffness, dt = K.dt, mass = K.mass;
-  const int s = blockIdx.x;
-  int* c = cnt + s * NCNT;
-  if (!c[CNT_ACTIVE]) return;
-  const int ne = c[CNT_ELEM];
-  if (ne == 0) return;
-  const int* elems = elems_all + (size_t)s * cap_elem * 5;
-  const double* xyz = xyz_all + (size_t)s * np * 3;
-  double* uvw = uvw_all + (size_t)s * np * 3;
-  for (int i = threadIdx.x; i < IMPW_RING; i += blockDim.x) ready[i] = 0;
-  for (int i = threadIdx.x; i < IMPW_NV; i += blockDim.x) ctag[i] = -1;
-  if (threadIdx.x == 0) *walked = 0;
-  __syncthreads();
-  if (threadIdx.x >= IMPW_HELPER0) {
-    // ---------------------------------------------------------------- helpers: velocity-independent part, in order
-    const int nh = blockDim.x - IMPW_HELPER0;
-    for (int k = threadIdx.x - IMPW_HELPER0; k < ne; k += nh) {
-      int n[5];
-#pragma unroll
-      for (int a = 0; a < 5; a++) n[a] = elems[(size_t)k * 5 + a];
-      PrxGeom G;
-      V3 q[4];
-      if (!CCD) {
-        impulse_prx_geom(n, xyz, delta, G);
-        impulse_prx_geom_more(G, stiffness, dt);
-      } else {
-#pragma unroll
-        for (int a = 0; a < 4; a++) q[a] = ld3(xyz, n[a]);
-      }
-      // the slot's previous element (IMPW_RING back) must have been consumed
-      while (*walked < k + 1 - IMPW_RING) __nanosleep(200);
-      volatile double* d = ring_d + (size_t)(k & (IMPW_RING - 1)) * IMPW_D;
-      volatile int* ii = ring_i + (size_t)(k & (IMPW_RING - 1)) * IMPW_I;
-#pragma unroll
-      for (int a = 0; a < 4; a++) ii[a] = n[a];
-      if (!CCD) {
-        ii[4] = (G.ok ? 1 : 0) | (G.fv ? 2 : 0);
-        if (G.ok) {
-          d[0] = G.wa; d[1] = G.wb; d[2] = G.wc; d[3] = G.norm.x; d[4] = G.norm.y; d[5] = G.norm.z;
-          d[6] = G.p_depth; d[7] = G.thr; d[8] = G.imp_el; d[9] = G.den; d[10] = G.yden;
-        }
-      } else {
-        ii[4] = n[4];
-#pragma unroll
-        for (int a = 0; a < 4; a++) { d[a * 3 + 0] = q[a].x; d[a * 3 + 1] = q[a].y; d[a * 3 + 2] = q[a].z; }
-      }
-      IMP_FENCE();
-      ready[k & (IMPW_RING - 1)] = k + 1;
-    }
-    return;
-  }
-  if (threadIdx.x != 0) return;
-  // -------------------------------------------------------------------- the walker
-  for (int k = 0; k < ne; k++) {
-    const int sl = k & (IMPW_RING - 1);
-    while (ready[sl] != k + 1) { }
-    IMP_FENCE();
-    volatile double* d = ring_d + (size_t)sl * IMPW_D;
-    volatile int* ii = ring_i + (size_t)sl * IMPW_I;
-    int n[5];
-#pragma unroll
-    for (int a = 0; a < 5; a++) n[a] = ii[a];
-    PrxGeom G;
-    V3 q[4];
-    if (!CCD) {
-      G.ok = (n[4] & 1) != 0; G.fv = (n[4] & 2) != 0;
-      G.wa = d[0]; G.wb = d[1]; G.wc = d[2]; G.norm = v3(d[3], d[4], d[5]);
-      G.p_depth = d[6]; G.thr = d[7]; G.imp_el = d[8]; G.den = d[9]; G.yden = d[10];
-    } else {
-#pragma unroll
-      for (int a = 0; a < 4; a++) q[a] = v3(d[a * 3 + 0], d[a * 3 + 1], d[a * 3 + 2]);
-    }
-    *walked = k + 1;  // the slot's contents are in registers: the helpers may reuse it
-    if (!CCD && !G.ok) continue;
-    V3 v[4];
-#pragma unroll
-    for (int a = 0; a < 4; a++) v[a] = impw_get(ctag, cval, uvw, n[a]);
-    bool wrote;
-    if (CCD) {
-      int how = impulse_ccd_fast_v(n[4], q[0], q[1], q[2], q[3], v, K);
-      if (how == 2) {
-        // not certified: the reference arithmetic on global memory (current: the cache is write-through), then the
-        // cache takes the results over
-        atomicAdd(&c[CNT_IMP_SLOW], 1);
-        impulse_ccd_slow_call(n, xyz, uvw, delta, dt, mass);
-#pragma unroll
-        for (int a = 0; a < 4; a++) {
-          const int idx = n[a] & (IMPW_NV - 1);
-          ctag[idx] = -1;  // re-read from global memory on the next use
-        }
-        how = 0;
-      }
-      wrote = how == 1;
-    } else {
-      bool certified;
-      wrote = impulse_prx_apply_fast_v(G, v, K, certified);
-      if (!certified) atomicAdd(&c[CNT_IMP_SLOW], 1);
-    }
-    if (wrote) {
-#pragma unroll
-      for (int a = 0; a < 4; a++) impw_put(ctag, cval, uvw, n[a], v[a]);
-    }
-  }
-}
-
 // smallest x with sqrt(x) >= c / largest x with sqrt(x) <= c (the host sqrt is the correctly rounded IEEE operation)
 static double sqrt_ge_threshold(double c) {
   double x = c * c;
@@ -889,67 +589,6 @@ int launch_impulse(Ctx* c, const double* xyz, double* uvw, double delta, double 
     const int smem = (ne_max + 127) / 128 * 128;
     CG_CUDA(cudaFuncSetAttribute(k_imp_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(smem, 48 * 1024)));
     const int imp_threads = c->imp_threads;
-    {
-      const ImpConst K0 = make_imp_const(c, delta, stiffness, dt, mass);
-      if (K0.fast && c->imp_walk) {
-        const int smem_w = IMPW_RING * IMPW_D * 8 + IMPW_NV * 3 * 8 + IMPW_RING * IMPW_I * 4 + IMPW_RING * 4 + IMPW_NV * 4 + 16;
-        if (ccd) {
-          CG_CUDA(cudaFuncSetAttribute(k_imp_walk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_w));
-          k_imp_walk<1><<<c->B, 256, smem_w, KS(c, "k_imp_flow")>>>(c->np, c->cap_elem, c->elems, xyz, uvw, K0, c->cnt);
-        } else {
-          CG_CUDA(cudaFuncSetAttribute(k_imp_walk<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_w));
-          k_imp_walk<0><<<c->B, 256, smem_w, KS(c, "k_imp_flow")>>>(c->np, c->cap_elem, c->elems, xyz, uvw, K0, c->cnt);
-        }
-        CG_LAUNCH_CHECK(c);
-        return CLOTHGPU_OK;
-      }
-      const int done_bytes = (ne_max + 127) / 128 * 128;
-      const int smem_mb = done_bytes + IMP_RING * IMP_SLOT * 8;
-      if (K0.fast && c->imp_mailbox && smem_mb <= 227 * 1024) {
-#ifdef IMP_TRACE
-        static long long* tr_dev2 = nullptr;
-        if (!tr_dev2) {
-          CG_CUDA(cudaMalloc((void**)&tr_dev2, sizeof(long long) * 3 * (1 << 20)));
-          CG_CUDA(cudaMemcpyToSymbol(g_imp_trace, &tr_dev2, sizeof(tr_dev2)));
-        }
-#endif
-        if (ccd) {
-          CG_CUDA(cudaFuncSetAttribute(k_imp_flow_mb<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_mb));
-          k_imp_flow_mb<1><<<c->B, imp_threads, smem_mb, KS(c, "k_imp_flow")>>>(c->np, c->cap_elem, c->elems, c->imp_pred, xyz, uvw, K0,
-                                                                       done_bytes, c->cnt);
-        } else {
-          CG_CUDA(cudaFuncSetAttribute(k_imp_flow_mb<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_mb));
-          k_imp_flow_mb<0><<<c->B, imp_threads, smem_mb, KS(c, "k_imp_flow")>>>(c->np, c->cap_elem, c->elems, c->imp_pred, xyz, uvw, K0,
-                                                                       done_bytes, c->cnt);
-        }
-        CG_LAUNCH_CHECK(c);
-#ifdef IMP_TRACE
-        {
-          const int ne = std::min(c->h_cnt[CNT_ELEM], 1 << 20);
-          std::vector<long long> tr((size_t)ne * 3);
-          std::vector<int> pred((size_t)ne * 4);
-          CG_CUDA(cudaStreamSynchronize(c->stream));
-          CG_CUDA(cudaMemcpy(tr.data(), tr_dev2, sizeof(long long) * 3 * ne, cudaMemcpyDeviceToHost));
-          CG_CUDA(cudaMemcpy(pred.data(), c->imp_pred, sizeof(int) * 4 * ne, cudaMemcpyDeviceToHost));
-          double comp = 0, hand = 0, late = 0;
-          long long nh = 0, nlate = 0, tmin = LLONG_MAX, tmax = 0;
-          for (int k = 0; k < ne; k++) {
-            comp += (double)(tr[k * 3 + 1] - tr[k * 3 + 0]);
-            long long last = -1;
-            for (int a = 0; a < 4; a++) if (pred[k * 4 + a] >= 0) last = std::max(last, tr[(size_t)(pred[k * 4 + a] >> 2) * 3 + 1]);
-            if (last >= 0) {
-              hand += (double)(tr[k * 3 + 0] - last); nh++;
-              if (tr[k * 3 + 2] > last) { nlate++; late += (double)(tr[k * 3 + 2] - last); }
-            }
-            tmin = std::min(tmin, tr[k * 3 + 0]); tmax = std::max(tmax, tr[k * 3 + 1]);
-          }
-          fprintf(stderr, "imptrace MAILBOX ccd=%d ne=%d span=%lld cyc  compute/elem=%.0f  handoff/elem=%.0f (n=%lld)  late starters %lld (mean lateness %.0f)\n", ccd, ne,
-                  ne ? tmax - tmin : 0, ne ? comp / ne : 0.0, nh ? hand / nh : 0.0, nh, nlate, nlate ? late / nlate : 0.0);
-        }
-#endif
-        return CLOTHGPU_OK;
-      }
-    }
 #ifdef IMP_TRACE
     static long long* tr_dev = nullptr;
     const int tr_cap = 1 << 20;
