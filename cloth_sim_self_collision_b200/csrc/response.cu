@@ -934,6 +934,13 @@ __global__ void k_cert_selftest(long long per_thread, unsigned long long seed, u
 
 }  // namespace cg
 
+extern "C" int clothgpu_selftest_sqrt_thresholds(double c, double* ge, double* le) {
+  if (!(c > 0) || !ge || !le) { cg::set_error("clothgpu_selftest_sqrt_thresholds: bad argument"); return CLOTHGPU_ERR_ARG; }
+  *ge = cg::sqrt_ge_threshold(c);
+  *le = cg::sqrt_le_threshold(c);
+  return CLOTHGPU_OK;
+}
+
 extern "C" int clothgpu_selftest_certified_math(int device, long long samples, unsigned long long seed, long long* out10) {
   using namespace cg;
   if (!out10 || samples <= 0) { set_error("clothgpu_selftest_certified_math: bad argument"); return CLOTHGPU_ERR_ARG; }

@@ -207,6 +207,10 @@ int clothgpu_selftest_triplan(int np, const int* crs_rowptr, const int* crs_coli
  * operations), for k = 0 quotient from a Newton reciprocal, 1 quotient from the correctly rounded reciprocal,
  * 2 reciprocal, 3 square root, 4 reciprocal of the root. */
 int clothgpu_selftest_certified_math(int device, long long samples, unsigned long long seed, long long* out10);
+/* The radicand thresholds the impulse chain compares squared lengths against (host code, needs no GPU):
+ * *ge = the smallest x with sqrt(x) >= c  (length(v) < c  <=>  v.v < *ge),
+ * *le = the largest  x with sqrt(x) <= c  (length(v) > c  <=>  v.v > *le). */
+int clothgpu_selftest_sqrt_thresholds(double c, double* ge, double* le);
 /* Instrumentation of the triangular-solve kernels: while on, the compute warp of every CTA accumulates cycle counters.
  * out: NULL, or 2 x cap_ctas x 8 values of the last forward / backward launch {start ns, end ns, cycles waiting for
  * matrix chunks, cycles waiting for imported values, compute cycles, signalling cycles, micro-steps, strip};

@@ -147,3 +147,20 @@ def test_trisolve_plan_degenerate_patterns(lib):
         rp[i + 1] = len(ci)
     for force in (0, 1, 3):
         _selftest(lib, (n, rp, np.array(ci, dtype=np.int32)), force)
+
+
+def test_sqrt_comparison_thresholds(lib):
+    """The impulse chain compares squared lengths against host-computed thresholds instead of taking square roots
+    (csrc/imp_fast.cuh): `sqrt(x) < c` must be exactly `x < ge` and `sqrt(x) > c` exactly `x > le`, for the constants the
+    reference uses (1e-10, bvh_aabb.cpp:350) and for typical clearances.  IEEE sqrt is correctly rounded and monotone,
+    so checking the two doubles on either side of each threshold proves the equivalence."""
+    lib.clothgpu_selftest_sqrt_thresholds.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    rng = np.random.default_rng(5)
+    cs = [1.0e-10, 0.01, 0.02, 0.05, 1.0, 3.0] + list(10.0 ** rng.uniform(-12, 3, 200))
+    for c in cs:
+        ge, le = C.c_double(), C.c_double()
+        assert lib.clothgpu_selftest_sqrt_thresholds(c, C.byref(ge), C.byref(le)) == 0
+        ge, le = ge.value, le.value
+        assert np.sqrt(ge) >= c and np.sqrt(np.nextafter(ge, -np.inf)) < c, c
+        assert np.sqrt(le) <= c and np.sqrt(np.nextafter(le, np.inf)) > c, c
+    assert lib.clothgpu_selftest_sqrt_thresholds(0.0, C.byref(C.c_double()), C.byref(C.c_double())) != 0
