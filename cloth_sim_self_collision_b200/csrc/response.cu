@@ -710,20 +710,24 @@ __global__ void k_riz_keys(int np, const int* __restrict__ label, unsigned* __re
 // list, ascending vertex id inside the segment = std::set<int> order).
 // Reference quirk (:327-329): the "inertia tensor" diagonal uses v.v (velocity) where q.q (position) is meant.
 // one rigid impact zone: the members vals[i .. e) in ascending vertex id (ApplyRigidImpactZone, self_collision_cloth.cpp:298-348)
-__device__ __forceinline__ void riz_zone(int i, int e, const int* __restrict__ vals, const double* __restrict__ xyz,
-                                         const double* __restrict__ uvw0, double* __restrict__ uvw) {
+// STAGED: xyz / uvw0 are per-member copies in shared memory, indexed by the member's position in vals (a serial loop
+// over global memory pays one L2 round trip per member and pass)
+template <bool STAGED>
+__device__ __forceinline__ void riz_zone(int i, int e, const int* __restrict__ vals, const double* xyz,
+                                         const double* uvw0, double* __restrict__ uvw) {
+#define RZ_LD(A_, J_) ld3((A_), STAGED ? (J_) : vals[(J_)])
   V3 gc = v3(0, 0, 0), av = v3(0, 0, 0);
   for (int j = i; j < e; j++) {
-    gc = gc + ld3(xyz, vals[j]);
-    av = av + ld3(uvw0, vals[j]);
+    gc = gc + RZ_LD(xyz, j);
+    av = av + RZ_LD(uvw0, j);
   }
   gc = div_guarded(gc, (double)(e - i));
   av = div_guarded(av, (double)(e - i));
   V3 L = v3(0, 0, 0);
   double I[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int j = i; j < e; j++) {
-    const V3 p = ld3(xyz, vals[j]);
-    const V3 v = ld3(uvw0, vals[j]);
+    const V3 p = RZ_LD(xyz, j);
+    const V3 v = RZ_LD(uvw0, j);
     L = L + cross(p - gc, v - av);
     const V3 q = p - gc;
     const double vv = dot(v, v);
@@ -752,11 +756,12 @@ __device__ __forceinline__ void riz_zone(int i, int e, const int* __restrict__ v
   omg.z = Iinv[6] * L.x + Iinv[7] * L.y + Iinv[8] * L.z;
   for (int j = i; j < e; j++) {
     const int v = vals[j];
-    const V3 rot = -cross(ld3(xyz, v) - gc, omg);
+    const V3 rot = -cross(RZ_LD(xyz, j) - gc, omg);
     uvw[v * 3 + 0] = av.x + rot.x;
     uvw[v * 3 + 1] = av.y + rot.y;
     uvw[v * 3 + 2] = av.z + rot.z;
   }
+#undef RZ_LD
 }
 
 __global__ void k_riz_apply(int np, const unsigned* __restrict__ keys, const int* __restrict__ vals,
@@ -770,7 +775,7 @@ __global__ void k_riz_apply(int np, const unsigned* __restrict__ keys, const int
   if (i > 0 && keys[i - 1] == key) return;
   int e = i;
   while (e < np && keys[e] == key) e++;
-  riz_zone(i, e, vals, xyz, uvw0, uvw);
+  riz_zone<false>(i, e, vals, xyz, uvw0, uvw);
 }
 __global__ void k_zero_cnt(int* cnt, int slot) { cnt[blockIdx.x * NCNT + slot] = 0; }
 
@@ -778,11 +783,12 @@ __global__ void k_zero_cnt(int* cnt, int slot) { cnt[blockIdx.x * NCNT + slot] =
 // radix sort of all np vertices and the zone kernel: the members (a few hundred vertices, typically) are collected,
 // sorted by (zone label, vertex id) with a bitonic network -- in shared memory up to RIZ_SMEM members, in a global
 // scratch array beyond -- and every zone is then reduced by one thread exactly as in k_riz_apply (riz_zone).
-enum { RIZ_T = 1024, RIZ_SMEM = 4096 };
+enum { RIZ_T = 1024, RIZ_SMEM = 4096, RIZ_STAGE = 1024 };
 __global__ void __launch_bounds__(RIZ_T) k_riz_apply_all(int np, const int* __restrict__ label_all,
                                                           const double* __restrict__ xyz_all, const double* __restrict__ uvw0_all,
                                                           double* __restrict__ uvw_all, unsigned long long* __restrict__ gkeys_all,
                                                           int* __restrict__ gvals_all, int* cnt) {
+  extern __shared__ __align__(16) double riz_stage[];  // [RIZ_STAGE][3] positions, then [RIZ_STAGE][3] velocities
   __shared__ unsigned long long skeys[RIZ_SMEM];
   __shared__ int svals_n, s_total;
   const int s = blockIdx.x;
@@ -827,12 +833,22 @@ __global__ void __launch_bounds__(RIZ_T) k_riz_apply_all(int np, const int* __re
   int* vals = gvals_all + (size_t)s * np;
   for (int i = threadIdx.x; i < n; i += blockDim.x) vals[i] = (int)(keys[i] & 0xffffffffULL);
   __syncthreads();
+  const bool staged = n <= RIZ_STAGE;
+  if (staged) {  // the members' positions and start velocities, in member order, for the serial zone loops
+    for (int t = threadIdx.x; t < n * 3; t += blockDim.x) {
+      const int i = t / 3, k = t - i * 3;
+      riz_stage[t] = xyz[(size_t)vals[i] * 3 + k];
+      riz_stage[RIZ_STAGE * 3 + t] = uvw0[(size_t)vals[i] * 3 + k];
+    }
+    __syncthreads();
+  }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const unsigned zl = (unsigned)(keys[i] >> 32);
     if (i > 0 && (unsigned)(keys[i - 1] >> 32) == zl) continue;
     int e = i;
     while (e < n && (unsigned)(keys[e] >> 32) == zl) e++;
-    riz_zone(i, e, vals, xyz, uvw0, uvw);
+    if (staged) riz_zone<true>(i, e, vals, riz_stage, riz_stage + RIZ_STAGE * 3, uvw);
+    else riz_zone<false>(i, e, vals, xyz, uvw0, uvw);
   }
 }
 
@@ -858,7 +874,9 @@ int launch_riz_apply(Ctx* c, const double* xyz, double* uvw) {
   if (c->riz_fused) {
     // scratch per scene: 2 np keys (a power of two >= the member count) + np vertex ids
     CG_CHECK(ensure_sort_capacity(c, 2LL * c->np * c->B));
-    k_riz_apply_all<<<c->B, RIZ_T, 0, KS(c, "k_riz_apply")>>>(c->np, c->zone_label, xyz, c->uvw0, uvw, c->sort_keys, c->sort_vals, c->cnt);
+    const int smem = RIZ_STAGE * 6 * (int)sizeof(double);
+    CG_CUDA(cudaFuncSetAttribute(k_riz_apply_all, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_riz_apply_all<<<c->B, RIZ_T, smem, KS(c, "k_riz_apply")>>>(c->np, c->zone_label, xyz, c->uvw0, uvw, c->sort_keys, c->sort_vals, c->cnt);
     CG_LAUNCH_CHECK(c);
     return CLOTHGPU_OK;
   }
