@@ -357,20 +357,33 @@ __device__ __forceinline__ int impulse_ccd_fast(const int* n, V3 p0, V3 p1, V3 p
   return how;
 }
 
-// (vertex, element*4+corner) pairs in element order
-__global__ void k_imp_pairs(int ne, const int* __restrict__ elems, unsigned* __restrict__ keys, int* __restrict__ vals) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ne * 4) return;
-  const int k = i >> 2, a = i & 3;
-  keys[i] = (unsigned)elems[k * 5 + a];
-  vals[i] = i;
+// (vertex, element*4+corner) pairs in element order; all scenes in one launch (scene = blockIdx.y, stride cap4)
+__global__ void k_imp_pairs(long long cap_elem, long long cap4, const int* __restrict__ elems_all, unsigned* __restrict__ keys_all,
+                            int* __restrict__ vals_all, const int* __restrict__ cnt) {
+  const int s = blockIdx.y;
+  const int* c = cnt + s * NCNT;
+  if (!c[CNT_ACTIVE]) return;
+  const int n4 = c[CNT_ELEM] * 4;
+  const int* elems = elems_all + (size_t)s * cap_elem * 5;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const int k = i >> 2, a = i & 3;
+    keys_all[(size_t)s * cap4 + i] = (unsigned)elems[k * 5 + a];
+    vals_all[(size_t)s * cap4 + i] = i;
+  }
 }
 // predecessor of (element, corner): the previous element touching the same vertex and the corner the vertex has
 // there, as element * 4 + corner, or -1
-__global__ void k_imp_pred(int n4, const unsigned* __restrict__ keys, const int* __restrict__ vals, int* __restrict__ pred) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n4) return;
-  pred[vals[i]] = (i > 0 && keys[i - 1] == keys[i]) ? vals[i - 1] : -1;
+__global__ void k_imp_pred(long long cap_elem, long long cap4, const unsigned* __restrict__ keys_all,
+                           const int* __restrict__ vals_all, int* __restrict__ pred_all, const int* __restrict__ cnt) {
+  const int s = blockIdx.y;
+  const int* c = cnt + s * NCNT;
+  if (!c[CNT_ACTIVE]) return;
+  const int n4 = c[CNT_ELEM] * 4;
+  const unsigned* keys = keys_all + (size_t)s * cap4;
+  const int* vals = vals_all + (size_t)s * cap4;
+  int* pred = pred_all + (size_t)s * cap_elem * 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
+    pred[vals[i]] = (i > 0 && keys[i - 1] == keys[i]) ? vals[i - 1] : -1;
 }
 
 // one CTA per scene: level the dependency DAG, bucket the elements by level, apply level after level
@@ -558,27 +571,37 @@ static ImpConst make_imp_const(const Ctx* c, double delta, double stiffness, dou
 }
 
 int launch_impulse(Ctx* c, const double* xyz, double* uvw, double delta, double stiffness, double dt, double mass, int ccd) {
-  // element counts are on the host already (the reference's loop control needs them)
-  for (int s = 0; s < c->B; s++) {
-    if (!c->h_cnt[s * NCNT + CNT_ACTIVE]) continue;
-    const int ne = c->h_cnt[s * NCNT + CNT_ELEM];
-    if (ne == 0) continue;
-    const int n4 = ne * 4;
-    CG_CHECK(ensure_sort_capacity(c, n4));
-    unsigned* keys = (unsigned*)c->sort_keys;
-    unsigned* keys2 = (unsigned*)c->sort_keys2;
-    const int* elems = c->elems + (size_t)s * c->cap_elem * 5;
-    int end_bit = 1;
-    while ((1LL << end_bit) < c->np) end_bit++;
-    size_t tb = 0;
-    CG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys2, c->sort_vals, c->sort_vals2, n4, 0, end_bit, c->stream));
-    CG_CHECK(ensure_scratch(c, tb));
-    k_imp_pairs<<<div_up(n4, 256), 256, 0, KS(c, "k_imp_pairs")>>>(ne, elems, keys, c->sort_vals);
-    CG_LAUNCH_CHECK(c);
-    CG_CUDA(cub::DeviceRadixSort::SortPairs(c->scratch, tb, keys, keys2, c->sort_vals, c->sort_vals2, n4, 0, end_bit, c->stream));
-    c->launches += 3;
-    k_imp_pred<<<div_up(n4, 256), 256, 0, KS(c, "k_imp_pred")>>>(n4, keys2, c->sort_vals2, c->imp_pred + (size_t)s * c->cap_elem * 4);
-    CG_LAUNCH_CHECK(c);
+  // element counts are on the host already (the reference's loop control needs them).  Pairs and predecessors of all
+  // scenes in one launch each; the library radix sort in between runs scene by scene on the scene's slice.
+  {
+    int ne_all = 0;
+    for (int s = 0; s < c->B; s++)
+      if (c->h_cnt[s * NCNT + CNT_ACTIVE]) ne_all = std::max(ne_all, c->h_cnt[s * NCNT + CNT_ELEM]);
+    if (ne_all > 0) {
+      const long long cap4 = (long long)ne_all * 4;
+      CG_CHECK(ensure_sort_capacity(c, cap4 * c->B));
+      unsigned* keys = (unsigned*)c->sort_keys;
+      unsigned* keys2 = (unsigned*)c->sort_keys2;
+      int end_bit = 1;
+      while ((1LL << end_bit) < c->np) end_bit++;
+      size_t tb = 0;
+      CG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys2, c->sort_vals, c->sort_vals2, (int)cap4, 0, end_bit, c->stream));
+      CG_CHECK(ensure_scratch(c, tb));
+      dim3 g(std::min(div_up((int)cap4, 256), 148 * 4), c->B);
+      k_imp_pairs<<<g, 256, 0, KS(c, "k_imp_pairs")>>>(c->cap_elem, cap4, c->elems, keys, c->sort_vals, c->cnt);
+      CG_LAUNCH_CHECK(c);
+      for (int s = 0; s < c->B; s++) {
+        if (!c->h_cnt[s * NCNT + CNT_ACTIVE]) continue;
+        const int n4 = c->h_cnt[s * NCNT + CNT_ELEM] * 4;
+        if (n4 == 0) continue;
+        size_t tbs = tb;
+        CG_CUDA(cub::DeviceRadixSort::SortPairs(c->scratch, tbs, keys + s * cap4, keys2 + s * cap4, c->sort_vals + s * cap4,
+                                                c->sort_vals2 + s * cap4, n4, 0, end_bit, c->stream));
+        c->launches += 3;
+      }
+      k_imp_pred<<<g, 256, 0, KS(c, "k_imp_pred")>>>(c->cap_elem, cap4, keys2, c->sort_vals2, c->imp_pred, c->cnt);
+      CG_LAUNCH_CHECK(c);
+    }
   }
   int ne_max = 0;
   for (int s = 0; s < c->B; s++)
