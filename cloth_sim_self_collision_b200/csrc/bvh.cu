@@ -189,6 +189,9 @@ __global__ void k_trav_reset(int* cnt) {
 }
 
 // the self() calls: every internal node starts one pair recursion on its two children
+// SLIM: frontier / leaf entries are just the two node ids (8 bytes instead of 32); the depth-first rank of a leaf
+// pair is then rebuilt from the root paths for narrow-phase hits (pair_rank), as for the leaf query
+template <bool SLIM>
 __global__ void k_trav_init(int ninternal, const int* __restrict__ internal_list, const int* __restrict__ nodes,
                             const uint32_t* __restrict__ pre, PairEnt* front, long long cap, int* cnt,
                             int nnode, const int* __restrict__ ndirty) {
@@ -202,6 +205,10 @@ __global__ void k_trav_init(int ninternal, const int* __restrict__ internal_list
   e.i0 = nodes[n * 3 + 1];
   e.i1 = nodes[n * 3 + 2];
   if (ndirty && !ndirty[(size_t)s * nnode + n]) e.i0 = -1;  // nothing below this node changed: a dead entry
+  if (SLIM) {
+    reinterpret_cast<int2*>(front)[(size_t)s * cap + k] = make_int2(e.i0, e.i1);
+    return;
+  }
   e.pre = pre[n];
   e.depth = 0;
   e.path_hi = 0;
@@ -233,6 +240,7 @@ __device__ __forceinline__ void path_push(PairEnt& e, unsigned code) {
 
 // one level of the pair recursion (bvh_aabb.cpp:441-475 / 797-833): prune on CAABB3D::IsIntersect, descend in the
 // child order (0,0),(1,0),(0,1),(1,1), collect leaf pairs
+template <bool SLIM>
 __device__ __forceinline__ void trav_step_body(int d, int nnode, const int* __restrict__ nodes,
                                                const double* __restrict__ boxes, const PairEnt* __restrict__ fin,
                                                PairEnt* __restrict__ fout, long long cap_front,
@@ -263,9 +271,14 @@ __device__ __forceinline__ void trav_step_body(int d, int nnode, const int* __re
     unsigned okmask = 0;           // bit (ib * 2 + ia): child pair (a[ia], b[ib]) survives
     bool self_leaf = false;        // a seed whose two sides are leaves
     if (idx < nin) {
-      e = in[idx];
+      if (SLIM) {
+        const int2 p = reinterpret_cast<const int2*>(fin)[(size_t)s * cap_front + idx];
+        e.i0 = p.x; e.i1 = p.y; e.depth = (uint32_t)d; e.pre = 0; e.path_hi = 0; e.path_lo = 0;
+      } else {
+        e = in[idx];
+      }
       bool live = e.i0 >= 0;
-      if (live && e.depth == 0) {
+      if (live && e.depth == 0) {  // (the seeds are exactly the entries of level 0)
         live = (!nd || nd[e.i0] || nd[e.i1]) && box_intersect(ld_box(bx, e.i0), ld_box(bx, e.i1));
       }
       if (live) {
@@ -313,6 +326,19 @@ __device__ __forceinline__ void trav_step_body(int d, int nnode, const int* __re
     int lpos = warp_reserve(nleaf, &c[CNT_LEAF]);
     if (nfront > 0 && (long long)fpos + nfront > cap_front) { atomicOr(&c[CNT_OVERFLOW], 1); okmask &= leafmask; }
     if (nleaf > 0 && (long long)lpos + nleaf > cap_leaf) { atomicOr(&c[CNT_OVERFLOW], 2); okmask &= ~leafmask; self_leaf = false; }
+    if (SLIM) {
+      int2* lf2 = reinterpret_cast<int2*>(leaf) + (size_t)s * cap_leaf;
+      int2* out2 = reinterpret_cast<int2*>(fout) + (size_t)s * cap_front;
+      if (self_leaf) lf2[lpos++] = make_int2(e.i0, e.i1);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (!(okmask >> k & 1)) continue;
+        const int2 ch = make_int2(a[k & 1], b[k >> 1]);
+        if (leafmask >> k & 1) lf2[lpos++] = ch;
+        else out2[fpos++] = ch;
+      }
+      continue;
+    }
     if (self_leaf) lf[lpos++] = e;
     if (okmask) {
       PairEnt ch = e;
@@ -336,12 +362,13 @@ __device__ __forceinline__ void trav_step_body(int d, int nnode, const int* __re
   }
 }
 
+template <bool SLIM>
 __global__ void __launch_bounds__(256) k_trav_step(int d, int nnode, const int* __restrict__ nodes,
                                                     const double* __restrict__ boxes, const PairEnt* __restrict__ fin,
                                                     PairEnt* __restrict__ fout, long long cap_front,
                                                     PairEnt* __restrict__ leaf, long long cap_leaf, int* cnt,
                                                     const int* __restrict__ ndirty) {
-  trav_step_body(d, nnode, nodes, boxes, fin, fout, cap_front, leaf, cap_leaf, cnt, ndirty);
+  trav_step_body<SLIM>(d, nnode, nodes, boxes, fin, fout, cap_front, leaf, cap_leaf, cnt, ndirty);
 }
 
 // All levels of the pair recursion in ONE cooperative launch (co-residency guaranteed by the launch API): the CTAs
@@ -356,8 +383,8 @@ __global__ void __launch_bounds__(256) k_trav_all(int ndepth, int nnode, const i
   for (int d = 0; d < ndepth; d++) {
     // level d is complete (barrier below / previous kernel): an empty frontier ends the recursion for every CTA
     if (((volatile int*)c)[CNT_FRONT + d] == 0) break;
-    trav_step_body(d, nnode, nodes, boxes, (d & 1) ? frontB : frontA, (d & 1) ? frontA : frontB, cap_front, leaf,
-                   cap_leaf, cnt, ndirty);
+    trav_step_body<false>(d, nnode, nodes, boxes, (d & 1) ? frontB : frontA, (d & 1) ? frontA : frontB, cap_front, leaf,
+                          cap_leaf, cnt, ndirty);
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
@@ -383,7 +410,7 @@ __global__ void __launch_bounds__(QRY_WARPS * 32) k_query(int nnode, const int* 
                                                            const unsigned long long* __restrict__ npath,
                                                            const int* __restrict__ ndirty,
                                                            const int* __restrict__ dirty_list, PairEnt* __restrict__ leaf,
-                                                           long long cap_leaf, int* cnt, int qcap) {
+                                                           long long cap_leaf, int* cnt, int qcap, int slim) {
   // one warp per dirty leaf, breadth first: the lanes test the children of up to 32 frontier nodes at once, so a query
   // costs one round of dependent loads per tree level instead of one per visited node
   __shared__ int q[QRY_WARPS][2][QRY_CAP];
@@ -437,7 +464,8 @@ __global__ void __launch_bounds__(QRY_WARPS * 32) k_query(int nnode, const int* 
                 e.depth = 0;
                 e.path_hi = 0;
                 e.path_lo = 0;
-                lf[pos] = e;
+                if (slim) reinterpret_cast<int2*>(leaf)[(size_t)s * cap_leaf + pos] = make_int2(e.i0, e.i1);
+                else lf[pos] = e;
               }
             }
           }
@@ -581,7 +609,8 @@ __global__ void __launch_bounds__(CULL_T, CULL_B) k_cull(int ccd, int nnode, int
                                                const double* __restrict__ boxes,
                                                const double* __restrict__ xyz, const double* __restrict__ uvw,
                                                double dt, double delta, const PairEnt* __restrict__ leaf,
-                                               long long cap_leaf, int4* __restrict__ cand, long long cap_cand, int* cnt) {
+                                               long long cap_leaf, int4* __restrict__ cand, long long cap_cand, int* cnt,
+                                               int slim) {
   const int s = blockIdx.y;
   int* c = cnt + s * NCNT;
   if (!c[CNT_ACTIVE]) return;
@@ -597,9 +626,11 @@ __global__ void __launch_bounds__(CULL_T, CULL_B) k_cull(int ccd, int nnode, int
     unsigned mask = 0;
     int ei0 = 0, ei1 = 0;
     if (idx < nleaf) {
-      const PairEnt e = lf[idx];
-      ei0 = e.i0; ei1 = e.i1;
-      const int4 ta = node_tri[e.i0], tb = node_tri[e.i1];  // {v0, v1, v2, triangle} of the two leaves
+      int2 e;
+      if (slim) e = reinterpret_cast<const int2*>(leaf)[(size_t)s * cap_leaf + idx];
+      else e = make_int2(lf[idx].i0, lf[idx].i1);
+      ei0 = e.x; ei1 = e.y;
+      const int4 ta = node_tri[e.x], tb = node_tri[e.y];  // {v0, v1, v2, triangle} of the two leaves
       const int it = ta.w, jt = tb.w;
       const int in[3] = {ta.x, ta.y, ta.z}, jn[3] = {tb.x, tb.y, tb.z};
       V3 p[3], q[3], pe[3], qe[3];
@@ -612,7 +643,7 @@ __global__ void __launch_bounds__(CULL_T, CULL_B) k_cull(int ccd, int nnode, int
           pe[a] = v3(x[i * 3] + dt * v[i * 3], x[i * 3 + 1] + dt * v[i * 3 + 1], x[i * 3 + 2] + dt * v[i * 3 + 2]);
           qe[a] = v3(x[j * 3] + dt * v[j * 3], x[j * 3 + 1] + dt * v[j * 3 + 1], x[j * 3 + 2] + dt * v[j * 3 + 2]);
         }
-        const Box b0 = ld_box(bx, e.i0), b1 = ld_box(bx, e.i1);
+        const Box b0 = ld_box(bx, e.x), b1 = ld_box(bx, e.y);
 #pragma unroll
         for (int a = 0; a < 3; a++) {
           if (maybe_fv_ccd(in[0], in[1], in[2], jn[a], p[0], p[1], p[2], q[a], pe[0], pe[1], pe[2], qe[a], b0)) mask |= 1u << a;
@@ -671,7 +702,7 @@ __global__ void __launch_bounds__(128, NARROW_B) k_narrow(int ccd, int nnode, in
                                                  RawElem* __restrict__ raw, long long cap_raw, int* cnt,
                                                  const int* __restrict__ nodes, const uint32_t* __restrict__ pre,
                                                  const unsigned long long* __restrict__ npath,
-                                                 const int* __restrict__ ndepth, int rank_check) {
+                                                 const int* __restrict__ ndepth, int rank_check, int slim) {
   const int s = blockIdx.y;
   int* c = cnt + s * NCNT;
   if (!c[CNT_ACTIVE]) return;
@@ -698,7 +729,9 @@ __global__ void __launch_bounds__(128, NARROW_B) k_narrow(int ccd, int nnode, in
       int key[4];
       if (slot < 6) canon_fv(S.n[0], S.n[1], S.n[2], S.n[3], key);
       else canon_ee(S.n[0], S.n[1], S.n[2], S.n[3], key);
-      PairEnt e = lf[cs.w];  // the pair's DFS rank is only needed for the (rare) hits
+      PairEnt e;  // the pair's DFS rank is only needed for the (rare) hits
+      if (slim) { e.i0 = cs.x; e.i1 = cs.y; e.pre = 0xffffffffu; }
+      else e = lf[cs.w];
       if (e.pre == 0xffffffffu) {
         pair_rank(e.i0, e.i1, nodes, pre, npath, ndepth, e);
       } else if (rank_check) {
@@ -940,22 +973,29 @@ static int traverse_and_test(Ctx* c, const double* xyz, const double* uvw, doubl
     CG_LAUNCH_CHECK(c);
   }
   const bool query = incremental && c->query_trav && c->inc_refit;  // (the incremental refit lists the dirty leaves)
+  const bool coop = !query && incremental && c->trav_coop > 0 && c->B <= c->trav_coop && !c->ktiming;
+  // 8-byte frontier / leaf entries wherever the per-level kernels or the leaf query produce them (the cooperative
+  // kernel and the rank cross-check keep the 32-byte entries that carry the depth-first rank)
+  const bool slim = c->slim_frontier && !c->rank_check && !coop;
+  c->leaf_slim = slim;
   if (query) {
     dim3 g(std::max(8, 148 * 8 / c->B), c->B);
     k_query<<<g, QRY_WARPS * 32, 0, KS(c, "k_query")>>>(c->nnode, c->nodes, c->boxes, c->npath, nd, c->dirty_list, c->leaf, c->cap_leaf,
-                                                c->cnt, std::min((int)QRY_CAP, c->query_cap));
+                                                c->cnt, std::min((int)QRY_CAP, c->query_cap), slim ? 1 : 0);
     CG_LAUNCH_CHECK(c);
   } else {
     dim3 g(div_up(c->ninternal, 256), c->B);
-    k_trav_init<<<g, 256, 0, KS(c, "k_trav_init")>>>(c->ninternal, c->internal_list, c->nodes, c->pre, c->frontA, c->cap_front, c->cnt,
-                                             c->nnode, nd);
+    if (slim) k_trav_init<true><<<g, 256, 0, KS(c, "k_trav_init")>>>(c->ninternal, c->internal_list, c->nodes, c->pre, c->frontA, c->cap_front, c->cnt,
+                                                             c->nnode, nd);
+    else k_trav_init<false><<<g, 256, 0, KS(c, "k_trav_init")>>>(c->ninternal, c->internal_list, c->nodes, c->pre, c->frontA, c->cap_front, c->cnt,
+                                                          c->nnode, nd);
     CG_LAUNCH_CHECK(c);
   }
   // every descent moves at least one side of the pair one level down: bvh_height + 1 steps reach all leaf pairs
   bool fused = query;
   // (used for the incremental passes only: their frontiers are tiny and nothing else runs beside them, while the
   // full passes overlap the solve on the second stream, where a cooperative launch would have to wait for room)
-  if (!query && incremental && c->trav_coop > 0 && c->B <= c->trav_coop && !c->ktiming) {
+  if (coop) {
     int ndepth = c->bvh_height + 1, nnode = c->nnode;
     long long capf = c->cap_front, capl = c->cap_leaf;
     const int* nodes = c->nodes; const double* boxes = c->boxes; PairEnt* fa = c->frontA; PairEnt* fb = c->frontB;
@@ -975,18 +1015,19 @@ static int traverse_and_test(Ctx* c, const double* xyz, const double* uvw, doubl
     dim3 g(incremental ? 74 : 148 * 4, c->B);  // incremental frontiers are small: a small grid launches faster
     PairEnt* fin = (d & 1) ? c->frontB : c->frontA;
     PairEnt* fout = (d & 1) ? c->frontA : c->frontB;
-    k_trav_step<<<g, 256, 0, KS(c, "k_trav_step")>>>(d, c->nnode, c->nodes, c->boxes, fin, fout, c->cap_front, c->leaf, c->cap_leaf, c->cnt, nd);
+    if (slim) k_trav_step<true><<<g, 256, 0, KS(c, "k_trav_step")>>>(d, c->nnode, c->nodes, c->boxes, fin, fout, c->cap_front, c->leaf, c->cap_leaf, c->cnt, nd);
+    else k_trav_step<false><<<g, 256, 0, KS(c, "k_trav_step")>>>(d, c->nnode, c->nodes, c->boxes, fin, fout, c->cap_front, c->leaf, c->cap_leaf, c->cnt, nd);
     CG_LAUNCH_CHECK(c);
   }
   {
     dim3 g(148 * 8 * (256 / CULL_T), c->B);
     k_cull<<<g, CULL_T, 0, KS(c, "k_cull")>>>(ccd, c->nnode, c->np, (const int4*)c->node_tri, c->boxes, xyz, uvw, dt, delta, c->leaf,
-                                   c->cap_leaf, c->cand, c->cap_leaf * 2, c->cnt);
+                                   c->cap_leaf, c->cand, c->cap_leaf * 2, c->cnt, slim ? 1 : 0);
     CG_LAUNCH_CHECK(c);
     dim3 g2(148 * 4, c->B);
     k_narrow<<<g2, 128, 0, KS(c, "k_narrow")>>>(ccd, c->nnode, c->np, (const int4*)c->node_tri, c->boxes, xyz, uvw, dt, delta, c->leaf,
                                         c->cap_leaf, c->cand, c->cap_leaf * 2, c->raw, c->cap_raw, c->cnt, c->nodes, c->pre, c->npath,
-                                        c->ndepth, c->rank_check ? 1 : 0);
+                                        c->ndepth, c->rank_check ? 1 : 0, slim ? 1 : 0);
     CG_LAUNCH_CHECK(c);
   }
   return CLOTHGPU_OK;

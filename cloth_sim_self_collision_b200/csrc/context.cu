@@ -456,6 +456,8 @@ static int create_impl(Ctx* c, int nscene, int np, int ntri, int nquad, const in
     {
       const char* e1 = getenv("CLOTHGPU_INC_REFIT");
       c->inc_refit = !(e1 && atoi(e1) == 0);
+      const char* e7 = getenv("CLOTHGPU_SLIM_FRONTIER");
+      c->slim_frontier = !(e7 && atoi(e7) == 0);
       const char* e6 = getenv("CLOTHGPU_RIZ_FUSED");
       c->riz_fused = !(e6 && atoi(e6) == 0);
       const char* e5 = getenv("CLOTHGPU_RANK_CHECK");
@@ -638,6 +640,12 @@ int clothgpu_read(clothgpu_ctx* c, int buf, int scene, void* host, long long cou
   if (!bi.ptr) { set_error("buffer not allocated (context created without a BVH?)"); return CLOTHGPU_ERR_STATE; }
   if (buf == CLOTHGPU_BUF_LEAF_PAIRS) {  // strip the traversal bookkeeping: keep the two node ids per entry
     const long long n = count / 2;
+    if (c->leaf_slim) {  // the last traversal wrote 8-byte pairs, scene stride cap_leaf pairs
+      const int2* src = reinterpret_cast<const int2*>(c->leaf) + (long long)scene * c->cap_leaf;
+      CG_CUDA(cudaMemcpyAsync(host, src, (size_t)n * sizeof(int2), cudaMemcpyDeviceToHost, c->stream));
+      CG_CUDA(cudaStreamSynchronize(c->stream));
+      return CLOTHGPU_OK;
+    }
     std::vector<PairEnt> tmp((size_t)n);
     CG_CUDA(cudaMemcpyAsync(tmp.data(), bi.ptr, (size_t)n * sizeof(PairEnt), cudaMemcpyDeviceToHost, c->stream));
     CG_CUDA(cudaStreamSynchronize(c->stream));

@@ -187,6 +187,8 @@ struct Ctx {
   unsigned long long* npath = nullptr;  // per node: child choices from the root, left aligned (bit 63 - d = choice at depth d)
   int* ndepth = nullptr;                // per node: depth
   bool inc_refit = true;                // CLOTHGPU_INC_REFIT=0: incremental passes refit the whole tree
+  bool slim_frontier = true;            // CLOTHGPU_SLIM_FRONTIER=0: frontier / leaf entries always carry the depth-first rank (32 bytes)
+  bool leaf_slim = false;               // layout of the leaf list of the last traversal (8-byte pairs or 32-byte entries)
   bool riz_fused = true;                // CLOTHGPU_RIZ_FUSED=0: impact zones applied scene by scene through a library sort of all vertices
   bool rank_check = false;              // CLOTHGPU_RANK_CHECK=1: k_narrow cross-checks pair_rank against the ranks the frontier traversal carries
   int query_cap = 256;                  // CLOTHGPU_QUERY_CAP: per-leaf frontier capacity of k_query (tests force the overflow path)

@@ -575,13 +575,14 @@ def test_measurement_switches_do_not_change_results(oracle, monkeypatch):
     variants = [{}, {"CLOTHGPU_INCREMENTAL": "0"}, {"CLOTHGPU_FUSED_TRAVERSAL": "0"}, {"CLOTHGPU_TRISOLVE": "levels"},
                 {"CLOTHGPU_IMP_THREADS": "64"}, {"CLOTHGPU_IMP_FAST": "0"}, {"CLOTHGPU_QUERY_TRAVERSAL": "0"},
                 {"CLOTHGPU_INC_REFIT": "0"}, {"CLOTHGPU_IMP_LANES": "1", "CLOTHGPU_IMP_SLEEP": "0"},
-                {"CLOTHGPU_CANON_SMALL": "0"}, {"CLOTHGPU_QUERY_CAP": "2"}, {"CLOTHGPU_RIZ_FUSED": "0"}]
+                {"CLOTHGPU_CANON_SMALL": "0"}, {"CLOTHGPU_QUERY_CAP": "2"}, {"CLOTHGPU_RIZ_FUSED": "0"},
+                {"CLOTHGPU_SLIM_FRONTIER": "0"}]
     results = []
     for env in variants:
         for k in ("CLOTHGPU_INCREMENTAL", "CLOTHGPU_FUSED_TRAVERSAL", "CLOTHGPU_TRISOLVE", "CLOTHGPU_IMP_THREADS",
                   "CLOTHGPU_IMP_FAST", "CLOTHGPU_QUERY_TRAVERSAL", "CLOTHGPU_INC_REFIT", "CLOTHGPU_IMP_LANES",
                   "CLOTHGPU_IMP_SLEEP", "CLOTHGPU_CANON_SMALL", "CLOTHGPU_QUERY_CAP",
-                  "CLOTHGPU_RIZ_FUSED"):
+                  "CLOTHGPU_RIZ_FUSED", "CLOTHGPU_SLIM_FRONTIER"):
             monkeypatch.delenv(k, raising=False)
         for k, val in env.items():
             monkeypatch.setenv(k, val)
