@@ -17,6 +17,7 @@
 // ascending vertex id; a stable sort by zone label lays the zones out as segments in that order and each zone is
 // reduced sequentially, so the sums are bit-identical too.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_segmented_radix_sort.cuh>
 
 #include <climits>
 #include <cstdio>
@@ -371,6 +372,15 @@ __global__ void k_imp_pairs(long long cap_elem, long long cap4, const int* __res
     vals_all[(size_t)s * cap4 + i] = i;
   }
 }
+// segment offsets of the scenes' (vertex, element) slices for the segmented sort; inactive scenes get empty segments
+__global__ void k_imp_segments(int B, long long cap4, const int* __restrict__ cnt, int* __restrict__ seg) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= B) return;
+  const int* c = cnt + s * NCNT;
+  const int n4 = c[CNT_ACTIVE] ? c[CNT_ELEM] * 4 : 0;
+  seg[s] = (int)(s * cap4);
+  seg[B + s] = (int)(s * cap4) + n4;
+}
 // predecessor of (element, corner): the previous element touching the same vertex and the corner the vertex has
 // there, as element * 4 + corner, or -1
 __global__ void k_imp_pred(long long cap_elem, long long cap4, const unsigned* __restrict__ keys_all,
@@ -590,14 +600,28 @@ int launch_impulse(Ctx* c, const double* xyz, double* uvw, double delta, double 
       dim3 g(std::min(div_up((int)cap4, 256), 148 * 4), c->B);
       k_imp_pairs<<<g, 256, 0, KS(c, "k_imp_pairs")>>>(c->cap_elem, cap4, c->elems, keys, c->sort_vals, c->cnt);
       CG_LAUNCH_CHECK(c);
-      for (int s = 0; s < c->B; s++) {
-        if (!c->h_cnt[s * NCNT + CNT_ACTIVE]) continue;
-        const int n4 = c->h_cnt[s * NCNT + CNT_ELEM] * 4;
-        if (n4 == 0) continue;
-        size_t tbs = tb;
-        CG_CUDA(cub::DeviceRadixSort::SortPairs(c->scratch, tbs, keys + s * cap4, keys2 + s * cap4, c->sort_vals + s * cap4,
-                                                c->sort_vals2 + s * cap4, n4, 0, end_bit, c->stream));
+      if (c->B >= 4) {
+        // batches: one segmented sort (segment = scene) instead of a device-wide sort per scene
+        int* seg = c->imp_level;  // 2 B ints of scratch: begin / end offsets of the scenes' slices
+        k_imp_segments<<<div_up(c->B, 128), 128, 0, KS(c, "k_imp_segments")>>>(c->B, cap4, c->cnt, seg);
+        CG_LAUNCH_CHECK(c);
+        size_t tbs = 0;
+        CG_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tbs, keys, keys2, c->sort_vals, c->sort_vals2, (int)(cap4 * c->B), c->B,
+                                                         seg, seg + c->B, 0, end_bit, c->stream));
+        CG_CHECK(ensure_scratch(c, tbs));
+        CG_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(c->scratch, tbs, keys, keys2, c->sort_vals, c->sort_vals2, (int)(cap4 * c->B),
+                                                         c->B, seg, seg + c->B, 0, end_bit, c->stream));
         c->launches += 3;
+      } else {
+        for (int s = 0; s < c->B; s++) {
+          if (!c->h_cnt[s * NCNT + CNT_ACTIVE]) continue;
+          const int n4 = c->h_cnt[s * NCNT + CNT_ELEM] * 4;
+          if (n4 == 0) continue;
+          size_t tbs = tb;
+          CG_CUDA(cub::DeviceRadixSort::SortPairs(c->scratch, tbs, keys + s * cap4, keys2 + s * cap4, c->sort_vals + s * cap4,
+                                                  c->sort_vals2 + s * cap4, n4, 0, end_bit, c->stream));
+          c->launches += 3;
+        }
       }
       k_imp_pred<<<g, 256, 0, KS(c, "k_imp_pred")>>>(c->cap_elem, cap4, keys2, c->sort_vals2, c->imp_pred, c->cnt);
       CG_LAUNCH_CHECK(c);
