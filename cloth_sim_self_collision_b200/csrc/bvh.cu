@@ -841,25 +841,29 @@ __global__ void k_compact_elems(int n, const RawElem* __restrict__ raw, const in
 // library merge sort, a flag kernel, a library scan and a compaction kernel per scene.  The sorted list is written
 // back (it is the "previous" list of the next incremental pass).  Scenes with more than CANON_SMALL raw elements are
 // left to the library path.
-enum { CANON_SMALL = 2048, CANON_T = 1024 };  // (a 4096-record list takes 176 us here: no faster than the library path)
-__global__ void __launch_bounds__(CANON_T) k_canon_small(int npow2, long long cap_raw, long long cap_elem, RawElem* __restrict__ raw_all,
+enum { CANON_SMALL = 2048, CANON_BIG = 32768, CANON_T = 1024 };  // (a 4096-record list takes 176 us here: no faster than the library path)
+// In batches (limit > CANON_SMALL) lists of up to `limit` elements are sorted by the same CTA in place in global
+// memory: slower per scene than the library sort, but all scenes run at once instead of eight launches per scene.
+__global__ void __launch_bounds__(CANON_T) k_canon_small(int limit, long long cap_raw, long long cap_elem, RawElem* __restrict__ raw_all,
                                                           int* __restrict__ elems_all, int* cnt) {
   extern __shared__ __align__(16) unsigned char canon_sm[];
-  RawElem* sm = reinterpret_cast<RawElem*>(canon_sm);
   __shared__ int wsum[CANON_T / 32];
   __shared__ int carry;
   const int s = blockIdx.x;
   int* c = cnt + s * NCNT;
   if (!c[CNT_ACTIVE]) return;
   const int n = c[CNT_RAW];
-  if (n > CANON_SMALL || n > npow2) return;  // the library path handles this scene
+  if (n > limit) return;  // the library path handles this scene
   if (n == 0) { if (threadIdx.x == 0) c[CNT_ELEM] = 0; return; }
   RawElem* raw = raw_all + (size_t)s * cap_raw;
   int* elems = elems_all + (size_t)s * cap_elem * 5;
   int N = 1;
   while (N < n) N <<= 1;
+  const bool in_smem = N <= CANON_SMALL;
+  if (!in_smem && N > cap_raw) return;  // (no room for the padding: library path; the host applies the same rule)
+  RawElem* sm = in_smem ? reinterpret_cast<RawElem*>(canon_sm) : raw;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    if (i < n) sm[i] = raw[i];
+    if (i < n) { if (in_smem) sm[i] = raw[i]; }
     else { RawElem r; r.n[0] = r.n[1] = r.n[2] = r.n[3] = INT_MAX; r.pre = 0xffffffffu; r.slot = 0xffffffffu; r.path_hi = ~0ULL; r.path_lo = ~0ULL; sm[i] = r; }
   }
   __syncthreads();
@@ -877,7 +881,8 @@ __global__ void __launch_bounds__(CANON_T) k_canon_small(int npow2, long long ca
       __syncthreads();
     }
   }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) raw[i] = sm[i];
+  if (in_smem)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) raw[i] = sm[i];
   // first record of every key -> compact (std::set keeps the first inserted of equal keys: smallest DFS rank)
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
@@ -1078,12 +1083,14 @@ int run_contacts(Ctx* c, const double* xyz, const double* uvw, double dt, double
     // small raw lists (most incremental passes) are sorted / compacted right away, one launch for all scenes, before
     // the counters come back: such a pass costs one host round trip, not two.  The kernel skips scenes whose list is
     // longer than CANON_SMALL; those go through the library sort below.
+    const int canon_limit = !c->canon_small ? -1 : (c->B >= 4 ? (int)std::min<long long>(CANON_BIG, c->cap_raw / 2) : CANON_SMALL);
     if (c->canon_small) {
       const int smem = CANON_SMALL * (int)sizeof(RawElem);
       CG_CUDA(cudaFuncSetAttribute(k_canon_small, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(smem, 48 * 1024)));
-      k_canon_small<<<c->B, CANON_T, smem, KS(c, "k_canon_small")>>>(CANON_SMALL, c->cap_raw, c->cap_elem, c->raw, c->elems, c->cnt);
+      k_canon_small<<<c->B, CANON_T, smem, KS(c, "k_canon_small")>>>(canon_limit, c->cap_raw, c->cap_elem, c->raw, c->elems, c->cnt);
       CG_LAUNCH_CHECK(c);
     }
+    c->canon_limit = canon_limit;
     CG_CHECK(fetch_counters(c));
     phase_end(c, 4);
     int bits = 0;
@@ -1098,7 +1105,7 @@ int run_contacts(Ctx* c, const double* xyz, const double* uvw, double dt, double
     for (int s = 0; s < c->B; s++) {
       if (!c->h_cnt[s * NCNT + CNT_ACTIVE]) continue;
       const int nraw = c->h_cnt[s * NCNT + CNT_RAW];
-      if (c->canon_small && nraw <= CANON_SMALL) continue;
+      if (nraw <= c->canon_limit) continue;
       CG_CHECK(canonical_set(c, s, nraw));
       any_large = true;
     }

@@ -192,6 +192,7 @@ struct Ctx {
   bool riz_fused = true;                // CLOTHGPU_RIZ_FUSED=0: impact zones applied scene by scene through a library sort of all vertices
   bool rank_check = false;              // CLOTHGPU_RANK_CHECK=1: k_narrow cross-checks pair_rank against the ranks the frontier traversal carries
   int query_cap = 256;                  // CLOTHGPU_QUERY_CAP: per-leaf frontier capacity of k_query (tests force the overflow path)
+  int canon_limit = -1;                 // raw-list length up to which the last pass used k_canon_small
   bool canon_small = true;              // CLOTHGPU_CANON_SMALL=0: every raw list goes through the library sort
   bool query_trav = true;               // CLOTHGPU_QUERY_TRAVERSAL=0: incremental passes use the frontier traversal
   bool incremental_ccd = true;  // CLOTHGPU_INCREMENTAL=0 re-runs every pass in full
