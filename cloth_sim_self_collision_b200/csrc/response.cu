@@ -600,7 +600,7 @@ int launch_impulse(Ctx* c, const double* xyz, double* uvw, double delta, double 
       dim3 g(std::min(div_up((int)cap4, 256), 148 * 4), c->B);
       k_imp_pairs<<<g, 256, 0, KS(c, "k_imp_pairs")>>>(c->cap_elem, cap4, c->elems, keys, c->sort_vals, c->cnt);
       CG_LAUNCH_CHECK(c);
-      if (c->B >= 4) {
+      if (c->B >= 4 && cap4 * c->B < (1LL << 31)) {
         // batches: one segmented sort (segment = scene) instead of a device-wide sort per scene
         int* seg = c->imp_level;  // 2 B ints of scratch: begin / end offsets of the scenes' slices
         k_imp_segments<<<div_up(c->B, 128), 128, 0, KS(c, "k_imp_segments")>>>(c->B, cap4, c->cnt, seg);
