@@ -6,15 +6,21 @@
 //
 // Design (the reference recurses depth first on one core):
 //  * refit: one thread per leaf computes its box and climbs; the second arrival at a parent merges the two
-//    children (atomic ticket).  min/max only, so the result is order independent and bit-exact.
-//  * traversal: breadth first over a frontier of node pairs.  It starts from the (child0, child1) pair of EVERY
-//    internal node (the self() calls of bvh_aabb.cpp:540-557) and expands one tree level per launch; surviving pairs
-//    are pushed with warp-aggregated atomics.  The set of leaf pairs reached is the same as the depth-first walk's.
-//  * every frontier entry carries its position in the reference's depth-first order (preorder rank of the self()
-//    node + the child choices of the pair recursion, 2 bits per descent).  std::set keeps the FIRST inserted of two
-//    elements with equal keys and its comparison ignores is_fv (bvh_aabb.h:96-102), so when a face-vertex and an
-//    edge-edge element share a 4-tuple the winner depends on visiting order; sorting raw elements by
-//    (key, DFS rank) and keeping the first of each key reproduces that bit for bit.
+//    children (atomic ticket).  min/max only, so the result is order independent and bit-exact.  Incremental CCD
+//    passes (positions fixed, few velocities changed) rebuild only the dirty leaves and their ancestors
+//    (k_refit_mark / k_refit_inc).
+//  * traversal, full passes: breadth first over a frontier of node pairs.  It starts from the (child0, child1) pair of
+//    EVERY internal node (the self() calls of bvh_aabb.cpp:540-557) and expands one tree level per launch; surviving
+//    pairs are pushed with warp-aggregated atomics.  The set of leaf pairs reached is the same as the depth-first
+//    walk's.  Incremental passes: one warp per dirty leaf queries the tree for the leaves its box meets (k_query).
+//  * std::set keeps the FIRST inserted of two elements with equal keys and its comparison ignores is_fv
+//    (bvh_aabb.h:96-102), so when a face-vertex and an edge-edge element share a 4-tuple the winner depends on the
+//    visiting order of the reference's depth-first walk.  That order is a function of the two leaves alone: preorder
+//    rank of their lowest common ancestor (the self() node) + the child choices of the pair recursion, 2 bits per
+//    descent.  It is rebuilt from the per-node root paths for narrow-phase hits (pair_rank) -- frontier and leaf
+//    entries are just the two node ids -- or carried along in 32-byte entries (CLOTHGPU_SLIM_FRONTIER=0, the
+//    cooperative kernel, the rank cross-check); sorting raw elements by (key, DFS rank) and keeping the first of each
+//    key reproduces the set bit for bit.
 #include <cub/device/device_merge_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
