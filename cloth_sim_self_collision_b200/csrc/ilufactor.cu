@@ -4,17 +4,19 @@
 //
 // Row i of the factorisation needs the finished upper parts U'_k = D_k^-1 U_k of its lower neighbours k, so the
 // rows form the same dependency wavefront as the forward substitution (1021 levels on a 256^2 grid).  The kernel
-// reuses the forward sweep's strips and micro-steps (trisolve.cu): one CTA per strip, <= 10 rows per micro-step,
-// three lanes per row -- lane r owns block-row r of every 3x3 block of its matrix row, so the update
-// A_ij -= A_ik U'_kj needs no cross-lane traffic.  Per micro-step
+// uses the forward sweep's strip / micro-step scheme (trisolve.cu; a single scene takes narrower strips): one CTA per
+// strip, <= 10 rows per micro-step, nine lanes per row -- lane (r, c) owns entry (r, c) of every 3x3 block of its
+// matrix row, so the update A_ij -= A_ik U'_kj needs no cross-lane traffic.  Per micro-step
 //   * the row's blocks arrive by one TMA bulk copy per stage, packed by k_pack_rows into a lane-major layout
-//     ([block][column][lane], 8-byte lane stride): whatever block each row group addresses, the 16 lanes of a
+//     ([block][96 lane slots], 8-byte lane stride): whatever block each row group addresses, the 16 lanes of a
 //     half-warp hit 16 distinct bank pairs, so the dynamic per-row block indices cost no bank conflicts;
-//   * the update list (ik, kj, ij) in the reference's order is applied in shared memory;
+//   * the update list (ik, kj, ij) in the reference's order is applied in shared memory, one lower block k at a time;
 //   * operands U'_k produced by this strip within the last FC_H micro-steps are read from a shared-memory ring;
 //     older ones and those of other strips are fetched by an import lane with TMA bulk copies from a padded
 //     global copy of the upper parts ("uexp"), gated by the producer strip's progress counter;
-//   * D_i is inverted by cofactors, U'_i = D_i^-1 U_i is written to the ring, to the ILU arrays and to uexp.
+//   * D_i is inverted by cofactors (every lane its own entry), U'_i = D_i^-1 U_i goes to the ring;
+//   * drain warps copy the finished micro-step (L, D^-1, U') from shared memory to the ILU arrays and to uexp and
+//     publish the strip's progress: the compute warps never touch global memory.
 // Arithmetic per entry is the reference's (same operand order, -fmad=false): results are bit identical.
 #include <algorithm>
 #include <cstdio>

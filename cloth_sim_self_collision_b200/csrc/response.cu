@@ -6,10 +6,11 @@
 // Impulses: the reference applies the elements one after the other in std::set order and every element reads the
 // velocities written by the earlier ones (Gauss-Seidel).  Two elements only interact through a shared vertex, so
 // the serial order is equivalent to any order that keeps, for every vertex, the relative order of the elements
-// touching it.  We build that dependency DAG (predecessor of element k on each of its 4 vertices = the previous
-// element touching the vertex, found with one stable radix sort of (vertex, element) pairs), level it
-// (level = 1 + max level of the predecessors) and run level after level inside one CTA per scene: elements of a
-// level touch disjoint vertices.  Bit-identical to the serial loop.
+// touching it.  The predecessor of element k on each of its 4 vertices (the previous element touching the vertex) comes
+// from one stable radix sort of (vertex, element * 4 + corner) pairs; k_imp_flow (the default) starts an element as
+// soon as its predecessors have finished, k_imp_run levels the dependency DAG and runs level after level
+// (CLOTHGPU_IMPULSE=levels).  The divisions / square roots on the dependency chain use the certified fast forms of
+// imp_fast.cuh.  Bit-identical to the serial loop.
 //
 // Impact zones: the reference's zone list equals the connected components of the member vertices under
 // "same contact element" and "mesh-adjacent and both members" (order independent, verified against the
